@@ -1,0 +1,75 @@
+"""Seeded synthetic grids and star catalogues.
+
+Used by the tests, ``bench.py`` and ``__graft_entry__.smoke()``; there is no network, so the
+reference's real grids (``grid_mist_v9.h5`` ...) cannot be fetched.  The grid has the reference's
+format: float32 ``(Nmodel, Nfilt, 3)`` holding ``(mag0 @ 1 kpc, R0, dR/dRv)`` per band
+(produced at brutus/seds.py:828-832, consumed at brutus/utils.py:293-298).
+"""
+import numpy as np
+
+__all__ = ["make_grid", "make_stars", "CONFIGS"]
+
+# BASELINE.json configs (index -> workload shape)
+CONFIGS = {
+    1: dict(nmodel=10_000, nfilt=5, nstar=1, avlim=(0., 20.), av_max=2.0, dropout=0.0),
+    2: dict(nmodel=1_000_000, nfilt=8, nstar=1_000, avlim=(0., 20.), av_max=2.0, dropout=0.0),
+    3: dict(nmodel=3_000_000, nfilt=12, nstar=100_000, avlim=(0., 6.), av_max=6.0, dropout=0.1),
+    5: dict(nmodel=3_000_000, nfilt=8, nstar=1_000_000, avlim=(0., 20.), av_max=2.0, dropout=0.0),
+}
+
+
+def make_grid(nmodel, nfilt, seed=1000):
+    """Mock SED grid: absolute magnitude ~U(-2,12), a one-parameter colour family plus 0.03 mag
+    scatter, reddening vector falling from 1.2 to 0.2 across the bands, small dR/dRv.
+    Also returns labels (structured: 'Mr', 'feh') like ``load_models`` does
+    (brutus/utils.py:608-609)."""
+    rs = np.random.RandomState(seed)
+    mabs = rs.uniform(-2., 12., nmodel)
+    col = rs.normal(0., 0.5, nmodel)
+    x = np.linspace(-1., 1., nfilt)
+    grid = np.empty((nmodel, nfilt, 3), dtype=np.float32)
+    chunk = 1 << 18
+    for lo in range(0, nmodel, chunk):  # chunked to bound temporaries at 3M models
+        hi = min(nmodel, lo + chunk)
+        n = hi - lo
+        grid[lo:hi, :, 0] = (mabs[lo:hi, None] + col[lo:hi, None] * x[None, :]
+                             + rs.normal(0., 0.03, (n, nfilt)))
+        grid[lo:hi, :, 1] = np.linspace(1.2, 0.2, nfilt)[None, :] + rs.normal(0., 0.01, (n, nfilt))
+        grid[lo:hi, :, 2] = (np.linspace(0.05, -0.02, nfilt)[None, :]
+                             + rs.normal(0., 0.002, (n, nfilt)))
+    labels = np.zeros(nmodel, dtype=[("Mr", "f8"), ("feh", "f8")])
+    labels["Mr"] = grid[:, min(1, nfilt - 1), 0]
+    labels["feh"] = rs.uniform(-2., 0.5, nmodel)
+    return grid, labels
+
+
+def make_stars(grid, nstar, seed=2000, av_max=2.0, dropout=0.0, par_nan_frac=0.3,
+               snr_range=(10., 100.)):
+    """Mock catalogue drawn from the grid: returns dict(flux, err, mask, parallax, parallax_err,
+    truth=(idx, av, rv, dist))."""
+    rs = np.random.RandomState(seed)
+    nmodel, nfilt, _ = grid.shape
+    idx = rs.randint(0, nmodel, nstar)
+    av = rs.uniform(0., av_max, nstar)
+    rv = np.clip(rs.normal(3.32, 0.18, nstar), 2., 5.)
+    dist = 10. ** rs.uniform(-1., 1., nstar)  # kpc
+    co = grid[idx].astype(np.float64)
+    mag = co[:, :, 0] + av[:, None] * (co[:, :, 1] + rv[:, None] * co[:, :, 2])
+    flux = 10. ** (-0.4 * mag) / dist[:, None] ** 2
+    snr = rs.uniform(snr_range[0], snr_range[1], (nstar, nfilt))
+    err = flux / snr
+    flux = flux + rs.normal(0., 1., (nstar, nfilt)) * err
+    perr = rs.uniform(0.02, 0.3, nstar)
+    par = 1. / dist + rs.normal(0., 1., nstar) * perr
+    nan = rs.uniform(size=nstar) < par_nan_frac
+    par[nan] = np.nan
+    perr[nan] = np.nan
+    mask = np.ones((nstar, nfilt), dtype=bool)
+    if dropout > 0:
+        drop = rs.uniform(size=(nstar, nfilt)) < dropout
+        # keep at least 4 bands (brutus/fitting.py:1413-1420)
+        for i in np.where((~drop).sum(axis=1) < 4)[0]:
+            drop[i] = False
+        mask &= ~drop
+    return dict(flux=flux, err=err, mask=mask, parallax=par, parallax_err=perr,
+                truth=dict(idx=idx, av=av, rv=rv, dist=dist))

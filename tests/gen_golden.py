@@ -1,0 +1,99 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (numba/NumPy) from
+/root/reference.  Run in the build container only:  python tests/gen_golden.py
+
+The fixtures pin (a) the C oracle (tests/test_oracle.py) and (b) the CUDA path (-m gpu tests).
+Inputs are regenerated from seeds by brutus_b200.mock; only the reference's outputs are stored.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import ref_import  # noqa: E402
+from brutus_b200 import mock  # noqa: E402
+
+GOLD = os.path.join(HERE, "golden")
+
+
+def toy_galprior(dist, coord, labels=None):
+    """User-supplied Galactic prior (the hook at brutus/fitting.py:870-878): volume element times
+    an exponential fall-off.  Shared with the tests via tests/golden_cases.py."""
+    return 2. * np.log(dist) - dist / 2.
+
+
+# name -> (grid kwargs, star kwargs, per-star tweaks, loglike kwargs)
+LOGLIKE_CASES = {
+    # BASELINE.json configs[0]: 1 star, 5 bands, 10k-model grid
+    "c1_plumbing": dict(grid=dict(nmodel=10_000, nfilt=5, seed=1001),
+                        stars=dict(nstar=1, seed=2001, par_nan_frac=0.0), kw={}),
+    "mixed_9band": dict(grid=dict(nmodel=2_000, nfilt=9, seed=1010),
+                        stars=dict(nstar=6, seed=2010, dropout=0.15), kw={}, negflux=[(2, 3)]),
+    "nodimprior": dict(grid=dict(nmodel=2_000, nfilt=8, seed=1011),
+                       stars=dict(nstar=3, seed=2011), kw=dict(dim_prior=False)),
+    "avlim6_rvprior": dict(grid=dict(nmodel=2_000, nfilt=12, seed=1012),
+                           stars=dict(nstar=3, seed=2012, av_max=6.0, dropout=0.1),
+                           kw=dict(avlim=(0., 6.), rv_gauss=(3.1, 0.3), av_gauss=(1.0, 2.0))),
+    "loose_tol": dict(grid=dict(nmodel=2_000, nfilt=6, seed=1013),
+                      stars=dict(nstar=3, seed=2013, snr_range=(5., 20.)),
+                      kw=dict(ltol=1e-3, ltol_subthresh=5e-2, init_thresh=1e-4)),
+}
+
+
+def build_case(name):
+    spec = LOGLIKE_CASES[name]
+    grid, labels = mock.make_grid(**spec["grid"])
+    st = mock.make_stars(grid, **spec["stars"])
+    for (i, j) in spec.get("negflux", []):
+        st["flux"][i, j] = -0.1 * abs(st["flux"][i, j])
+    return grid, labels, st, spec["kw"]
+
+
+def gen_loglike(fit):
+    for name in LOGLIKE_CASES:
+        grid, labels, st, kw = build_case(name)
+        gF = np.array(grid, order="F")  # as _fit does, brutus/fitting.py:1964
+        out = {}
+        for i in range(len(st["flux"])):
+            m = st["mask"][i].copy()
+            r = fit.loglike(st["flux"][i], st["err"][i], m, gF, return_vals=True,
+                            parallax=st["parallax"][i], parallax_err=st["parallax_err"][i], **kw)
+            for key, val in zip(("lnl", "ndim", "chi2", "scale", "av", "rv", "icov"), r):
+                out["%s_%d" % (key, i)] = np.asarray(val)
+            out["mask_%d" % i] = m
+        np.savez_compressed(os.path.join(GOLD, "loglike_%s.npz" % name), **out)
+        print("wrote", name)
+
+
+FIT_CASE = dict(grid=dict(nmodel=3_000, nfilt=8, seed=1020), stars=dict(nstar=5, seed=2020),
+                Nmc_prior=20, Ndraws=40, rseed=77)
+
+
+def gen_fit(fit):
+    grid, labels, st = None, None, None
+    grid, labels = mock.make_grid(**FIT_CASE["grid"])
+    st = mock.make_stars(grid, **FIT_CASE["stars"])
+    lmask = np.ones(1, dtype=[("Mr", bool), ("feh", bool)])
+    bf = fit.BruteForce(grid, labels, lmask)
+    lnprior = -0.1 * (labels["Mr"] - 5.) ** 2
+    out = {}
+    names = ("sidxs", "scales", "avs", "rvs", "cov_sar", "Ndim", "lnprob", "levid", "chi2min",
+             "dists", "reds", "dreds", "logwts")
+    gen = bf._fit(st["flux"], st["err"], st["mask"].copy(), parallax=st["parallax"],
+                  parallax_err=st["parallax_err"], Nmc_prior=FIT_CASE["Nmc_prior"],
+                  lnprior=lnprior, Ndraws=FIT_CASE["Ndraws"], lngalprior=toy_galprior,
+                  dustfile=None, data_coords=np.zeros((len(st["flux"]), 2)),
+                  rstate=np.random.RandomState(FIT_CASE["rseed"]))
+    for i, res in enumerate(gen):
+        for key, val in zip(names, res):
+            out["%s_%d" % (key, i)] = np.asarray(val)
+    np.savez_compressed(os.path.join(GOLD, "fit_generator.npz"), **out)
+    print("wrote fit_generator")
+
+
+if __name__ == "__main__":
+    fit = ref_import.import_reference()
+    os.makedirs(GOLD, exist_ok=True)
+    gen_loglike(fit)
+    gen_fit(fit)
