@@ -1,0 +1,232 @@
+"""ctypes binding of libbrutus_b200.so (C ABI: include/brutus_b200.h).
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is present, every
+compute entry point raises :class:`BrutusCudaError`.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbrutus_b200.so")
+
+BF_OK, BF_E_INVALID, BF_E_CUDA, BF_E_NOGRID, BF_E_CAPACITY, BF_E_THRESH, BF_E_NOMEM = 0, -1, -2, -3, -4, -5, -6
+LAYOUT_C, LAYOUT_F = 0, 1
+PRECISION_F32, PRECISION_F64 = 0, 1
+MAX_FILT = 16
+
+# every symbol include/brutus_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = ("bf_default_options", "bf_create", "bf_destroy", "bf_last_error", "bf_set_grid",
+           "bf_set_grid_device", "bf_set_labels", "bf_loglike_full", "bf_sweep_batch",
+           "bf_get_stats", "bf_device_count", "bf_version")
+
+
+class BrutusCudaError(RuntimeError):
+    pass
+
+
+class Options(C.Structure):
+    _fields_ = [("avlim", C.c_double * 2), ("av_gauss", C.c_double * 2), ("rvlim", C.c_double * 2),
+                ("rv_gauss", C.c_double * 2), ("ltol", C.c_double), ("ltol_subthresh", C.c_double),
+                ("init_thresh", C.c_double), ("wt_thresh", C.c_double), ("dim_prior", C.c_int32),
+                ("max_iter", C.c_int32), ("apply_parallax_clip", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("ms_device", C.c_double), ("ms_magfit", C.c_double), ("ms_flux", C.c_double),
+                ("ms_select", C.c_double), ("kernel_launches", C.c_int64),
+                ("magfit_launches", C.c_int64), ("resweeps", C.c_int64), ("survivors", C.c_int64),
+                ("selected", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (building is __graft_entry__.build()/brutus_b200.build's job)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BrutusCudaError("libbrutus_b200.so not built (run `python -m brutus_b200.build`); "
+                              "brutus_b200 has no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    vp, dp, fp = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_float)
+    u8p, i32p, i64p = C.POINTER(C.c_uint8), C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    op = C.POINTER(Options)
+    lib.bf_default_options.argtypes = [op]
+    lib.bf_default_options.restype = None
+    lib.bf_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
+    lib.bf_destroy.argtypes = [vp]
+    lib.bf_last_error.argtypes = [vp]
+    lib.bf_last_error.restype = C.c_char_p
+    lib.bf_set_grid.argtypes = [vp, fp, C.c_int64, C.c_int32, C.c_int32]
+    lib.bf_set_grid_device.argtypes = [vp, vp, C.c_int64, C.c_int32, C.c_int32]
+    lib.bf_set_labels.argtypes = [vp, dp, C.c_int32]
+    lib.bf_loglike_full.argtypes = [vp, dp, dp, u8p, C.c_double, C.c_double, op,
+                                    dp, dp, dp, dp, dp, dp, u8p, i64p]
+    lib.bf_sweep_batch.argtypes = [vp, C.c_int64, dp, dp, u8p, dp, dp, dp, dp, op,
+                                   i32p, i32p, i64p, dp, i64p, C.c_int64, i64p,
+                                   i32p, dp, dp, dp, dp, dp, dp]
+    lib.bf_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.bf_device_count.restype = C.c_int
+    lib.bf_version.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def _ptr(a, t):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+def make_options(avlim=(0., 20.), av_gauss=(0., 1e6), rvlim=(1., 8.), rv_gauss=(3.32, 0.18),
+                 dim_prior=True, ltol=3e-2, ltol_subthresh=1e-2, init_thresh=5e-3, wt_thresh=1e-3,
+                 max_iter=0, apply_parallax_clip=True):
+    if av_gauss is None:  # brutus/fitting.py:695-696
+        av_gauss = (0., 1e6)
+    o = Options()
+    o.avlim[:] = [float(x) for x in avlim]
+    o.av_gauss[:] = [float(x) for x in av_gauss]
+    o.rvlim[:] = [float(x) for x in rvlim]
+    o.rv_gauss[:] = [float(x) for x in rv_gauss]
+    o.ltol, o.ltol_subthresh, o.init_thresh = float(ltol), float(ltol_subthresh), float(init_thresh)
+    o.wt_thresh = float(wt_thresh)
+    o.dim_prior, o.max_iter = int(bool(dim_prior)), int(max_iter)
+    o.apply_parallax_clip = int(bool(apply_parallax_clip))
+    return o
+
+
+class Handle:
+    """One sweep engine bound to one CUDA device (not re-entrant)."""
+
+    def __init__(self, device=0, precision="f32"):
+        self._lib = load()
+        self._h = C.c_void_p()
+        prec = {"f32": PRECISION_F32, "f64": PRECISION_F64}[precision]
+        rc = self._lib.bf_create(int(device), prec, C.byref(self._h))
+        if rc != BF_OK:
+            raise BrutusCudaError(self._lib.bf_last_error(None).decode())
+        self.precision = precision
+        self.device = int(device)
+        self.nmodel = 0
+        self.nfilt = 0
+        self.nlabel = 0
+        self._grid_token = None
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.bf_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != BF_OK:
+            msg = self._lib.bf_last_error(self._h).decode()
+            if rc in (BF_E_THRESH, BF_E_INVALID):
+                raise ValueError(msg)
+            raise BrutusCudaError("rc=%d: %s" % (rc, msg))
+
+    def set_grid(self, mag_coeffs):
+        """Stage a float32 (Nmodel, Nfilt, 3) grid (C or Fortran order, no copy for either)."""
+        a = np.asarray(mag_coeffs)
+        if a.ndim != 3 or a.shape[2] != 3:
+            raise ValueError("mag_coeffs must have shape (Nmodel, Nfilt, 3)")
+        if a.dtype != np.float32:
+            a = a.astype(np.float32)
+        if a.flags.c_contiguous:
+            layout = LAYOUT_C
+        elif a.flags.f_contiguous:
+            layout = LAYOUT_F
+        else:
+            a, layout = np.ascontiguousarray(a), LAYOUT_C
+        self._check(self._lib.bf_set_grid(self._h, _ptr(a, C.c_float), a.shape[0], a.shape[1], layout))
+        self.nmodel, self.nfilt = a.shape[0], a.shape[1]
+        self.nlabel = 0
+
+    def set_grid_device(self, dev_ptr, nmodel, nfilt, layout=LAYOUT_C):
+        self._check(self._lib.bf_set_grid_device(self._h, C.c_void_p(int(dev_ptr)), int(nmodel),
+                                                 int(nfilt), int(layout)))
+        self.nmodel, self.nfilt = int(nmodel), int(nfilt)
+        self.nlabel = 0
+
+    def set_labels(self, cols):
+        """cols: (nlabel, Nmodel) float64."""
+        a = np.ascontiguousarray(cols, dtype=np.float64)
+        if a.ndim != 2 or a.shape[1] != self.nmodel:
+            raise ValueError("labels must have shape (nlabel, Nmodel)")
+        self._check(self._lib.bf_set_labels(self._h, _ptr(a, C.c_double), a.shape[0]))
+        self.nlabel = a.shape[0]
+
+    def stats(self):
+        s = Stats()
+        self._lib.bf_get_stats(self._h, C.byref(s))
+        return s.as_dict()
+
+    def loglike_full(self, flux, err, mask, parallax, parallax_err, opts, want_icov=True):
+        n = self.nmodel
+        f = np.ascontiguousarray(flux, dtype=np.float64)
+        e = np.ascontiguousarray(err, dtype=np.float64)
+        m = np.ascontiguousarray(mask).astype(np.uint8)
+        if f.shape != (self.nfilt,) or e.shape != (self.nfilt,) or m.shape != (self.nfilt,):
+            raise ValueError("data, data_err and data_mask must have shape (Nfilt,)")
+        lnl, chi2, sc, av, rv = (np.empty(n) for _ in range(5))
+        icov = np.empty((n, 3, 3)) if want_icov else None
+        mclean = np.zeros(self.nfilt, dtype=np.uint8)
+        diag = np.zeros(4, dtype=np.int64)
+        self._check(self._lib.bf_loglike_full(
+            self._h, _ptr(f, C.c_double), _ptr(e, C.c_double), _ptr(m, C.c_uint8), float(parallax),
+            float(parallax_err), C.byref(opts), _ptr(lnl, C.c_double), _ptr(chi2, C.c_double),
+            _ptr(sc, C.c_double), _ptr(av, C.c_double), _ptr(rv, C.c_double), _ptr(icov, C.c_double),
+            _ptr(mclean, C.c_uint8), _ptr(diag, C.c_int64)))
+        return lnl, chi2, sc, av, rv, icov, mclean.astype(bool), diag
+
+    def sweep_batch(self, flux, err, mask, parallax=None, parallax_err=None, ext_mean=None,
+                    ext_std=None, opts=None, want_icov=True, capacity=None):
+        """B2 entry point; returns a dict of per-star arrays and CSR-compacted records."""
+        f = np.ascontiguousarray(flux, dtype=np.float64)
+        e = np.ascontiguousarray(err, dtype=np.float64)
+        m = np.ascontiguousarray(mask).astype(np.uint8)
+        ns = f.shape[0]
+        if f.ndim != 2 or f.shape[1] != self.nfilt or e.shape != f.shape or m.shape != f.shape:
+            raise ValueError("data, data_err and data_mask must have shape (Ndata, Nfilt)")
+        par = None if parallax is None else np.ascontiguousarray(parallax, dtype=np.float64)
+        perr = None if parallax_err is None else np.ascontiguousarray(parallax_err, dtype=np.float64)
+        em = es = None
+        if ext_mean is not None and self.nlabel:
+            em = np.ascontiguousarray(ext_mean, dtype=np.float64)
+            es = np.ascontiguousarray(ext_std, dtype=np.float64)
+        if opts is None:
+            opts = make_options()
+        ndim = np.zeros(ns, dtype=np.int32)
+        nit = np.zeros((ns, 2), dtype=np.int32)
+        nsurv = np.zeros(ns, dtype=np.int64)
+        mx = np.zeros(ns)
+        offsets = np.zeros(ns + 1, dtype=np.int64)
+        cap = int(capacity) if capacity is not None else max(1024, 4096 * ns)
+        while True:
+            idx = np.empty(cap, dtype=np.int32)
+            lnl, chi2, sc, av, rv = (np.empty(cap) for _ in range(5))
+            icov = np.empty((cap, 6)) if want_icov else None
+            need = C.c_int64(0)
+            rc = self._lib.bf_sweep_batch(
+                self._h, ns, _ptr(f, C.c_double), _ptr(e, C.c_double), _ptr(m, C.c_uint8),
+                _ptr(par, C.c_double), _ptr(perr, C.c_double), _ptr(em, C.c_double),
+                _ptr(es, C.c_double), C.byref(opts), _ptr(ndim, C.c_int32), _ptr(nit, C.c_int32),
+                _ptr(nsurv, C.c_int64), _ptr(mx, C.c_double), _ptr(offsets, C.c_int64), cap,
+                C.byref(need), _ptr(idx, C.c_int32), _ptr(lnl, C.c_double), _ptr(chi2, C.c_double),
+                _ptr(sc, C.c_double), _ptr(av, C.c_double), _ptr(rv, C.c_double),
+                _ptr(icov, C.c_double))
+            if rc == BF_E_CAPACITY:
+                cap = int(need.value)
+                continue
+            self._check(rc)
+            break
+        n = int(need.value)
+        return dict(ndim=ndim, n_iter=nit, n_surv=nsurv, max_lnprob=mx, offsets=offsets,
+                    model_idx=idx[:n], lnl=lnl[:n], chi2=chi2[:n], scale=sc[:n], av=av[:n],
+                    rv=rv[:n], icov6=None if icov is None else icov[:n])

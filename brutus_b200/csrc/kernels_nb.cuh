@@ -1,0 +1,409 @@
+// kernels_nb.cuh -- the band-count-templated kernels of the likelihood sweep.
+//
+// One thread owns one model; every sum over bands is a register accumulation (no shuffles).
+// The arithmetic is the reference's (brutus/fitting.py:34-576) rewritten in
+// per-star normalised, centred units so that float32 keeps ~1e-7 absolute accuracy on O(1) values:
+//
+//   centred magnitude residual  e'_j = e_j - c,  e_j = m_j - (mu_j + A r_j),  c = mbar - bbar_i
+//   flux ratio                  F_j / d*_j = 10^(0.4 e_j) = g_j E,  g_j = 2^(kC2 e'_j), E = 2^(kC2 c)
+//   sigma-normalised model      M_j/sigma_j = shat g_j be_j,  shat = s E,  residual t_j = al_j - shat g_j be_j
+//
+// so  scale s = (sum g be al / sum (g be)^2) / E   and   chi2 = sum t_j^2   (fitting.py:510-518, :745).
+#pragma once
+#include "common.cuh"
+
+namespace bf {
+
+// Star-independent per-model quantities, hoisted out of the star loop.
+template <typename T, int NB> struct ModelRegs {
+    T cb[NB];   // b_j - bbar, b_j = mu_j + Abar r0_j  (model magnitudes at the prior-mean reddening)
+    T r0[NB];   // R_j + Rbar D_j                      (brutus/utils.py:337-338 at rv = rv_gauss[0])
+    T D[NB];    // dR/dRv
+    T bbar;
+};
+
+template <typename T, int NB>
+__device__ __forceinline__ void load_model(const float* __restrict__ grid, int64_t npad, int64_t i,
+                                           const DevOpts<T>& o, ModelRegs<T, NB>& m) {
+    T sum = T(0);
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+        T mu = (T)__ldg(grid + (int64_t)(0 * NB + j) * npad + i);
+        T R = (T)__ldg(grid + (int64_t)(1 * NB + j) * npad + i);
+        T D = (T)__ldg(grid + (int64_t)(2 * NB + j) * npad + i);
+        m.D[j] = D;
+        m.r0[j] = fma(o.Rbar, D, R);
+        m.cb[j] = fma(o.Abar, m.r0[j], mu);
+        sum += m.cb[j];
+    }
+    m.bbar = sum * (T(1) / T(NB));
+#pragma unroll
+    for (int j = 0; j < NB; j++) m.cb[j] -= m.bbar;
+}
+
+// Result of the flux-space MLE at fixed (A, rho): brutus/fitting.py:430-576 (_get_sed_mle), normalised.
+template <typename T, int NB> struct Mle {
+    T gb[NB];     // g_j be_j
+    T shat;       // s E (after the 1e-20 floor on s)
+    T s;          // scale                                  (:516-518)
+    T E;          // 2^(kC2 c)
+    T den;        // sum (g be)^2  (s_den = E^2 den, :515)
+    T chi2;       // sum t^2                                 (:745 / :792)
+};
+
+template <typename T, int NB>
+__device__ __forceinline__ void mle_from_resid(const T (&e)[NB], T c, const T* __restrict__ srow,
+                                               Mle<T, NB>& r) {
+    T num = T(0), den = T(0);
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+        T g = Num<T>::exp2(T(kC2) * e[j]);
+        T gb = g * srow[SR_BE + j];
+        r.gb[j] = gb;
+        num = fma(gb, srow[SR_AL + j], num);
+        den = fma(gb, gb, den);
+    }
+    T E = Num<T>::exp2(T(kC2) * c);
+    T shat = Num<T>::div(num, den);
+    T s = Num<T>::div(shat, E);
+    if (s <= T(1e-20)) {  // brutus/fitting.py:517-518
+        s = T(1e-20);
+        shat = s * E;
+    }
+    T chi2 = T(0);
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+        T t = fma(-shat, r.gb[j], srow[SR_AL + j]);
+        chi2 = fma(t, t, chi2);
+    }
+    r.shat = shat; r.s = s; r.E = E; r.den = den; r.chi2 = chi2;
+}
+
+// lnl_p of the cull (brutus/fitting.py:747-756): -chi2/2 - (sqrt(s) - parallax)^2 / (2 parallax_err^2)
+template <typename T>
+__device__ __forceinline__ T cull_lnl(T chi2, T s, const T* __restrict__ srow) {
+    T dp = Num<T>::sqrt(s) - srow[SR_SC + SC_PAR];
+    return T(-0.5) * fma(dp * dp, srow[SR_SC + SC_PIVAR], chi2);
+}
+
+// =================================================================================================
+// Kernel 1: full-grid magnitude-space fit (brutus/fitting.py:728-741 -> _optimize_fit_mag :34-271,
+// then _get_sed_mle :267 and the cull statistic :745-756) for a list of stars.
+// grid = (model tiles, star chunks); each thread keeps its model in registers and loops over the
+// chunk's stars, whose rows sit in shared memory (broadcast reads).
+// The number of mag iterations applied to every model of a star is a grid-wide decision in the
+// reference (:246-263).  It is speculated here (SI_KSPEC) and verified afterwards from two plain
+// max-reductions per iteration:  "err < tol"  <=>  max{logwt_i : max(|dAv_i|,|dRv_i|) >= tol} <=
+// max logwt + ln(init_thresh).
+// =================================================================================================
+template <typename T, int NB>
+__global__ void __launch_bounds__(kTile) k_magfit(const SweepParams<T> p) {
+    using U = typename Enc<T>::U;
+    __shared__ T s_star[kStarChunk][kStarStride];
+    __shared__ int s_slot[kStarChunk];
+    __shared__ int s_kspec[kStarChunk];
+    __shared__ U s_red[kStarChunk][5];
+
+    const int first = blockIdx.y * kStarChunk;
+    const int nst = min(kStarChunk, p.nlist - first);
+    for (int t = threadIdx.x; t < nst * kStarStride; t += kTile) {
+        int s = t / kStarStride, k = t - s * kStarStride;
+        s_star[s][k] = p.stars[(int64_t)p.list[first + s] * kStarStride + k];
+    }
+    for (int t = threadIdx.x; t < nst; t += kTile) {
+        int slot = p.list[first + t];
+        s_slot[t] = slot;
+        s_kspec[t] = p.star_int[slot * SI_COUNT + SI_KSPEC];
+    }
+    for (int t = threadIdx.x; t < nst * 5; t += kTile) s_red[t / 5][t % 5] = Enc<T>::enc(Num<T>::neg_inf());
+    __syncthreads();
+
+    const int64_t i = (int64_t)blockIdx.x * kTile + threadIdx.x;  // npad is a multiple of kTile
+    const bool valid = i < p.nmodel;
+    const DevOpts<T> o = p.o;
+    ModelRegs<T, NB> m;
+    load_model<T, NB>(p.grid, p.npad, i, o, m);
+    const int lane = threadIdx.x & 31;
+
+    for (int s = 0; s < nst; s++) {
+        const T* __restrict__ srow = s_star[s];
+        const int kspec = s_kspec[s];
+        const T S = srow[SR_SC + SC_S];
+        const T c = srow[SR_SC + SC_MBAR] - m.bbar;
+        T A = o.Abar, rho = o.Rbar;
+        T e[NB], r[NB];
+        T Q = T(0), Tm = T(0), gs = T(0);
+        // brutus/fitting.py:158-164 (rp_den, srp_mix) and the initial residuals (:733)
+#pragma unroll
+        for (int j = 0; j < NB; j++) {
+            const T u = srow[SR_U + j];
+            e[j] = srow[SR_CM + j] - m.cb[j];
+            r[j] = m.r0[j];
+            T Du = m.D[j] * u;
+            Q = fma(Du, m.D[j], Q);
+            Tm += Du;
+            gs = fma(e[j], u, gs);
+        }
+        T ell = T(0), delta = T(0);
+        for (int k = 1; k <= kspec; k++) {
+            // --- solve for Av (:176-204) ---
+            T a = o.PA, b = T(0), ga = (o.Abar - A) * o.PA;
+#pragma unroll
+            for (int j = 0; j < NB; j++) {
+                T ru = r[j] * srow[SR_U + j];
+                a = fma(ru, r[j], a);
+                b += ru;
+                ga = fma(ru, e[j], ga);
+            }
+            T dA = Num<T>::div_fast(S * ga - b * gs, S * a - b * b);
+            dA = tmax(dA, o.avmin - A);
+            dA = tmin(dA, o.avmax - A);
+            A += dA;
+            // --- solve for Rv (:206-237) ---
+            T gr = T(0), gs2 = T(0);
+#pragma unroll
+            for (int j = 0; j < NB; j++) {
+                e[j] = fma(-dA, r[j], e[j]);
+                T eu = e[j] * srow[SR_U + j];
+                gs2 += eu;
+                gr = fma(eu, m.D[j], gr);
+            }
+            gr = fma(gr, A, (o.Rbar - rho) * o.PR);
+            T q = fma(Q * A, A, o.PR);
+            T tt = Tm * A;
+            T dR = Num<T>::div_fast(S * gr - tt * gs2, S * q - tt * tt);
+            dR = tmax(dR, o.rvmin - rho);
+            dR = tmin(dR, o.rvmax - rho);
+            rho += dR;
+            // --- update residuals / reddening vector, chi2 in magnitudes (:235-243) ---
+            const T AdR = A * dR;
+            T chi = T(0);
+            gs = T(0);
+#pragma unroll
+            for (int j = 0; j < NB; j++) {
+                e[j] = fma(-AdR, m.D[j], e[j]);
+                r[j] = fma(dR, m.D[j], r[j]);
+                T eu = e[j] * srow[SR_U + j];
+                gs += eu;
+                chi = fma(eu, e[j], chi);
+            }
+            // logwt uses the un-centred residual e = e' + c (reference quirk)
+            ell = T(-0.5) * (chi + c * (T(2) * gs + c * S));
+            delta = tmax(tabs(dA), tabs(dR));
+            if (k >= kspec - 1) {
+                T v1 = (valid && ell == ell) ? ell : Num<T>::neg_inf();
+                T v2 = (delta >= o.mtol) ? v1 : Num<T>::neg_inf();
+                v1 = warp_max(v1);
+                v2 = warp_max(v2);
+                if (lane == 0) {
+                    const int base = (k == kspec) ? 2 : 0;
+                    atomicMax(&s_red[s][base], Enc<T>::enc(v1));
+                    atomicMax(&s_red[s][base + 1], Enc<T>::enc(v2));
+                }
+            }
+        }
+        // --- _get_sed_mle at the fitted (Av, Rv) (:267) and the cull statistic (:745-756) ---
+        Mle<T, NB> r4;
+        mle_from_resid<T, NB>(e, c, srow, r4);
+        T lp = cull_lnl(r4.chi2, r4.s, srow);
+        {
+            T v = (valid && lp == lp) ? lp : Num<T>::neg_inf();
+            v = warp_max(v);
+            if (lane == 0) atomicMax(&s_red[s][4], Enc<T>::enc(v));
+        }
+        if (valid) {
+            const int64_t off = (int64_t)s_slot[s] * p.npad + i;
+            p.st.chi2[off] = r4.chi2;
+            p.st.scale[off] = r4.s;
+            p.st.sden[off] = r4.den * r4.E * r4.E;
+            p.st.av[off] = A;
+            p.st.rv[off] = rho;
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nst * 5; t += kTile) {
+        int s = t / 5, k = t % 5;
+        const int map[5] = {RED_L0, RED_B0, RED_L1, RED_B1, RED_LP};
+        atomicMax(&p.red[(int64_t)s_slot[s] * kNumRed + map[k]], s_red[s][k]);
+    }
+}
+
+// residuals at an arbitrary (A, rho): e'_j = cm_j - cb_j - (A r_j - Abar r0_j), r_j = r0_j + (rho - Rbar) D_j
+template <typename T, int NB>
+__device__ __forceinline__ void resid_at(const ModelRegs<T, NB>& m, const DevOpts<T>& o,
+                                         const T* __restrict__ srow, T A, T rho, T (&e)[NB], T (&r)[NB]) {
+    const T drho = rho - o.Rbar;
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+        r[j] = fma(drho, m.D[j], m.r0[j]);
+        T red = fma(A, r[j], -o.Abar * m.r0[j]);
+        e[j] = (srow[SR_CM + j] - m.cb[j]) - red;
+    }
+}
+
+// =================================================================================================
+// Kernel 2: flux-space refinement of the survivors (brutus/fitting.py:778-803 with
+// _optimize_fit_flux :274-427).  One thread per survivor record; `nit` iterations are executed in
+// registers, and the convergence reductions are recorded for the last one:
+//   "lerr <= ltol"  <=>  max{lnl_new_i : |lnl_new_i - lnl_old_i| > ltol} <= max lnl_new + ln(ltol_subthresh)
+// =================================================================================================
+template <typename T, int NB>
+__global__ void __launch_bounds__(kTile) k_flux(const FluxParams<T> p) {
+    const int64_t q = (int64_t)blockIdx.x * kTile + threadIdx.x;
+    const bool inrange = q < p.nsv;
+    int slot = inrange ? p.pool.star[q] : -1;
+    const bool act = inrange && p.star_int[slot * SI_COUNT + SI_ACTIVE] != 0;
+    const DevOpts<T> o = p.o;
+    T v1 = Num<T>::neg_inf(), v2 = Num<T>::neg_inf();
+    if (act) {
+        const int64_t i = p.pool.model[q];
+        const T* __restrict__ srow = p.stars + (int64_t)slot * kStarStride;
+        ModelRegs<T, NB> m;
+        load_model<T, NB>(p.grid, p.npad, i, o, m);
+        const T c = srow[SR_SC + SC_MBAR] - m.bbar;
+        T A = p.pool.av[q], rho = p.pool.rv[q], eta = p.pool.eta[q], lold = p.pool.lold[q];
+        T e[NB], r[NB];
+        Mle<T, NB> r4;
+        resid_at<T, NB>(m, o, srow, A, rho, e, r);
+        mle_from_resid<T, NB>(e, c, srow, r4);
+        T lnew = lold;
+        for (int it = 0; it < p.nit; it++) {
+            // one (dAv, dRv) step from the current model / residuals (:385-420)
+            T an = T(0), ad = T(0), rn = T(0), rd = T(0);
+#pragma unroll
+            for (int j = 0; j < NB; j++) {
+                T Ms = r4.shat * r4.gb[j];                 // M_j / sigma_j
+                T t = srow[SR_AL + j] - Ms;                // resid_j / sigma_j
+                T rM = r[j] * Ms, DM = m.D[j] * Ms;
+                an = fma(rM, t, an);
+                ad = fma(rM, rM, ad);
+                rn = fma(DM, t, rn);
+                rd = fma(DM, DM, rd);
+            }
+            T dA = Num<T>::div(fma(T(kFac), an, (o.Abar - A) * o.PA), fma(T(kFac * kFac), ad, o.PA)) * eta;
+            T dR = Num<T>::div(fma(T(kFac), rn, (o.Rbar - rho) * o.PR), fma(T(kFac * kFac), rd, o.PR)) * eta;
+            dA = tmax(dA, o.avmin - A);
+            dA = tmin(dA, o.avmax - A);
+            A += dA;
+            dR = tmax(dR, o.rvmin - rho);
+            dR = tmin(dR, o.rvmax - rho);
+            rho += dR;
+            resid_at<T, NB>(m, o, srow, A, rho, e, r);
+            mle_from_resid<T, NB>(e, c, srow, r4);          // :423
+            lnew = T(-0.5) * r4.chi2;                       // :792-795
+            if (it == p.nit - 1) {
+                v1 = (lnew == lnew) ? lnew : Num<T>::neg_inf();
+                v2 = (tabs(lnew - lold) > o.ltol) ? v1 : Num<T>::neg_inf();
+            }
+            if (lnew < lold) eta = eta / T(1.2);            // :802
+            lold = lnew;                                    // :803
+        }
+        p.pool.av[q] = A;
+        p.pool.rv[q] = rho;
+        p.pool.eta[q] = eta;
+        p.pool.lold[q] = lold;
+        p.pool.chi2[q] = r4.chi2;
+        p.pool.scale[q] = r4.s;
+        p.pool.sden[q] = r4.den * r4.E * r4.E;
+    }
+    // per-star reductions; survivors of one star are contiguous, so a warp usually holds one star
+    const int slot0 = __shfl_sync(0xffffffffu, slot, 0);
+    if (__all_sync(0xffffffffu, slot == slot0)) {
+        if (slot0 >= 0) {
+            v1 = warp_max(v1);
+            v2 = warp_max(v2);
+            if ((threadIdx.x & 31) == 0) {
+                atomicMax(&p.red[(int64_t)slot0 * kNumRed + RED_FL], Enc<T>::enc(v1));
+                atomicMax(&p.red[(int64_t)slot0 * kNumRed + RED_FB], Enc<T>::enc(v2));
+            }
+        }
+    } else if (act) {
+        atomicMax(&p.red[(int64_t)slot * kNumRed + RED_FL], Enc<T>::enc(v1));
+        atomicMax(&p.red[(int64_t)slot * kNumRed + RED_FB], Enc<T>::enc(v2));
+    }
+}
+
+// =================================================================================================
+// Kernel 3: output records.  Recomputes _get_sed_mle (brutus/fitting.py:502-576) at the final
+// (Av, Rv) of each requested (star, model) to produce the full precision matrix icov_sar, and
+// writes float64 outputs.  Mode A: compacted records of the selected models (6 unique icov entries);
+// mode B: every model of one star (9 entries, the layout loglike returns).
+// =================================================================================================
+template <typename T, int NB>
+__global__ void __launch_bounds__(kTile) k_records(const RecordParams<T> p) {
+    const int64_t q = (int64_t)blockIdx.x * kTile + threadIdx.x;
+    int slot;
+    int64_t i;
+    if (p.sel_model) {
+        if (q >= p.nrec) return;
+        slot = p.sel_star[q];
+        i = p.sel_model[q];
+    } else {
+        if (q >= p.nmodel) return;
+        slot = p.star_slot;
+        i = q;
+    }
+    const DevOpts<T> o = p.o;
+    const T* __restrict__ srow = p.stars + (int64_t)slot * kStarStride;
+    const int64_t off = (int64_t)slot * p.npad + i;
+    ModelRegs<T, NB> m;
+    load_model<T, NB>(p.grid, p.npad, i, o, m);
+    const T c = srow[SR_SC + SC_MBAR] - m.bbar;
+    const T A = p.st.av[off], rho = p.st.rv[off];
+    T e[NB], r[NB];
+    Mle<T, NB> r4;
+    resid_at<T, NB>(m, o, srow, A, rho, e, r);
+    mle_from_resid<T, NB>(e, c, srow, r4);
+    // cross terms (:526-561) in sigma-normalised units; see the header comment and DESIGN.md
+    T sa = T(0), sr = T(0), ar = T(0), aden = T(0), rden = T(0);
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+        T Ms = r4.shat * r4.gb[j];
+        T t = srow[SR_AL + j] - Ms;
+        T h = Num<T>::exp2(T(kC2) * A * r[j]);     // F0_j / F_j = 10^(0.4 A r_j)   (:529-530)
+        T mmr = Ms - t;                            // (models - resid)/sigma         (:539-542)
+        sa = fma(r[j] * r4.gb[j], mmr, sa);
+        sr = fma(m.D[j] * r4.gb[j], mmr, sr);
+        T DM = m.D[j] * Ms, rM = r[j] * Ms;
+        ar = fma(DM, fma(Ms, T(1) - h, -t), ar);   // drvecs (reddening - resid)/var (:550-551)
+        aden = fma(rM, rM, aden);
+        rden = fma(DM, DM, rden);
+    }
+    const double f = kFac;
+    const double ss = (double)r4.den * (double)r4.E * (double)r4.E;
+    const double dsa = f * (double)r4.E * (double)sa, dsr = f * (double)r4.E * (double)sr;
+    const double dar = f * (double)ar;
+    const double daa = f * f * (double)aden + (double)o.PA + 1. / (0.05 * 0.05);
+    const double drr = f * f * (double)rden + (double)o.PR + 1. / (0.1 * 0.1);
+    p.o_lnl[q] = (double)p.st.lnl[off];
+    p.o_chi2[q] = (double)p.st.chi2[off];
+    p.o_scale[q] = (double)p.st.scale[off];
+    p.o_av[q] = (double)A;
+    p.o_rv[q] = (double)rho;
+    if (p.o_icov) {
+        if (p.sel_model) {
+            double* w = p.o_icov + q * 6;
+            w[0] = ss; w[1] = dsa; w[2] = dsr; w[3] = daa; w[4] = dar; w[5] = drr;
+        } else {
+            double* w = p.o_icov + q * 9;
+            w[0] = ss; w[1] = dsa; w[2] = dsr; w[3] = dsa; w[4] = daa; w[5] = dar; w[6] = dsr; w[7] = dar; w[8] = drr;
+        }
+    }
+}
+
+// ---- launchers -------------------------------------------------------------------------------------
+template <typename T, int NB> void launch_magfit(const SweepParams<T>& p, cudaStream_t st) {
+    dim3 grid((unsigned)(p.npad / kTile), (unsigned)((p.nlist + kStarChunk - 1) / kStarChunk));
+    k_magfit<T, NB><<<grid, kTile, 0, st>>>(p);
+}
+template <typename T, int NB> void launch_flux(const FluxParams<T>& p, cudaStream_t st) {
+    if (p.nsv <= 0) return;
+    k_flux<T, NB><<<(unsigned)((p.nsv + kTile - 1) / kTile), kTile, 0, st>>>(p);
+}
+template <typename T, int NB> void launch_records(const RecordParams<T>& p, cudaStream_t st) {
+    int64_t n = p.sel_model ? p.nrec : p.nmodel;
+    if (n <= 0) return;
+    k_records<T, NB><<<(unsigned)((n + kTile - 1) / kTile), kTile, 0, st>>>(p);
+}
+
+}  // namespace bf

@@ -1,0 +1,136 @@
+/*
+ * brutus_b200.h -- C ABI of libbrutus_b200.so: the B200 (sm_100a) implementation of the
+ * brute-force photometric likelihood sweep of joshspeagle/brutus.
+ *
+ * The reference has no FFI: its seams are plain Python callables.  Each entry
+ * point below names the reference interface it stands in for (paths relative to the reference
+ * tree).  Plain pointers and sizes only; no exceptions cross the boundary; every call returns
+ * an int status (0 = OK, negative = error, see BF_E_*), and bf_last_error() gives the message.
+ *
+ * Threading: a handle is bound to one CUDA device and one stream and is NOT re-entrant; distinct
+ * handles are independent (one handle per GPU, one process per GPU under torchrun).
+ * Inputs are never modified.  All host buffers are caller-owned.
+ */
+#ifndef BRUTUS_B200_H
+#define BRUTUS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BF_OK 0
+#define BF_E_INVALID (-1)   /* bad argument (message says which)                          */
+#define BF_E_CUDA (-2)      /* CUDA runtime error                                          */
+#define BF_E_NOGRID (-3)    /* sweep requested before bf_set_grid                           */
+#define BF_E_CAPACITY (-4)  /* caller's compacted-output buffers too small; see n_required */
+#define BF_E_THRESH (-5)    /* init_thresh > ltol_subthresh (ValueError at brutus/fitting.py:691-693) */
+#define BF_E_NOMEM (-6)
+
+#define BF_MAX_FILT 16      /* bands per grid supported by the compiled kernels */
+
+/* grid memory layouts accepted by bf_set_grid */
+#define BF_LAYOUT_C 0       /* (Nmodel, Nfilt, 3) C order: what load_models returns, brutus/utils.py:588-605 */
+#define BF_LAYOUT_F 1       /* same shape, Fortran order: what _fit builds, brutus/fitting.py:1964 */
+
+/* arithmetic the kernels compute in */
+#define BF_PRECISION_F32 0  /* throughput path */
+#define BF_PRECISION_F64 1  /* verification path (the reference computes in float64) */
+
+typedef struct bf_handle bf_handle;
+
+/* Fit options: the keyword arguments of loglike (brutus/fitting.py:579-585) that reach the kernels,
+ * plus wt_thresh of lnpost (brutus/fitting.py:824, :988-991). */
+typedef struct bf_options {
+    double avlim[2];        /* default (0, 20)      */
+    double av_gauss[2];     /* default (0, 1e6)     */
+    double rvlim[2];        /* default (1, 8)       */
+    double rv_gauss[2];     /* default (3.32, 0.18) */
+    double ltol;            /* default 3e-2         */
+    double ltol_subthresh;  /* default 1e-2         */
+    double init_thresh;     /* default 5e-3         */
+    double wt_thresh;       /* default 1e-3 (bf_sweep_batch only) */
+    int32_t dim_prior;      /* default 1            */
+    int32_t max_iter;       /* cap on mag/flux loop iterations (reference: unbounded); 0 = 64 */
+    int32_t apply_parallax_clip; /* 1: lnpost's rough parallax prior (fitting.py:976-980) is applied
+                                    before thresholding; 0 mimics lnpost(parallax=None) */
+    int32_t reserved;
+} bf_options;
+
+/* Per-call statistics (device times from CUDA events on the handle's stream). */
+typedef struct bf_stats {
+    double ms_device;       /* first kernel -> last kernel of the call                */
+    double ms_magfit;       /* sum over launches of the full-grid magnitude-fit sweep  */
+    double ms_flux;         /* survivor flux-space refinement                          */
+    double ms_select;       /* threshold / compaction / record kernels                 */
+    int64_t kernel_launches;
+    int64_t magfit_launches;
+    int64_t resweeps;       /* stars whose speculated mag-iteration count was wrong    */
+    int64_t survivors;      /* total models that survived the cull (brutus/fitting.py:758-759)  */
+    int64_t selected;       /* total models that passed wt_thresh                     */
+    int64_t h2d_bytes, d2h_bytes;
+} bf_stats;
+
+void bf_default_options(bf_options* opt);
+
+/* Lifetime.  device = CUDA ordinal; precision = BF_PRECISION_*. */
+int bf_create(int device, int precision, bf_handle** out);
+int bf_destroy(bf_handle* h);
+const char* bf_last_error(const bf_handle* h); /* h may be NULL: last error of a failed bf_create */
+
+/* Stage the SED grid in HBM once.  Replaces BruteForce.__init__'s self.models (brutus/fitting.py:1139)
+ * and the per-star copies `np.array(self.models, order='F')` / `mag_coeffs[:, mask, :]`
+ * (:1964, :714).  coeffs: float32, nmodel*nfilt*3 values in `layout`; re-tiled on the device to
+ * [coef][band][model].  bf_set_grid_device takes a DEVICE pointer (e.g. the target of an NCCL
+ * broadcast) in BF_LAYOUT_C or _F. */
+int bf_set_grid(bf_handle* h, const float* coeffs, int64_t nmodel, int32_t nfilt, int32_t layout);
+int bf_set_grid_device(bf_handle* h, const void* d_coeffs, int64_t nmodel, int32_t nfilt, int32_t layout);
+
+/* Optional model label columns used by lnprior_ext (brutus/fitting.py:1995-2009):
+ * labels[l*nmodel + i], float64. */
+int bf_set_labels(bf_handle* h, const double* labels, int32_t nlabel);
+
+/* B1: one star, full-length outputs -- the contract of
+ *   loglike(data, data_err, data_mask, mag_coeffs, ..., return_vals=True)  (brutus/fitting.py:579-820)
+ * flux/err: nfilt float64; mask: nfilt uint8 (NOT modified; mask_clean_out receives the cleaned mask
+ * the reference writes in place at :709).  parallax/parallax_err: NaN = not provided (:750-751).
+ * Outputs (caller-allocated float64): lnl, chi2, scale, av, rv [nmodel]; icov [nmodel*9] or NULL.
+ * diag (may be NULL): [0]=Ndim [1]=mag iterations [2]=flux iterations [3]=survivors of the cull. */
+int bf_loglike_full(bf_handle* h, const double* flux, const double* err, const uint8_t* mask,
+                    double parallax, double parallax_err, const bf_options* opt,
+                    double* lnl, double* chi2, double* scale, double* av, double* rv, double* icov,
+                    uint8_t* mask_clean_out, int64_t* diag);
+
+/* B2: many stars, compacted outputs -- the per-star body of BruteForce._fit
+ * (brutus/fitting.py:1980-2009: loglike + lnprior_ext) fused with lnpost's first stage (:976-991:
+ * rough parallax prior, -1e300 clean-up, selection lnprob > max + ln wt_thresh).
+ *   flux, err      [nstar*nfilt] float64;  mask [nstar*nfilt] uint8
+ *   parallax, parallax_err [nstar] float64 (NaN = none); either may be NULL (= all NaN)
+ *   ext_mean, ext_std [nstar*nlabel] float64 or NULL (lnprior_ext; needs bf_set_labels)
+ * per-star outputs (each may be NULL): ndim [nstar] int32, n_iter [nstar*2] int32 (mag, flux loop
+ *   iterations), n_surv [nstar] int64 (survivors of the cull), max_lnprob [nstar] float64
+ * compacted outputs, CSR over stars: offsets [nstar+1] int64; for k in [offsets[s], offsets[s+1]):
+ *   model_idx (int32, ascending), lnl (incl. lnprior_ext), chi2, scale, av, rv float64,
+ *   icov6 float64 x6 = (ss, sa, sr, aa, ar, rr) of the symmetric precision matrix (:563-574).
+ * capacity = number of records the compacted buffers can hold.  If more are needed the call
+ * returns BF_E_CAPACITY with *n_required set; nothing else is valid then. */
+int bf_sweep_batch(bf_handle* h, int64_t nstar, const double* flux, const double* err,
+                   const uint8_t* mask, const double* parallax, const double* parallax_err,
+                   const double* ext_mean, const double* ext_std, const bf_options* opt,
+                   int32_t* ndim, int32_t* n_iter, int64_t* n_surv, double* max_lnprob,
+                   int64_t* offsets, int64_t capacity, int64_t* n_required,
+                   int32_t* model_idx, double* lnl, double* chi2, double* scale, double* av,
+                   double* rv, double* icov6);
+
+/* Statistics of the most recent bf_loglike_full / bf_sweep_batch call on this handle. */
+int bf_get_stats(const bf_handle* h, bf_stats* out);
+
+/* Build / device introspection. */
+int bf_device_count(void);
+const char* bf_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRUTUS_B200_H */

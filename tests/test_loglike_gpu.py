@@ -1,0 +1,126 @@
+"""GPU parity tests for the B1 seam (bf_loglike_full through brutus_b200.fitting.loglike):
+CUDA path vs the C oracle on seeded inputs and vs the golden vectors of the unmodified reference.
+
+Tolerances (stated, per output):
+  float64 kernels: 1e-8 relative on every output (observed ~1e-12); identical iteration counts
+                   and identical cull sets.
+  float32 kernels: chi2, lnl  |d| <= 2e-3 + 2e-5 |x|   (S/N 100 photometry amplifies 1e-7 model
+                                                       errors to ~1e-5 sigma residual errors)
+                   av   |d| <= 2e-4 ; rv |d| <= 2e-3 ; scale rel 2e-5 ; icov rel 2e-3 of the
+                   matrix scale sqrt(|ii||jj|)
+  for models whose cull membership matches; membership may differ only within 1e-3 of the
+  threshold, and the mag/flux iteration counts must match the oracle's.
+"""
+import numpy as np
+import pytest
+
+import golden_cases as gc
+from brutus_b200 import mock
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fitting():
+    from brutus_b200 import fitting
+    yield fitting
+    fitting.release_handles()
+
+
+def _compare_f64(out, ref, tag):
+    for key, a, b in zip(gc.KEYS, out, ref):
+        if key == "ndim":
+            assert a == b
+        else:
+            assert gc.rel_err(a, b) < 1e-8, (tag, key)
+
+
+def _icov_scale(ic):
+    d = np.sqrt(np.abs(np.einsum("nii->ni", ic)))
+    return d[:, :, None] * d[:, None, :]
+
+
+def _compare_f32(out, ref, tag, strict_idx=None):
+    lnl, nd, chi2, sc, av, rv, ic = out
+    rl, rnd, rchi2, rsc, rav, rrv, ric = ref
+    assert nd == rnd
+    sel = np.ones(len(chi2), bool) if strict_idx is None else strict_idx
+    fin = np.isfinite(rlnl := rl)
+    assert np.array_equal(np.isfinite(lnl), fin)
+
+    def close(a, b, atol, rtol, name):
+        d = np.abs(a[sel] - b[sel])
+        lim = atol + rtol * np.abs(b[sel])
+        bad = d > lim
+        assert not bad.any(), (tag, name, int(bad.sum()), float(d[bad].max()), float(np.abs(b[sel])[bad].min()))
+    close(chi2, rchi2, 2e-3, 2e-5, "chi2")
+    close(np.where(fin, lnl, 0), np.where(fin, rlnl, 0), 2e-3, 2e-5, "lnl")
+    close(av, rav, 2e-4, 0, "av")
+    close(rv, rrv, 2e-3, 0, "rv")
+    close(sc, rsc, 0, 2e-5, "scale")
+    d = np.abs(ic - ric) / _icov_scale(ric)
+    assert d[sel].max() < 2e-3, (tag, "icov", float(d[sel].max()))
+
+
+def _run_case(fitting, oracle_mod, name, precision):
+    grid, labels, st, kw = gc.build_case(name)
+    gold = gc.load_loglike(name)
+    for i in range(len(st["flux"])):
+        args = (st["flux"][i], st["err"][i])
+        pk = dict(parallax=st["parallax"][i], parallax_err=st["parallax_err"][i])
+        m = st["mask"][i].copy()
+        out = fitting.loglike(*args, m, grid, return_vals=True, precision=precision,
+                              return_diag=True, **pk, **kw)
+        orc = oracle_mod.loglike(*args, st["mask"][i].copy(), grid, return_vals=True,
+                                 return_diag=True, **pk, **kw)
+        assert np.array_equal(m, gold["mask_%d" % i])
+        ref = tuple(gold["%s_%d" % (k, i)] if k != "ndim" else int(gold["ndim_%d" % i]) for k in gc.KEYS)
+        tag = (name, i, precision)
+        assert out[7]["n_iter_mag"] == orc[7]["n_iter_mag"], tag
+        assert out[7]["n_iter_flux"] == orc[7]["n_iter_flux"], tag
+        if precision == "f64":
+            assert out[7]["n_surv"] == orc[7]["n_surv"], tag
+            _compare_f64(out[:7], ref, tag)
+            _compare_f64(out[:7], orc[:7], tag)
+        else:
+            assert abs(out[7]["n_surv"] - orc[7]["n_surv"]) <= max(2, orc[7]["n_surv"] // 500), tag
+            _compare_f32(out[:7], ref, tag)
+
+
+@pytest.mark.parametrize("name", sorted(gc.LOGLIKE_CASES))
+def test_golden_f64(fitting, oracle_mod, name):
+    _run_case(fitting, oracle_mod, name, "f64")
+
+
+@pytest.mark.parametrize("name", sorted(gc.LOGLIKE_CASES))
+def test_golden_f32(fitting, oracle_mod, name):
+    _run_case(fitting, oracle_mod, name, "f32")
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_oracle_100k(fitting, oracle_mod, precision):
+    """Larger seeded case against the oracle: 100k models x 8 bands, a handful of stars."""
+    grid, labels = mock.make_grid(100_000, 8, seed=1100)
+    st = mock.make_stars(grid, 6, seed=2100)
+    for i in range(6):
+        pk = dict(parallax=st["parallax"][i], parallax_err=st["parallax_err"][i])
+        out = fitting.loglike(st["flux"][i], st["err"][i], st["mask"][i].copy(), grid,
+                              return_vals=True, precision=precision, return_diag=True, **pk)
+        orc = oracle_mod.loglike(st["flux"][i], st["err"][i], st["mask"][i].copy(), grid,
+                                 return_vals=True, return_diag=True, **pk)
+        tag = ("100k", i, precision)
+        assert out[7]["n_iter_mag"] == orc[7]["n_iter_mag"], tag
+        assert out[7]["n_iter_flux"] == orc[7]["n_iter_flux"], tag
+        if precision == "f64":
+            assert out[7]["n_surv"] == orc[7]["n_surv"]
+            _compare_f64(out[:7], orc[:7], tag)
+        else:
+            _compare_f32(out[:7], orc[:7], tag)
+
+
+def test_threshold_valueerror(fitting):
+    grid, labels = mock.make_grid(1000, 5, seed=1)
+    st = mock.make_stars(grid, 1, seed=2)
+    with pytest.raises(ValueError):
+        fitting.loglike(st["flux"][0], st["err"][0], st["mask"][0].copy(), grid,
+                        init_thresh=0.5, ltol_subthresh=1e-2)
