@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- stars/sec of the full-grid brute-force likelihood sweep (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config 2]
+
+A step = one pass of the hot path (loglike + label priors + lnpost's first threshold, i.e.
+``bf_sweep_batch``) over one synthetic catalogue of ``nstar`` stars against the whole grid.
+N=1 workload: BASELINE.json configs[1] (1k stars, 8 bands, 1M-point grid).  For N>1 (torchrun, one
+rank per GPU) every rank sweeps its own ``nstar`` stars against a replica of the grid (rank 0
+builds it, one NCCL broadcast, no collective in the hot loop): weak scaling.
+
+  value            stars/s from CUDA-event device time (first kernel -> last kernel of each call,
+                   grid and scratch resident in HBM), max over ranks
+  e2e              stars/s through the C ABI with host buffers: wall clock of the calls, including
+                   host preparation of the star rows, H2D of the star rows and D2H of the records
+  roofline         dominant kernel k_magfit: algorithmic bytes (Nmodel x Nfilt x 12 B per star per
+                   pass) / its CUDA-event time, against the measured HBM copy peak
+  cpu_baseline     the C oracle (port of the reference's loglike) on this box's host cores
+--impl reference   times only that CPU path (the reference is Python+numba and cannot travel to
+                   the GPU box; oracle/loglike_ref.c is its pinned restatement).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "stars/sec (full-grid loglike sweep)"
+CONFIG_NAMES = {
+    1: "C1: 1 star x 10k models x 5 bands",
+    2: "C2: 1k stars x 1M models x 8 bands",
+    3: "C3: 3M models x 12 bands, avlim (0,6), 10% band drop-outs",
+    5: "C5: 3M models x 8 bands",
+}
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def read_traffic():
+    """DRAM bytes per k_magfit launch from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "magfit_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], 0.0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload(cfg_id, nstar, rank):
+    from brutus_b200 import mock
+    cfg = dict(mock.CONFIGS[cfg_id])
+    if nstar:
+        cfg["nstar"] = nstar
+    return cfg
+
+
+def make_inputs(cfg_id, cfg, rank, need_grid=True):
+    from brutus_b200 import mock
+    grid = labels = None
+    if need_grid:
+        grid, labels = mock.make_grid(cfg["nmodel"], cfg["nfilt"], seed=1000 + cfg_id)
+    return grid, labels
+
+
+def make_stars(cfg_id, cfg, grid, rank):
+    from brutus_b200 import mock
+    return mock.make_stars(grid, cfg["nstar"], seed=2000 + cfg_id + 100 * rank, av_max=cfg["av_max"],
+                           dropout=cfg["dropout"])
+
+
+def cpu_sample(cfg, grid, stars, nthreads, nsample):
+    """Times the oracle (port of the reference loglike) on `nsample` stars with `nthreads` threads."""
+    from oracle import oracle
+    oracle.build()
+    nt = nthreads or oracle.num_threads()
+    sl = slice(0, nsample)
+    t0 = time.perf_counter()
+    oracle.loglike_batch(stars["flux"][sl], stars["err"][sl], stars["mask"][sl], grid,
+                         parallax=stars["parallax"][sl], parallax_err=stars["parallax_err"][sl],
+                         nthreads=nt, avlim=cfg["avlim"])
+    dt = time.perf_counter() - t0
+    return nsample / dt, nt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cfg = workload(args.config, args.nstar, 0)
+    grid, _ = make_inputs(args.config, cfg, 0)
+    from oracle import oracle
+    oracle.build()
+    nt = oracle.num_threads()
+    per_step = max(nt, 8) if cfg["nmodel"] <= 1_000_000 else max(nt // 2, 4)
+    cfg_s = dict(cfg, nstar=per_step * (args.steps + args.warmup))
+    stars = make_stars(args.config, cfg_s, grid, 0)
+    times = []
+    for it in range(args.steps + args.warmup):
+        sl = slice(it * per_step, (it + 1) * per_step)
+        sub = {k: stars[k][sl] for k in ("flux", "err", "mask", "parallax", "parallax_err")}
+        rate, _, dt = cpu_sample(cfg, grid, sub, nt, per_step)
+        if it >= args.warmup:
+            times.append(dt)
+    tot = float(np.sum(times))
+    value = per_step * args.steps / tot
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "stars/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": CONFIG_NAMES[args.config], "nmodel": cfg["nmodel"],
+                       "nfilt": cfg["nfilt"], "stars_per_step": per_step},
+            "cpu_baseline": {"value": value, "unit": "stars/s", "cores": nt, "kind": "port",
+                             "sample": "%d stars per step x %d steps, OpenMP over stars, C port "
+                                       "(oracle/loglike_ref.c) of the reference's numba loglike"
+                                       % (per_step, args.steps)},
+            "e2e": {"value": value, "unit": "stars/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def run_b200(args):
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    cfg = workload(args.config, args.nstar, rank)
+    from brutus_b200 import _lib
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    h = _lib.Handle(local_rank, args.precision)
+    # ---- stage the grid: rank 0 builds it; one NCCL broadcast; device-side re-tiling ----
+    t0 = time.perf_counter()
+    if world > 1:
+        import torch
+        shape = (cfg["nmodel"], cfg["nfilt"], 3)
+        if rank == 0:
+            grid, _ = make_inputs(args.config, cfg, 0)
+            dgrid = torch.from_numpy(grid).cuda()
+        else:
+            grid = None
+            dgrid = torch.empty(shape, dtype=torch.float32, device="cuda")
+        dist.broadcast(dgrid, src=0)
+        torch.cuda.synchronize()
+        h.set_grid_device(dgrid.data_ptr(), cfg["nmodel"], cfg["nfilt"], _lib.LAYOUT_C)
+        if grid is None:
+            grid = dgrid.cpu().numpy()  # only to draw this rank's synthetic stars from
+        del dgrid
+        torch.cuda.empty_cache()
+    else:
+        grid, _ = make_inputs(args.config, cfg, 0)
+        h.set_grid(grid)
+    t_stage = time.perf_counter() - t0
+    stars = make_stars(args.config, cfg, grid, rank)
+    opts = _lib.make_options(avlim=cfg["avlim"])
+    nstar = cfg["nstar"]
+
+    def barrier():
+        if world > 1:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step(cap):
+        h.flush_l2()
+        t = time.perf_counter()
+        res = h.sweep_batch(stars["flux"], stars["err"], stars["mask"], stars["parallax"],
+                            stars["parallax_err"], opts=opts, capacity=cap)
+        wall = time.perf_counter() - t
+        return res, wall, h.stats()
+
+    cap = None
+    for _ in range(args.warmup):
+        res, _, _ = step(cap)
+        cap = int(res["offsets"][-1]) + 1024
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t_region = time.perf_counter()
+    dev_ms = wall_s = 0.0
+    agg = {}
+    for _ in range(args.steps):
+        res, wall, st = step(cap)
+        dev_ms += st["ms_device"]
+        wall_s += wall
+        for k, v in st.items():
+            agg[k] = agg.get(k, 0) + v
+    barrier()
+    t_region = time.perf_counter() - t_region
+    clocks = sampler.summary()
+    if world > 1:
+        import torch
+        t = torch.tensor([dev_ms, wall_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall_s = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    total_stars = nstar * args.steps * world
+    value = total_stars / (dev_ms * 1e-3)
+    e2e = total_stars / wall_s
+    peak, peak_src = read_peaks()
+    bytes_per_star = cfg["nmodel"] * cfg["nfilt"] * 12
+    launches = max(1, agg["magfit_launches"])
+    ach = (bytes_per_star * agg["magfit_star_passes"] / launches) / (agg["ms_magfit"] / launches * 1e-3) / 1e9
+    traffic = read_traffic()
+    line = {
+        "metric": METRIC, "value": value, "unit": "stars/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": CONFIG_NAMES[args.config], "nmodel": cfg["nmodel"], "nfilt": cfg["nfilt"],
+                   "stars_per_step_per_gpu": nstar, "parallelism": "stars sharded x%d, grid replicated" % world,
+                   "l2": "512 MB L2 flush before every step; per-batch state arrays (GBs) stream through L2",
+                   "grid_stage_s": round(t_stage, 3)},
+        "e2e": {"value": e2e, "unit": "stars/s", "ms_per_step": 1e3 * wall_s / args.steps,
+                "h2d_bytes_per_step": int(agg["h2d_bytes"] / args.steps),
+                "d2h_bytes_per_step": int(agg["d2h_bytes"] / args.steps)},
+        "gpu_launches": int(agg["kernel_launches"]),
+        "roofline": {"bound": "hbm", "kernel": "k_magfit", "achieved": ach, "peak": peak, "unit": "GB/s",
+                     "frac": ach / peak, "peak_source": peak_src,
+                     "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch"),
+                     "note": "algorithmic bytes = Nmodel*Nfilt*12 B per star per pass; stars are batched "
+                             "per grid tile, so DRAM traffic is lower than this (effective figure)",
+                     "kernel_share_of_step": agg["ms_magfit"] / dev_ms,
+                     "launches": int(agg["magfit_launches"]),
+                     "ms_per_launch": agg["ms_magfit"] / launches},
+        "phases_ms_per_step": {"magfit": agg["ms_magfit"] / args.steps, "flux": agg["ms_flux"] / args.steps,
+                               "select": agg["ms_select"] / args.steps},
+        "counts_per_step": {"survivors": agg["survivors"] / args.steps, "selected": agg["selected"] / args.steps,
+                            "resweeps": agg["resweeps"] / args.steps},
+        "clocks": clocks,
+        "region_wall_s": t_region,
+    }
+    if world == 1 and not args.no_cpu:
+        nt_probe = os.cpu_count() or 1
+        nsample = max(8, min(2 * nt_probe, 64)) if cfg["nmodel"] <= 1_000_000 else max(4, min(nt_probe, 32))
+        rate, nt, dt = cpu_sample(cfg, grid, stars, 0, min(nsample, nstar))
+        line["cpu_baseline"] = {"value": rate, "unit": "stars/s", "cores": nt, "kind": "port",
+                                "sample": "first %d stars of the same catalogue and grid, %.1f s, OpenMP over "
+                                          "stars, C port of the reference loglike" % (min(nsample, nstar), dt)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 5])
+    ap.add_argument("--nstar", type=int, default=0, help="stars per step per GPU (default: the config's; "
+                    "capped at 1000 for configs 3 and 5)")
+    ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if not args.nstar and args.config in (3, 5):
+        args.nstar = 1000
+    return run_reference(args) if args.impl == "reference" else run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

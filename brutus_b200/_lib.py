@@ -19,7 +19,7 @@ MAX_FILT = 16
 # every symbol include/brutus_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = ("bf_default_options", "bf_create", "bf_destroy", "bf_last_error", "bf_set_grid",
            "bf_set_grid_device", "bf_set_labels", "bf_loglike_full", "bf_sweep_batch",
-           "bf_get_stats", "bf_device_count", "bf_version")
+           "bf_get_stats", "bf_flush_l2", "bf_device_count", "bf_version")
 
 
 class BrutusCudaError(RuntimeError):
@@ -36,7 +36,8 @@ class Options(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("ms_device", C.c_double), ("ms_magfit", C.c_double), ("ms_flux", C.c_double),
                 ("ms_select", C.c_double), ("kernel_launches", C.c_int64),
-                ("magfit_launches", C.c_int64), ("resweeps", C.c_int64), ("survivors", C.c_int64),
+                ("magfit_launches", C.c_int64), ("magfit_star_passes", C.c_int64),
+                ("resweeps", C.c_int64), ("survivors", C.c_int64),
                 ("selected", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 
     def as_dict(self):
@@ -73,6 +74,7 @@ def load():
                                    i32p, i32p, i64p, dp, i64p, C.c_int64, i64p,
                                    i32p, dp, dp, dp, dp, dp, dp]
     lib.bf_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.bf_flush_l2.argtypes = [vp]
     lib.bf_device_count.restype = C.c_int
     lib.bf_version.restype = C.c_char_p
     _lib = lib
@@ -162,6 +164,9 @@ class Handle:
         self._check(self._lib.bf_set_labels(self._h, _ptr(a, C.c_double), a.shape[0]))
         self.nlabel = a.shape[0]
 
+    def flush_l2(self):
+        self._check(self._lib.bf_flush_l2(self._h))
+
     def stats(self):
         s = Stats()
         self._lib.bf_get_stats(self._h, C.byref(s))
@@ -192,6 +197,8 @@ class Handle:
         e = np.ascontiguousarray(err, dtype=np.float64)
         m = np.ascontiguousarray(mask).astype(np.uint8)
         ns = f.shape[0]
+        if not self.nfilt:
+            raise BrutusCudaError("no grid staged (call set_grid first)")
         if f.ndim != 2 or f.shape[1] != self.nfilt or e.shape != f.shape or m.shape != f.shape:
             raise ValueError("data, data_err and data_mask must have shape (Ndata, Nfilt)")
         par = None if parallax is None else np.ascontiguousarray(parallax, dtype=np.float64)

@@ -66,6 +66,7 @@ typedef struct bf_stats {
     double ms_select;       /* threshold / compaction / record kernels                 */
     int64_t kernel_launches;
     int64_t magfit_launches;
+    int64_t magfit_star_passes; /* stars x full-grid passes done by those launches         */
     int64_t resweeps;       /* stars whose speculated mag-iteration count was wrong    */
     int64_t survivors;      /* total models that survived the cull (brutus/fitting.py:758-759)  */
     int64_t selected;       /* total models that passed wt_thresh                     */
@@ -125,6 +126,10 @@ int bf_sweep_batch(bf_handle* h, int64_t nstar, const double* flux, const double
 
 /* Statistics of the most recent bf_loglike_full / bf_sweep_batch call on this handle. */
 int bf_get_stats(const bf_handle* h, bf_stats* out);
+
+/* Benchmark hygiene: overwrite a 512 MB scratch buffer so that nothing of the previous step stays
+ * in the 126 MB L2 (B200_PROFILING.md, "Timing hygiene"). */
+int bf_flush_l2(bf_handle* h);
 
 /* Build / device introspection. */
 int bf_device_count(void);

@@ -1,0 +1,60 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/brutus_b200.h declares; the
+product path fails loudly without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from brutus_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def test_exports_match_header(lib):
+    from brutus_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "brutus_b200.h")).read()
+    declared = set(re.findall(r"\b(bf_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for s in declared:
+        assert getattr(lib, s) is not None
+
+
+def test_struct_layout_matches_header(lib):
+    from brutus_b200 import _lib
+    o = _lib.Options()
+    lib.bf_default_options(C.byref(o))
+    assert tuple(o.avlim) == (0., 20.) and tuple(o.av_gauss) == (0., 1e6)
+    assert tuple(o.rvlim) == (1., 8.) and tuple(o.rv_gauss) == (3.32, 0.18)
+    assert (o.ltol, o.ltol_subthresh, o.init_thresh, o.wt_thresh) == (3e-2, 1e-2, 5e-3, 1e-3)
+    assert (o.dim_prior, o.max_iter, o.apply_parallax_clip) == (1, 0, 1)
+    assert C.sizeof(_lib.Options) == 8 * 8 + 4 * 8 + 4 * 4
+    assert C.sizeof(_lib.Stats) == 4 * 8 + 8 * 8
+
+
+def test_no_cpu_fallback(lib):
+    from brutus_b200 import _lib
+    if lib.bf_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(_lib.BrutusCudaError):
+        _lib.Handle(0)
+    import numpy as np
+    from brutus_b200 import fitting, mock
+    grid, _ = mock.make_grid(100, 5, seed=1)
+    st = mock.make_stars(grid, 1, seed=2)
+    with pytest.raises(_lib.BrutusCudaError):
+        fitting.loglike(st["flux"][0], st["err"][0], st["mask"][0].copy(), grid)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "brutus_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.replace("# oracle", ""), (f, "product code must not touch oracle/")

@@ -1,0 +1,113 @@
+"""GPU parity tests for the B2 seam (bf_sweep_batch): the batched sweep with label priors and
+lnpost's first selection, against the C oracle (loglike + select) star by star.
+
+float64 kernels: identical selections and iteration counts; records within 1e-8 relative.
+float32 kernels: selections may differ only for models within 2e-3 of the threshold; records of
+common models within the float32 tolerances stated in tests/test_loglike_gpu.py.
+"""
+import numpy as np
+import pytest
+
+from brutus_b200 import mock
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_star(oracle_mod, grid, st, i, labels=None, ext=None, **kw):
+    pk = dict(parallax=st["parallax"][i], parallax_err=st["parallax_err"][i])
+    ref = oracle_mod.loglike(st["flux"][i], st["err"][i], st["mask"][i].copy(), grid, return_vals=True,
+                             return_diag=True, **pk, **kw)
+    ek = {}
+    if labels is not None:
+        ek = dict(labels=labels, ext_mean=ext[0][i], ext_std=ext[1][i])
+    lnl, lnprob, sel = oracle_mod.select(ref[0], ref[3], ref[6], **pk, **ek)
+    return ref, lnl, lnprob, sel
+
+
+def _unpack6(ic):
+    return np.stack([ic[:, 0, 0], ic[:, 0, 1], ic[:, 0, 2], ic[:, 1, 1], ic[:, 1, 2], ic[:, 2, 2]], axis=1)
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_sweep_batch_vs_oracle(oracle_mod, precision):
+    from brutus_b200 import _lib
+    grid, labels = mock.make_grid(50_000, 8, seed=1200)
+    st = mock.make_stars(grid, 24, seed=2200, dropout=0.05)
+    st["flux"][3, 2] = -0.2 * abs(st["flux"][3, 2])
+    lab = np.stack([labels["Mr"], labels["feh"]])
+    rs = np.random.RandomState(5)
+    ext_mean = np.stack([st["truth"]["idx"] * 0 + labels["Mr"][st["truth"]["idx"]] + rs.normal(0, 0.3, 24),
+                         np.full(24, np.nan)], axis=1)
+    ext_std = np.stack([np.full(24, 0.5), np.full(24, 0.2)], axis=1)
+    ext_std[::3, 0] = -1.0  # inactive constraints (brutus/fitting.py:1999)
+    h = _lib.Handle(0, precision)
+    h.set_grid(grid)
+    h.set_labels(lab)
+    res = h.sweep_batch(st["flux"], st["err"], st["mask"], st["parallax"], st["parallax_err"],
+                        ext_mean=ext_mean, ext_std=ext_std, capacity=16)  # forces the E_CAPACITY retry
+    stats = h.stats()
+    h.close()
+    assert stats["kernel_launches"] > 0
+    assert res["offsets"][0] == 0 and res["offsets"][-1] == len(res["model_idx"])
+    for i in range(24):
+        ref, lnl, lnprob, sel = _oracle_star(oracle_mod, grid, st, i, labels=lab, ext=(ext_mean, ext_std))
+        lo, hi = res["offsets"][i], res["offsets"][i + 1]
+        idx = res["model_idx"][lo:hi]
+        assert np.all(np.diff(idx) > 0)
+        assert res["ndim"][i] == ref[1]
+        assert tuple(res["n_iter"][i]) == (ref[7]["n_iter_mag"], ref[7]["n_iter_flux"]), i
+        rec = {k: res[k][lo:hi] for k in ("lnl", "chi2", "scale", "av", "rv", "icov6")}
+        if precision == "f64":
+            assert res["n_surv"][i] == ref[7]["n_surv"]
+            assert np.array_equal(idx, sel), i
+            assert abs(res["max_lnprob"][i] - lnprob.max()) < 1e-8 * max(1, abs(lnprob.max()))
+            for k, r in (("lnl", lnl), ("chi2", ref[2]), ("scale", ref[3]), ("av", ref[4]), ("rv", ref[5])):
+                assert np.max(np.abs(rec[k] - r[sel]) / np.maximum(np.abs(r[sel]), 1e-300)) < 1e-8, (i, k)
+            r6 = _unpack6(ref[6][sel])
+            assert np.max(np.abs(rec["icov6"] - r6) / np.maximum(np.abs(r6), 1e-300)) < 1e-7, i
+        else:
+            thr = lnprob.max() + np.log(1e-3)
+            sym = np.setxor1d(idx, sel)
+            assert np.all(np.abs(lnprob[sym] - thr) < 2e-3 + 2e-5 * abs(thr)), (i, len(sym))
+            common = np.intersect1d(idx, sel)
+            pos = np.searchsorted(idx, common)
+            assert np.max(np.abs(rec["chi2"][pos] - ref[2][common])) < 2e-3 + 2e-5 * np.max(ref[2][common])
+            assert np.max(np.abs(rec["lnl"][pos] - lnl[common])) < 2e-3 + 2e-5 * np.max(np.abs(lnl[common]))
+            assert np.max(np.abs(rec["av"][pos] - ref[4][common])) < 2e-4
+            assert np.max(np.abs(rec["rv"][pos] - ref[5][common])) < 2e-3
+            assert np.max(np.abs(rec["scale"][pos] / ref[3][common] - 1)) < 2e-5
+
+
+def test_batch_equals_single_star():
+    """Shard invariance: a star's records do not depend on what else is in the batch (bitwise)."""
+    from brutus_b200 import _lib
+    grid, labels = mock.make_grid(20_000, 6, seed=1300)
+    st = mock.make_stars(grid, 40, seed=2300)
+    h = _lib.Handle(0, "f32")
+    h.set_grid(grid)
+    full = h.sweep_batch(st["flux"], st["err"], st["mask"], st["parallax"], st["parallax_err"])
+    for i in (0, 17, 39):
+        one = h.sweep_batch(st["flux"][i:i + 1], st["err"][i:i + 1], st["mask"][i:i + 1],
+                            st["parallax"][i:i + 1], st["parallax_err"][i:i + 1])
+        lo, hi = full["offsets"][i], full["offsets"][i + 1]
+        assert np.array_equal(one["model_idx"], full["model_idx"][lo:hi])
+        for k in ("lnl", "chi2", "scale", "av", "rv", "icov6"):
+            assert np.array_equal(one[k], full[k][lo:hi]), k
+    h.close()
+
+
+def test_empty_and_errors():
+    from brutus_b200 import _lib
+    grid, labels = mock.make_grid(5_000, 5, seed=1400)
+    h = _lib.Handle(0, "f32")
+    with pytest.raises(_lib.BrutusCudaError):  # no grid yet
+        h.sweep_batch(np.ones((1, 5)), np.ones((1, 5)), np.ones((1, 5), bool))
+    h.set_grid(grid)
+    res = h.sweep_batch(np.zeros((0, 5)), np.zeros((0, 5)), np.zeros((0, 5), bool))
+    assert len(res["model_idx"]) == 0 and res["offsets"].tolist() == [0]
+    with pytest.raises(ValueError):
+        h.sweep_batch(np.ones((1, 5)), np.ones((1, 5)), np.ones((1, 5), bool),
+                      opts=_lib.make_options(init_thresh=0.5))
+    with pytest.raises(ValueError):
+        h.set_grid(np.zeros((10, 17, 3), np.float32))
+    h.close()
