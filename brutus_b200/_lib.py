@@ -30,7 +30,16 @@ class Options(C.Structure):
     _fields_ = [("avlim", C.c_double * 2), ("av_gauss", C.c_double * 2), ("rvlim", C.c_double * 2),
                 ("rv_gauss", C.c_double * 2), ("ltol", C.c_double), ("ltol_subthresh", C.c_double),
                 ("init_thresh", C.c_double), ("wt_thresh", C.c_double), ("dim_prior", C.c_int32),
-                ("max_iter", C.c_int32), ("apply_parallax_clip", C.c_int32), ("reserved", C.c_int32)]
+                ("max_iter", C.c_int32), ("apply_parallax_clip", C.c_int32), ("skip_d2h", C.c_int32)]
+
+
+class Records(C.Structure):
+    _fields_ = [("n", C.c_int64), ("stride", C.c_int64), ("elem_size", C.c_int32),
+                ("nrows", C.c_int32), ("model_idx", C.c_void_p), ("rows", C.c_void_p)]
+
+
+REC_BASIC, REC_FIT, REC_FULL = 3, 5, 11
+ROW_NAMES = ("lnl", "scale", "av", "chi2", "rv")
 
 
 class Stats(C.Structure):
@@ -70,9 +79,8 @@ def load():
     lib.bf_set_labels.argtypes = [vp, dp, C.c_int32]
     lib.bf_loglike_full.argtypes = [vp, dp, dp, u8p, C.c_double, C.c_double, op,
                                     dp, dp, dp, dp, dp, dp, u8p, i64p]
-    lib.bf_sweep_batch.argtypes = [vp, C.c_int64, dp, dp, u8p, dp, dp, dp, dp, op,
-                                   i32p, i32p, i64p, dp, i64p, C.c_int64, i64p,
-                                   i32p, dp, dp, dp, dp, dp, dp]
+    lib.bf_sweep_batch.argtypes = [vp, C.c_int64, dp, dp, u8p, dp, dp, dp, dp, op, C.c_int32,
+                                   i32p, i32p, i64p, dp, i64p, C.POINTER(Records)]
     lib.bf_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.bf_flush_l2.argtypes = [vp]
     lib.bf_device_count.restype = C.c_int
@@ -87,7 +95,7 @@ def _ptr(a, t):
 
 def make_options(avlim=(0., 20.), av_gauss=(0., 1e6), rvlim=(1., 8.), rv_gauss=(3.32, 0.18),
                  dim_prior=True, ltol=3e-2, ltol_subthresh=1e-2, init_thresh=5e-3, wt_thresh=1e-3,
-                 max_iter=0, apply_parallax_clip=True):
+                 max_iter=0, apply_parallax_clip=True, skip_d2h=False):
     if av_gauss is None:  # brutus/fitting.py:695-696
         av_gauss = (0., 1e6)
     o = Options()
@@ -99,6 +107,7 @@ def make_options(avlim=(0., 20.), av_gauss=(0., 1e6), rvlim=(1., 8.), rv_gauss=(
     o.wt_thresh = float(wt_thresh)
     o.dim_prior, o.max_iter = int(bool(dim_prior)), int(max_iter)
     o.apply_parallax_clip = int(bool(apply_parallax_clip))
+    o.skip_d2h = int(bool(skip_d2h))
     return o
 
 
@@ -191,8 +200,11 @@ class Handle:
         return lnl, chi2, sc, av, rv, icov, mclean.astype(bool), diag
 
     def sweep_batch(self, flux, err, mask, parallax=None, parallax_err=None, ext_mean=None,
-                    ext_std=None, opts=None, want_icov=True, capacity=None):
-        """B2 entry point; returns a dict of per-star arrays and CSR-compacted records."""
+                    ext_std=None, opts=None, rows=REC_FULL, copy=False):
+        """B2 entry point.  Returns per-star arrays plus the CSR-compacted records of the selected
+        models: ``model_idx, lnl, scale, av[, chi2, rv[, icov6 (6, n)]]``.  Unless ``copy`` is set
+        the record arrays are zero-copy views of the library's pinned result arena and are only
+        valid until the next ``sweep_batch`` call on this handle."""
         f = np.ascontiguousarray(flux, dtype=np.float64)
         e = np.ascontiguousarray(err, dtype=np.float64)
         m = np.ascontiguousarray(mask).astype(np.uint8)
@@ -214,26 +226,27 @@ class Handle:
         nsurv = np.zeros(ns, dtype=np.int64)
         mx = np.zeros(ns)
         offsets = np.zeros(ns + 1, dtype=np.int64)
-        cap = int(capacity) if capacity is not None else max(1024, 4096 * ns)
-        while True:
-            idx = np.empty(cap, dtype=np.int32)
-            lnl, chi2, sc, av, rv = (np.empty(cap) for _ in range(5))
-            icov = np.empty((cap, 6)) if want_icov else None
-            need = C.c_int64(0)
-            rc = self._lib.bf_sweep_batch(
-                self._h, ns, _ptr(f, C.c_double), _ptr(e, C.c_double), _ptr(m, C.c_uint8),
-                _ptr(par, C.c_double), _ptr(perr, C.c_double), _ptr(em, C.c_double),
-                _ptr(es, C.c_double), C.byref(opts), _ptr(ndim, C.c_int32), _ptr(nit, C.c_int32),
-                _ptr(nsurv, C.c_int64), _ptr(mx, C.c_double), _ptr(offsets, C.c_int64), cap,
-                C.byref(need), _ptr(idx, C.c_int32), _ptr(lnl, C.c_double), _ptr(chi2, C.c_double),
-                _ptr(sc, C.c_double), _ptr(av, C.c_double), _ptr(rv, C.c_double),
-                _ptr(icov, C.c_double))
-            if rc == BF_E_CAPACITY:
-                cap = int(need.value)
-                continue
-            self._check(rc)
-            break
-        n = int(need.value)
-        return dict(ndim=ndim, n_iter=nit, n_surv=nsurv, max_lnprob=mx, offsets=offsets,
-                    model_idx=idx[:n], lnl=lnl[:n], chi2=chi2[:n], scale=sc[:n], av=av[:n],
-                    rv=rv[:n], icov6=None if icov is None else icov[:n])
+        rec = Records()
+        self._check(self._lib.bf_sweep_batch(
+            self._h, ns, _ptr(f, C.c_double), _ptr(e, C.c_double), _ptr(m, C.c_uint8),
+            _ptr(par, C.c_double), _ptr(perr, C.c_double), _ptr(em, C.c_double),
+            _ptr(es, C.c_double), C.byref(opts), int(rows), _ptr(ndim, C.c_int32),
+            _ptr(nit, C.c_int32), _ptr(nsurv, C.c_int64), _ptr(mx, C.c_double),
+            _ptr(offsets, C.c_int64), C.byref(rec)))
+        n = int(rec.n)
+        out = dict(ndim=ndim, n_iter=nit, n_surv=nsurv, max_lnprob=mx, offsets=offsets)
+        dt = np.float32 if rec.elem_size == 4 else np.float64
+        if n > 0:
+            idx = np.ctypeslib.as_array(C.cast(rec.model_idx, C.POINTER(C.c_int32)), shape=(n,))
+            mat = np.ctypeslib.as_array(C.cast(rec.rows, C.POINTER(C.c_float if rec.elem_size == 4 else C.c_double)),
+                                        shape=(rec.nrows, int(rec.stride)))[:, :n]
+        else:
+            idx = np.zeros(0, dtype=np.int32)
+            mat = np.zeros((rec.nrows, 0), dtype=dt)
+        if copy:
+            idx, mat = idx.copy(), mat.copy()
+        out["model_idx"] = idx
+        for k, name in enumerate(ROW_NAMES[:min(5, rec.nrows)]):
+            out[name] = mat[k]
+        out["icov6"] = mat[5:11] if rec.nrows >= 11 else None
+        return out

@@ -65,7 +65,7 @@ __global__ void k_reset_red(typename Enc<T>::U* red, const int* list, int nlist,
 
 // lnl_p of the cull, same expression as kernels_nb.cuh::cull_lnl
 template <typename T> __device__ __forceinline__ T cull_lnl2(T chi2, T s, const T* __restrict__ srow) {
-    T dp = Num<T>::sqrt(s) - srow[SR_SC + SC_PAR];
+    T dp = Num<T>::sqrt_fast(s) - srow[SR_SC + SC_PAR];
     return T(-0.5) * fma(dp * dp, srow[SR_SC + SC_PIVAR], chi2);
 }
 
@@ -267,10 +267,9 @@ struct EngineBase {
                              uint8_t* mask_out, int64_t* diag) = 0;
     virtual int sweep_batch(int64_t nstar, const double* flux, const double* errv, const uint8_t* mask,
                             const double* par, const double* perr, const double* ext_mean,
-                            const double* ext_std, const bf_options* opt, int32_t* ndim,
+                            const double* ext_std, const bf_options* opt, int record_rows, int32_t* ndim,
                             int32_t* n_iter, int64_t* n_surv, double* max_lnprob, int64_t* offsets,
-                            int64_t capacity, int64_t* n_required, int32_t* model_idx, double* lnl,
-                            double* chi2, double* scale, double* av, double* rv, double* icov6) = 0;
+                            bf_records* out) = 0;
 };
 
 #define CK(call)                                                                               \
@@ -368,8 +367,11 @@ static void prep_star(const double* flux, const double* errv, const uint8_t* mas
 
 template <typename T> struct Engine : EngineBase {
     using U = typename Enc<T>::U;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
+    cudaEvent_t ev_rec[2] = {nullptr, nullptr}, ev_cp[2] = {nullptr, nullptr};
+    char* arena = nullptr;      // pinned host memory holding the records of the last bf_sweep_batch
+    int64_t arena_cap = 0;
     int64_t nmodel = 0, npad = 0;
     int nfilt = 0, ntile = 0, nlabel = 0;
     int batch_cap = 0;
@@ -382,7 +384,7 @@ template <typename T> struct Engine : EngineBase {
     DevBuf<int64_t> d_tot, d_base;
     DevBuf<U> d_red;
     DevBuf<double> d_out;
-    DevBuf<char> d_flush;
+    DevBuf<char> d_flush, d_stage[2];
 
     std::vector<T> h_stars, h_ext;
     std::vector<int> h_int, h_list;
@@ -398,6 +400,13 @@ template <typename T> struct Engine : EngineBase {
         if (ev1) cudaEventDestroy(ev1);
         if (evA) cudaEventDestroy(evA);
         if (evB) cudaEventDestroy(evB);
+        for (int k = 0; k < 2; k++) {
+            d_stage[k].release();
+            if (ev_rec[k]) cudaEventDestroy(ev_rec[k]);
+            if (ev_cp[k]) cudaEventDestroy(ev_cp[k]);
+        }
+        if (arena) cudaFreeHost(arena);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         if (stream) cudaStreamDestroy(stream);
     }
 
@@ -406,6 +415,11 @@ template <typename T> struct Engine : EngineBase {
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
         CK(cudaEventCreate(&evA)); CK(cudaEventCreate(&evB));
+        CK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; k++) {
+            CK(cudaEventCreateWithFlags(&ev_rec[k], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ev_cp[k], cudaEventDisableTiming));
+        }
         return BF_OK;
     }
 
@@ -733,14 +747,14 @@ template <typename T> struct Engine : EngineBase {
         if (rc) return rc;
         const size_t per = icov ? 14 : 5;
         CK(d_out.ensure((size_t)nmodel * per));
-        RecordParams<T> rp{};
+        RecordParams<T, double> rp{};
         rp.grid = d_grid.p; rp.npad = npad; rp.nmodel = nmodel; rp.stars = d_stars.p; rp.o = o; rp.st = state();
-        rp.sel_model = nullptr; rp.sel_star = nullptr; rp.nrec = 0; rp.star_slot = 0;
+        rp.sel_model = nullptr; rp.sel_star = nullptr; rp.nrec = 0; rp.star_slot = 0; rp.ld = 0; rp.nrows = 11; rp.o_idx = nullptr;
         double* b = d_out.p;
         rp.o_lnl = b; rp.o_chi2 = b + nmodel; rp.o_scale = b + 2 * nmodel; rp.o_av = b + 3 * nmodel; rp.o_rv = b + 4 * nmodel;
         rp.o_icov = icov ? b + 5 * nmodel : nullptr;
         phase_begin();
-        kt->records(rp, stream);
+        kt->records_full(rp, stream);
         stats.kernel_launches++;
         CK(cudaGetLastError());
         CK(cudaEventRecord(ev1, stream));
@@ -760,15 +774,34 @@ template <typename T> struct Engine : EngineBase {
         return BF_OK;
     }
 
+    // ---- library-owned pinned result arena: [11 rows of T x cap][idx int32 x cap] ----
+    int ensure_arena(int64_t need, int64_t written) {
+        if (need <= arena_cap) return BF_OK;
+        int64_t ncap = std::max<int64_t>(std::max<int64_t>(need + need / 4, 2 * arena_cap), (int64_t)1 << 20);
+        CK(cudaStreamSynchronize(copy_stream));
+        char* na = nullptr;
+        CK(cudaHostAlloc((void**)&na, (size_t)ncap * (sizeof(int) + 11 * sizeof(T)), cudaHostAllocPortable));
+        if (arena && written > 0) {
+            std::memcpy(na + (size_t)11 * ncap * sizeof(T), arena + (size_t)11 * arena_cap * sizeof(T),
+                        (size_t)written * sizeof(int));
+            for (int r = 0; r < 11; r++)
+                std::memcpy(na + (size_t)r * ncap * sizeof(T), arena + (size_t)r * arena_cap * sizeof(T),
+                            (size_t)written * sizeof(T));
+        }
+        if (arena) cudaFreeHost(arena);
+        arena = na;
+        arena_cap = ncap;
+        return BF_OK;
+    }
+
     int sweep_batch(int64_t nstar, const double* flux, const double* errv, const uint8_t* mask,
                     const double* par, const double* perr, const double* ext_mean, const double* ext_std,
-                    const bf_options* opt, int32_t* ndim, int32_t* n_iter, int64_t* n_surv, double* max_lnprob,
-                    int64_t* offsets, int64_t capacity, int64_t* n_required, int32_t* model_idx, double* lnl,
-                    double* chi2, double* scale, double* av, double* rv, double* icov6) override {
+                    const bf_options* opt, int record_rows, int32_t* ndim, int32_t* n_iter, int64_t* n_surv,
+                    double* max_lnprob, int64_t* offsets, bf_records* out) override {
         CK(cudaSetDevice(device));
         if (!kt) { err = "bf_sweep_batch: no grid (call bf_set_grid)"; return BF_E_NOGRID; }
-        if (nstar < 0 || !flux || !errv || !mask || !opt || !offsets || !n_required) { err = "bf_sweep_batch: null argument"; return BF_E_INVALID; }
-        if (capacity > 0 && (!model_idx || !lnl || !chi2 || !scale || !av || !rv)) { err = "bf_sweep_batch: null output buffer"; return BF_E_INVALID; }
+        if (nstar < 0 || (nstar > 0 && (!flux || !errv || !mask)) || !opt || !offsets || !out) { err = "bf_sweep_batch: null argument"; return BF_E_INVALID; }
+        if (record_rows != 3 && record_rows != 5 && record_rows != 11) { err = "bf_sweep_batch: record_rows must be 3, 5 or 11"; return BF_E_INVALID; }
         stats = bf_stats{};
         DevOpts<T> o; int max_iter;
         int rc = make_opts(opt, o, max_iter);
@@ -777,8 +810,8 @@ template <typename T> struct Engine : EngineBase {
         const PoolArrays<T> pl = pool();
         std::vector<int> nm(batch_cap), nf(batch_cap);
         std::vector<int64_t> nsv(batch_cap);
-        int64_t written = 0;   // records delivered (or, once capacity is exceeded, merely counted)
-        bool overflow = false;
+        int64_t written = 0;
+        int grp = 0;
         offsets[0] = 0;
         for (int64_t s0 = 0; s0 < nstar; s0 += batch_cap) {
             const int ns = (int)std::min<int64_t>(batch_cap, nstar - s0);
@@ -812,56 +845,69 @@ template <typename T> struct Engine : EngineBase {
                 offsets[s0 + s + 1] = offsets[s0 + s] + h_tot[s];
                 stats.selected += h_tot[s];
             }
-            // groups of stars whose records fit in the pool; each group -> k_write, k_records, D2H
+            // groups of stars whose records fit in the pool: k_write + k_records into a device staging
+            // buffer, then an asynchronous D2H on the copy stream that overlaps the next batch's compute
             int g0 = 0;
             while (g0 < ns) {
                 int g1 = g0;
                 int64_t tot = 0;
                 while (g1 < ns && (g1 == g0 || tot + h_tot[g1] <= pool_cap)) { h_base[g1] = tot; tot += h_tot[g1]; g1++; }
                 const int ng = g1 - g0;
-                if (written + tot > capacity) overflow = true;
-                if (!overflow && tot > 0) {
+                if (tot > 0) {
+                    const int buf = grp & 1;
+                    grp++;
+                    CK(cudaStreamWaitEvent(stream, ev_cp[buf], 0));  // staging buffer free again?
                     CK(cudaMemcpyAsync(d_base.p + g0, h_base.data() + g0, (size_t)ng * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
                     fp.list = d_list.p + g0; fp.nlist = ng;
                     phase_begin();
                     k_write<T, FLAG_SELECT><<<dim3(ntile, ng), kTile, 0, stream>>>(fp);
-                    CK(d_out.ensure((size_t)tot * 11));
-                    RecordParams<T> rp{};
+                    CK(d_stage[buf].ensure((size_t)tot * (sizeof(int) + 11 * sizeof(T))));
+                    RecordParams<T, T> rp{};
                     rp.grid = d_grid.p; rp.npad = npad; rp.nmodel = nmodel; rp.stars = d_stars.p; rp.o = o; rp.st = st;
                     rp.sel_model = pl.model; rp.sel_star = pl.star; rp.nrec = tot; rp.star_slot = 0;
-                    double* b = d_out.p;
-                    rp.o_lnl = b; rp.o_chi2 = b + tot; rp.o_scale = b + 2 * tot; rp.o_av = b + 3 * tot;
-                    rp.o_rv = b + 4 * tot; rp.o_icov = icov6 ? b + 5 * tot : nullptr;
+                    T* b = (T*)d_stage[buf].p;                                   // [11][tot] rows, then idx
+                    rp.o_idx = (int*)(d_stage[buf].p + (size_t)11 * tot * sizeof(T));
+                    rp.ld = tot; rp.nrows = record_rows;
+                    rp.o_lnl = b; rp.o_scale = b + tot; rp.o_av = b + 2 * tot; rp.o_chi2 = b + 3 * tot;
+                    rp.o_rv = b + 4 * tot; rp.o_icov = b + 5 * tot;
                     kt->records(rp, stream);
                     stats.kernel_launches += 2;
                     CK(cudaGetLastError());
-                    CK(cudaEventRecord(ev1, stream));
-                    stats.ms_select += phase_end();
-                    const size_t nb = (size_t)tot * sizeof(double);
-                    CK(cudaMemcpy(model_idx + written, pl.model, (size_t)tot * sizeof(int), cudaMemcpyDeviceToHost));
-                    CK(cudaMemcpy(lnl + written, rp.o_lnl, nb, cudaMemcpyDeviceToHost));
-                    CK(cudaMemcpy(chi2 + written, rp.o_chi2, nb, cudaMemcpyDeviceToHost));
-                    CK(cudaMemcpy(scale + written, rp.o_scale, nb, cudaMemcpyDeviceToHost));
-                    CK(cudaMemcpy(av + written, rp.o_av, nb, cudaMemcpyDeviceToHost));
-                    CK(cudaMemcpy(rv + written, rp.o_rv, nb, cudaMemcpyDeviceToHost));
-                    if (icov6) CK(cudaMemcpy(icov6 + written * 6, rp.o_icov, nb * 6, cudaMemcpyDeviceToHost));
-                    stats.d2h_bytes += (size_t)tot * (sizeof(int) + (icov6 ? 11 : 5) * sizeof(double));
-                } else {
-                    CK(cudaEventRecord(ev1, stream));
-                    CK(cudaStreamSynchronize(stream));
+                    CK(cudaEventRecord(ev_rec[buf], stream));
+                    CK(cudaEventRecord(evB, stream));
+                    if (!opt->skip_d2h) {
+                    rc = ensure_arena(written + tot, written);
+                    if (rc) return rc;
+                    CK(cudaStreamWaitEvent(copy_stream, ev_rec[buf], 0));
+                    CK(cudaMemcpyAsync(arena + (size_t)11 * arena_cap * sizeof(T) + (size_t)written * sizeof(int),
+                                       rp.o_idx, (size_t)tot * sizeof(int), cudaMemcpyDeviceToHost, copy_stream));
+                    CK(cudaMemcpy2DAsync(arena + (size_t)written * sizeof(T),
+                                         (size_t)arena_cap * sizeof(T), b, (size_t)tot * sizeof(T),
+                                         (size_t)tot * sizeof(T), record_rows, cudaMemcpyDeviceToHost, copy_stream));
+                    CK(cudaEventRecord(ev_cp[buf], copy_stream));
+                    stats.d2h_bytes += (size_t)tot * (sizeof(int) + record_rows * sizeof(T));
+                    }
+                    CK(cudaEventSynchronize(evB));
+                    float msr = 0.f;
+                    CK(cudaEventElapsedTime(&msr, evA, evB));
+                    stats.ms_select += msr;
                 }
                 written += tot;
                 g0 = g1;
             }
+            CK(cudaEventRecord(ev1, stream));
+            CK(cudaEventSynchronize(ev1));
             float ms = 0.f;
             CK(cudaEventElapsedTime(&ms, ev0, ev1));
             stats.ms_device += ms;
         }
-        *n_required = written;
-        if (overflow) {
-            err = "bf_sweep_batch: compacted output capacity too small (see n_required)";
-            return BF_E_CAPACITY;
-        }
+        CK(cudaStreamSynchronize(copy_stream));
+        out->n = opt->skip_d2h ? 0 : written;
+        out->stride = arena_cap;
+        out->elem_size = (int32_t)sizeof(T);
+        out->nrows = record_rows;
+        out->model_idx = arena ? (const int32_t*)(arena + (size_t)11 * arena_cap * sizeof(T)) : nullptr;
+        out->rows = (const void*)arena;
         return BF_OK;
     }
 };
@@ -884,7 +930,7 @@ void bf_default_options(bf_options* o) {
     o->rvlim[0] = 1.; o->rvlim[1] = 8.;
     o->rv_gauss[0] = 3.32; o->rv_gauss[1] = 0.18;
     o->ltol = 3e-2; o->ltol_subthresh = 1e-2; o->init_thresh = 5e-3; o->wt_thresh = 1e-3;
-    o->dim_prior = 1; o->max_iter = 0; o->apply_parallax_clip = 1; o->reserved = 0;
+    o->dim_prior = 1; o->max_iter = 0; o->apply_parallax_clip = 1; o->skip_d2h = 0;
 }
 
 int bf_device_count(void) {
@@ -952,14 +998,11 @@ int bf_loglike_full(bf_handle* h, const double* flux, const double* err, const u
 
 int bf_sweep_batch(bf_handle* h, int64_t nstar, const double* flux, const double* err, const uint8_t* mask,
                    const double* parallax, const double* parallax_err, const double* ext_mean,
-                   const double* ext_std, const bf_options* opt, int32_t* ndim, int32_t* n_iter,
-                   int64_t* n_surv, double* max_lnprob, int64_t* offsets, int64_t capacity,
-                   int64_t* n_required, int32_t* model_idx, double* lnl, double* chi2, double* scale,
-                   double* av, double* rv, double* icov6) {
+                   const double* ext_std, const bf_options* opt, int32_t record_rows, int32_t* ndim,
+                   int32_t* n_iter, int64_t* n_surv, double* max_lnprob, int64_t* offsets, bf_records* out) {
     if (!h) return BF_E_INVALID;
-    return h->eng->sweep_batch(nstar, flux, err, mask, parallax, parallax_err, ext_mean, ext_std, opt, ndim,
-                               n_iter, n_surv, max_lnprob, offsets, capacity, n_required, model_idx, lnl, chi2,
-                               scale, av, rv, icov6);
+    return h->eng->sweep_batch(nstar, flux, err, mask, parallax, parallax_err, ext_mean, ext_std, opt,
+                               record_rows, ndim, n_iter, n_surv, max_lnprob, offsets, out);
 }
 
 int bf_flush_l2(bf_handle* h) {

@@ -104,6 +104,9 @@ template <> struct Num<float> {
     __device__ static float exp2(float x) { return exp2f(x); }          // MUFU.EX2
     __device__ static float log(float x) { return __logf(x); }          // MUFU.LG2 * ln2
     __device__ static float sqrt(float x) { return sqrtf(x); }
+    __device__ static float sqrt_fast(float x) { return x * rsqrtf(x); }   // x > 0 (scale >= 1e-20)
+    __device__ static float max(float a, float b) { return fmaxf(a, b); }  // FMNMX
+    __device__ static float min(float a, float b) { return fminf(a, b); }
     __device__ static float div_fast(float a, float b) { return __fdividef(a, b); }
     __device__ static float div(float a, float b) { return a / b; }
     __device__ static float neg_inf() { return -CUDART_INF_F; }
@@ -114,6 +117,9 @@ template <> struct Num<double> {
     __device__ static double exp2(double x) { return ::exp2(x); }
     __device__ static double log(double x) { return ::log(x); }
     __device__ static double sqrt(double x) { return ::sqrt(x); }
+    __device__ static double sqrt_fast(double x) { return ::sqrt(x); }
+    __device__ static double max(double a, double b) { return a > b ? a : b; }
+    __device__ static double min(double a, double b) { return a < b ? a : b; }
     __device__ static double div_fast(double a, double b) { return a / b; }
     __device__ static double div(double a, double b) { return a / b; }
     __device__ static double neg_inf() { return -CUDART_INF; }
@@ -181,7 +187,9 @@ template <typename T> struct FluxParams {
     typename Enc<T>::U* red;
 };
 
-template <typename T> struct RecordParams {
+// O = element type of the outputs: double for the full-length B1 arrays (the reference returns
+// float64), T for the compacted B2 records (no point shipping more bits than were computed).
+template <typename T, typename O> struct RecordParams {
     const float* grid;
     int64_t npad, nmodel;
     const T* stars;
@@ -193,15 +201,20 @@ template <typename T> struct RecordParams {
     int64_t nrec;
     // mode B (full-length, one star slot): sel_model == nullptr
     int star_slot;
-    // float64 outputs
-    double *o_lnl, *o_chi2, *o_scale, *o_av, *o_rv, *o_icov;  // icov: 6 per record (A) or 9 per model (B)
+    // outputs.  Mode A: rows of a [11][ld] matrix: lnl, scale, av, chi2, rv, icov(ss,sa,sr,aa,ar,rr);
+    // only the first `nrows` are produced (3, 5 or 11).  Mode B: separate arrays, icov 9 per model.
+    O *o_lnl, *o_chi2, *o_scale, *o_av, *o_rv, *o_icov;
+    int64_t ld;
+    int nrows;
+    int* o_idx;   // mode A: copy of sel_model next to the rows (the pool is reused by the next batch)
 };
 
 // Kernel launchers instantiated once per band count (inst.cu, -DBF_NB=n).
 template <typename T> struct KTable {
     void (*magfit)(const SweepParams<T>&, cudaStream_t);
     void (*flux)(const FluxParams<T>&, cudaStream_t);
-    void (*records)(const RecordParams<T>&, cudaStream_t);
+    void (*records)(const RecordParams<T, T>&, cudaStream_t);          // compacted records (B2)
+    void (*records_full)(const RecordParams<T, double>&, cudaStream_t); // full-length float64 (B1)
 };
 
 }  // namespace bf

@@ -63,13 +63,15 @@ __device__ __forceinline__ void mle_from_resid(const T (&e)[NB], T c, const T* _
         num = fma(gb, srow[SR_AL + j], num);
         den = fma(gb, gb, den);
     }
-    T E = Num<T>::exp2(T(kC2) * c);
-    T shat = Num<T>::div(num, den);
-    T s = Num<T>::div(shat, E);
-    if (s <= T(1e-20)) {  // brutus/fitting.py:517-518
-        s = T(1e-20);
-        shat = s * E;
-    }
+    // shat = num/den may use the approximate reciprocal: chi2 is stationary in shat at the MLE
+    // (sum t_j gb_j = 0), so a 2-ulp error in shat enters chi2 only at second order.
+    const T E = Num<T>::exp2(T(kC2) * c);
+    const T Einv = Num<T>::exp2(T(-kC2) * c);
+    T shat = Num<T>::div_fast(num, den);
+    T s = shat * Einv;
+    const bool floor_s = s <= T(1e-20);  // brutus/fitting.py:517-518
+    s = floor_s ? T(1e-20) : s;
+    shat = floor_s ? T(1e-20) * E : shat;
     T chi2 = T(0);
 #pragma unroll
     for (int j = 0; j < NB; j++) {
@@ -82,7 +84,7 @@ __device__ __forceinline__ void mle_from_resid(const T (&e)[NB], T c, const T* _
 // lnl_p of the cull (brutus/fitting.py:747-756): -chi2/2 - (sqrt(s) - parallax)^2 / (2 parallax_err^2)
 template <typename T>
 __device__ __forceinline__ T cull_lnl(T chi2, T s, const T* __restrict__ srow) {
-    T dp = Num<T>::sqrt(s) - srow[SR_SC + SC_PAR];
+    T dp = Num<T>::sqrt_fast(s) - srow[SR_SC + SC_PAR];
     return T(-0.5) * fma(dp * dp, srow[SR_SC + SC_PIVAR], chi2);
 }
 
@@ -96,9 +98,81 @@ __device__ __forceinline__ T cull_lnl(T chi2, T s, const T* __restrict__ srow) {
 // max-reductions per iteration:  "err < tol"  <=>  max{logwt_i : max(|dAv_i|,|dRv_i|) >= tol} <=
 // max logwt + ln(init_thresh).
 // =================================================================================================
+// One (Av, Rv) update of the magnitude fit for one (model, star): brutus/fitting.py:174-243.
+// Carries gs = sum e' u between iterations; gs2 and the post-update gs follow algebraically from
+// the updates (e' -= dA r; e' -= A dR D) instead of being re-summed over the bands.
+template <typename T, int NB>
+__device__ __forceinline__ void mag_iter(const ModelRegs<T, NB>& m, const DevOpts<T>& o,
+                                         const T* __restrict__ srow, T S, T c, T Q, T Tm, T (&e)[NB],
+                                         T (&r)[NB], T& A, T& rho, T& gs, T& ell, T& delta) {
+    // --- solve for Av (:176-204) ---
+    T a = o.PA, b = T(0), ga = (o.Abar - A) * o.PA;
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+        T ru = r[j] * srow[SR_U + j];
+        a = fma(ru, r[j], a);
+        b += ru;
+        ga = fma(ru, e[j], ga);
+    }
+    T dA = Num<T>::div_fast(S * ga - b * gs, S * a - b * b);
+    dA = Num<T>::max(dA, o.avmin - A);
+    dA = Num<T>::min(dA, o.avmax - A);
+    A += dA;
+    // --- solve for Rv (:206-237) ---
+    const T gs2 = fma(-dA, b, gs);             // sum (e' - dA r) u
+    T gr = T(0);
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+        e[j] = fma(-dA, r[j], e[j]);
+        gr = fma(e[j] * srow[SR_U + j], m.D[j], gr);
+    }
+    gr = fma(gr, A, (o.Rbar - rho) * o.PR);
+    const T q = fma(Q * A, A, o.PR);
+    const T tt = Tm * A;
+    T dR = Num<T>::div_fast(S * gr - tt * gs2, S * q - tt * tt);
+    dR = Num<T>::max(dR, o.rvmin - rho);
+    dR = Num<T>::min(dR, o.rvmax - rho);
+    rho += dR;
+    // --- update residuals / reddening vector, chi2 in magnitudes (:235-243) ---
+    const T AdR = A * dR;
+    gs = fma(-AdR, Tm, gs2);                   // sum (e' - A dR D) u
+    T chi = T(0);
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+        e[j] = fma(-AdR, m.D[j], e[j]);
+        r[j] = fma(dR, m.D[j], r[j]);
+        chi = fma(e[j] * srow[SR_U + j], e[j], chi);
+    }
+    // logwt uses the un-centred residual e = e' + c (reference quirk)
+    ell = T(-0.5) * (chi + c * (T(2) * gs + c * S));
+    delta = Num<T>::max(tabs(dA), tabs(dR));
+}
+
+// warp-wide max.  float: one CREDUX.MAX.F32 (sm_100a redux.sync on f32; NaN inputs are ignored);
+// double: shuffle butterfly.
+__device__ __forceinline__ float warp_max_fast(float v) {
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ double warp_max_fast(double v) { return warp_max((v == v) ? v : -CUDART_INF); }
+
+// =================================================================================================
+// Kernel 1: full-grid magnitude-space fit (brutus/fitting.py:728-741 -> _optimize_fit_mag :34-271,
+// then _get_sed_mle :267 and the cull statistic :745-756) for a list of stars.
+// grid = (model tiles, star chunks); each thread keeps its model in registers and loops over the
+// chunk's stars, whose rows sit in shared memory (broadcast reads).
+// The number of mag iterations applied to every model of a star is a grid-wide decision in the
+// reference (:246-263).  It is speculated here (SI_KSPEC) and verified afterwards from two plain
+// max-reductions per iteration:  "err < tol"  <=>  max{logwt_i : max(|dAv_i|,|dRv_i|) >= tol} <=
+// max logwt + ln(init_thresh).
+// Per-star reductions: lane s of every warp keeps the warp's five maxima for star s of the chunk
+// (kStarChunk == 32), so the star loop contains no shared-memory atomics.
+// =================================================================================================
 template <typename T, int NB>
 __global__ void __launch_bounds__(kTile) k_magfit(const SweepParams<T> p) {
     using U = typename Enc<T>::U;
+    static_assert(kStarChunk == 32, "lane <-> star mapping of the reductions");
     __shared__ T s_star[kStarChunk][kStarStride];
     __shared__ int s_slot[kStarChunk];
     __shared__ int s_kspec[kStarChunk];
@@ -115,7 +189,7 @@ __global__ void __launch_bounds__(kTile) k_magfit(const SweepParams<T> p) {
         s_slot[t] = slot;
         s_kspec[t] = p.star_int[slot * SI_COUNT + SI_KSPEC];
     }
-    for (int t = threadIdx.x; t < nst * 5; t += kTile) s_red[t / 5][t % 5] = Enc<T>::enc(Num<T>::neg_inf());
+    for (int t = threadIdx.x; t < kStarChunk * 5; t += kTile) s_red[t / 5][t % 5] = Enc<T>::enc(Num<T>::neg_inf());
     __syncthreads();
 
     const int64_t i = (int64_t)blockIdx.x * kTile + threadIdx.x;  // npad is a multiple of kTile
@@ -124,6 +198,8 @@ __global__ void __launch_bounds__(kTile) k_magfit(const SweepParams<T> p) {
     ModelRegs<T, NB> m;
     load_model<T, NB>(p.grid, p.npad, i, o, m);
     const int lane = threadIdx.x & 31;
+    const T ninf = Num<T>::neg_inf();
+    T acc0 = ninf, acc1 = ninf, acc2 = ninf, acc3 = ninf, acc4 = ninf;  // lane s <-> star s
 
     for (int s = 0; s < nst; s++) {
         const T* __restrict__ srow = s_star[s];
@@ -145,72 +221,32 @@ __global__ void __launch_bounds__(kTile) k_magfit(const SweepParams<T> p) {
             gs = fma(e[j], u, gs);
         }
         T ell = T(0), delta = T(0);
-        for (int k = 1; k <= kspec; k++) {
-            // --- solve for Av (:176-204) ---
-            T a = o.PA, b = T(0), ga = (o.Abar - A) * o.PA;
-#pragma unroll
-            for (int j = 0; j < NB; j++) {
-                T ru = r[j] * srow[SR_U + j];
-                a = fma(ru, r[j], a);
-                b += ru;
-                ga = fma(ru, e[j], ga);
-            }
-            T dA = Num<T>::div_fast(S * ga - b * gs, S * a - b * b);
-            dA = tmax(dA, o.avmin - A);
-            dA = tmin(dA, o.avmax - A);
-            A += dA;
-            // --- solve for Rv (:206-237) ---
-            T gr = T(0), gs2 = T(0);
-#pragma unroll
-            for (int j = 0; j < NB; j++) {
-                e[j] = fma(-dA, r[j], e[j]);
-                T eu = e[j] * srow[SR_U + j];
-                gs2 += eu;
-                gr = fma(eu, m.D[j], gr);
-            }
-            gr = fma(gr, A, (o.Rbar - rho) * o.PR);
-            T q = fma(Q * A, A, o.PR);
-            T tt = Tm * A;
-            T dR = Num<T>::div_fast(S * gr - tt * gs2, S * q - tt * tt);
-            dR = tmax(dR, o.rvmin - rho);
-            dR = tmin(dR, o.rvmax - rho);
-            rho += dR;
-            // --- update residuals / reddening vector, chi2 in magnitudes (:235-243) ---
-            const T AdR = A * dR;
-            T chi = T(0);
-            gs = T(0);
-#pragma unroll
-            for (int j = 0; j < NB; j++) {
-                e[j] = fma(-AdR, m.D[j], e[j]);
-                r[j] = fma(dR, m.D[j], r[j]);
-                T eu = e[j] * srow[SR_U + j];
-                gs += eu;
-                chi = fma(eu, e[j], chi);
-            }
-            // logwt uses the un-centred residual e = e' + c (reference quirk)
-            ell = T(-0.5) * (chi + c * (T(2) * gs + c * S));
-            delta = tmax(tabs(dA), tabs(dR));
-            if (k >= kspec - 1) {
-                T v1 = (valid && ell == ell) ? ell : Num<T>::neg_inf();
-                T v2 = (delta >= o.mtol) ? v1 : Num<T>::neg_inf();
-                v1 = warp_max(v1);
-                v2 = warp_max(v2);
-                if (lane == 0) {
-                    const int base = (k == kspec) ? 2 : 0;
-                    atomicMax(&s_red[s][base], Enc<T>::enc(v1));
-                    atomicMax(&s_red[s][base + 1], Enc<T>::enc(v2));
+        T l0 = ninf, b0 = ninf, l1, b1;
+        if (kspec == 2) {   // the common case, fully unrolled
+            mag_iter<T, NB>(m, o, srow, S, c, Q, Tm, e, r, A, rho, gs, ell, delta);
+            l0 = valid ? ell : ninf;
+            b0 = (delta >= o.mtol) ? l0 : ninf;
+            mag_iter<T, NB>(m, o, srow, S, c, Q, Tm, e, r, A, rho, gs, ell, delta);
+        } else {
+            for (int k = 1; k <= kspec; k++) {
+                mag_iter<T, NB>(m, o, srow, S, c, Q, Tm, e, r, A, rho, gs, ell, delta);
+                if (k == kspec - 1) {
+                    l0 = valid ? ell : ninf;
+                    b0 = (delta >= o.mtol) ? l0 : ninf;
                 }
             }
         }
+        l1 = valid ? ell : ninf;
+        b1 = (delta >= o.mtol) ? l1 : ninf;
         // --- _get_sed_mle at the fitted (Av, Rv) (:267) and the cull statistic (:745-756) ---
         Mle<T, NB> r4;
         mle_from_resid<T, NB>(e, c, srow, r4);
         T lp = cull_lnl(r4.chi2, r4.s, srow);
-        {
-            T v = (valid && lp == lp) ? lp : Num<T>::neg_inf();
-            v = warp_max(v);
-            if (lane == 0) atomicMax(&s_red[s][4], Enc<T>::enc(v));
-        }
+        lp = valid ? lp : ninf;
+        l0 = warp_max_fast(l0); b0 = warp_max_fast(b0);
+        l1 = warp_max_fast(l1); b1 = warp_max_fast(b1);
+        lp = warp_max_fast(lp);
+        if (lane == s) { acc0 = l0; acc1 = b0; acc2 = l1; acc3 = b1; acc4 = lp; }
         if (valid) {
             const int64_t off = (int64_t)s_slot[s] * p.npad + i;
             p.st.chi2[off] = r4.chi2;
@@ -219,6 +255,14 @@ __global__ void __launch_bounds__(kTile) k_magfit(const SweepParams<T> p) {
             p.st.av[off] = A;
             p.st.rv[off] = rho;
         }
+    }
+    // NaN maxima (every lane NaN) must not poison the unsigned-encoded atomics
+    if (lane < nst) {
+        if (acc0 == acc0) atomicMax(&s_red[lane][0], Enc<T>::enc(acc0));
+        if (acc1 == acc1) atomicMax(&s_red[lane][1], Enc<T>::enc(acc1));
+        if (acc2 == acc2) atomicMax(&s_red[lane][2], Enc<T>::enc(acc2));
+        if (acc3 == acc3) atomicMax(&s_red[lane][3], Enc<T>::enc(acc3));
+        if (acc4 == acc4) atomicMax(&s_red[lane][4], Enc<T>::enc(acc4));
     }
     __syncthreads();
     for (int t = threadIdx.x; t < nst * 5; t += kTile) {
@@ -329,12 +373,13 @@ __global__ void __launch_bounds__(kTile) k_flux(const FluxParams<T> p) {
 // writes float64 outputs.  Mode A: compacted records of the selected models (6 unique icov entries);
 // mode B: every model of one star (9 entries, the layout loglike returns).
 // =================================================================================================
-template <typename T, int NB>
-__global__ void __launch_bounds__(kTile) k_records(const RecordParams<T> p) {
+template <typename T, int NB, typename O>
+__global__ void __launch_bounds__(kTile) k_records(const RecordParams<T, O> p) {
     const int64_t q = (int64_t)blockIdx.x * kTile + threadIdx.x;
     int slot;
     int64_t i;
-    if (p.sel_model) {
+    const bool modeA = p.sel_model != nullptr;
+    if (modeA) {
         if (q >= p.nrec) return;
         slot = p.sel_star[q];
         i = p.sel_model[q];
@@ -346,10 +391,28 @@ __global__ void __launch_bounds__(kTile) k_records(const RecordParams<T> p) {
     const DevOpts<T> o = p.o;
     const T* __restrict__ srow = p.stars + (int64_t)slot * kStarStride;
     const int64_t off = (int64_t)slot * p.npad + i;
+    const T A = p.st.av[off], rho = p.st.rv[off];
+    if (modeA) {
+        p.o_idx[q] = (int)i;
+        p.o_lnl[q] = (O)p.st.lnl[off];
+        p.o_scale[q] = (O)p.st.scale[off];
+        p.o_av[q] = (O)A;
+        if (p.nrows > 3) {
+            p.o_chi2[q] = (O)p.st.chi2[off];
+            p.o_rv[q] = (O)rho;
+        }
+        if (p.nrows <= 5) return;
+    } else {
+        p.o_lnl[q] = (O)p.st.lnl[off];
+        p.o_chi2[q] = (O)p.st.chi2[off];
+        p.o_scale[q] = (O)p.st.scale[off];
+        p.o_av[q] = (O)A;
+        p.o_rv[q] = (O)rho;
+        if (!p.o_icov) return;
+    }
     ModelRegs<T, NB> m;
     load_model<T, NB>(p.grid, p.npad, i, o, m);
     const T c = srow[SR_SC + SC_MBAR] - m.bbar;
-    const T A = p.st.av[off], rho = p.st.rv[off];
     T e[NB], r[NB];
     Mle<T, NB> r4;
     resid_at<T, NB>(m, o, srow, A, rho, e, r);
@@ -369,25 +432,18 @@ __global__ void __launch_bounds__(kTile) k_records(const RecordParams<T> p) {
         aden = fma(rM, rM, aden);
         rden = fma(DM, DM, rden);
     }
-    const double f = kFac;
-    const double ss = (double)r4.den * (double)r4.E * (double)r4.E;
-    const double dsa = f * (double)r4.E * (double)sa, dsr = f * (double)r4.E * (double)sr;
-    const double dar = f * (double)ar;
-    const double daa = f * f * (double)aden + (double)o.PA + 1. / (0.05 * 0.05);
-    const double drr = f * f * (double)rden + (double)o.PR + 1. / (0.1 * 0.1);
-    p.o_lnl[q] = (double)p.st.lnl[off];
-    p.o_chi2[q] = (double)p.st.chi2[off];
-    p.o_scale[q] = (double)p.st.scale[off];
-    p.o_av[q] = (double)A;
-    p.o_rv[q] = (double)rho;
-    if (p.o_icov) {
-        if (p.sel_model) {
-            double* w = p.o_icov + q * 6;
-            w[0] = ss; w[1] = dsa; w[2] = dsr; w[3] = daa; w[4] = dar; w[5] = drr;
-        } else {
-            double* w = p.o_icov + q * 9;
-            w[0] = ss; w[1] = dsa; w[2] = dsr; w[3] = dsa; w[4] = daa; w[5] = dar; w[6] = dsr; w[7] = dar; w[8] = drr;
-        }
+    const O f = (O)kFac, E = (O)r4.E;
+    const O ss = (O)r4.den * E * E;
+    const O dsa = f * E * (O)sa, dsr = f * E * (O)sr;
+    const O dar = f * (O)ar;
+    const O daa = f * f * (O)aden + (O)o.PA + (O)(1. / (0.05 * 0.05));
+    const O drr = f * f * (O)rden + (O)o.PR + (O)(1. / (0.1 * 0.1));
+    if (modeA) {
+        O* w = p.o_icov + q;
+        w[0] = ss; w[p.ld] = dsa; w[2 * p.ld] = dsr; w[3 * p.ld] = daa; w[4 * p.ld] = dar; w[5 * p.ld] = drr;
+    } else {
+        O* w = p.o_icov + q * 9;
+        w[0] = ss; w[1] = dsa; w[2] = dsr; w[3] = dsa; w[4] = daa; w[5] = dar; w[6] = dsr; w[7] = dar; w[8] = drr;
     }
 }
 
@@ -400,10 +456,10 @@ template <typename T, int NB> void launch_flux(const FluxParams<T>& p, cudaStrea
     if (p.nsv <= 0) return;
     k_flux<T, NB><<<(unsigned)((p.nsv + kTile - 1) / kTile), kTile, 0, st>>>(p);
 }
-template <typename T, int NB> void launch_records(const RecordParams<T>& p, cudaStream_t st) {
+template <typename T, int NB, typename O> void launch_records(const RecordParams<T, O>& p, cudaStream_t st) {
     int64_t n = p.sel_model ? p.nrec : p.nmodel;
     if (n <= 0) return;
-    k_records<T, NB><<<(unsigned)((n + kTile - 1) / kTile), kTile, 0, st>>>(p);
+    k_records<T, NB, O><<<(unsigned)((n + kTile - 1) / kTile), kTile, 0, st>>>(p);
 }
 
 }  // namespace bf

@@ -24,7 +24,7 @@ extern "C" {
 #define BF_E_INVALID (-1)   /* bad argument (message says which)                          */
 #define BF_E_CUDA (-2)      /* CUDA runtime error                                          */
 #define BF_E_NOGRID (-3)    /* sweep requested before bf_set_grid                           */
-#define BF_E_CAPACITY (-4)  /* caller's compacted-output buffers too small; see n_required */
+#define BF_E_CAPACITY (-4)  /* reserved */
 #define BF_E_THRESH (-5)    /* init_thresh > ltol_subthresh (ValueError at brutus/fitting.py:691-693) */
 #define BF_E_NOMEM (-6)
 
@@ -55,7 +55,7 @@ typedef struct bf_options {
     int32_t max_iter;       /* cap on mag/flux loop iterations (reference: unbounded); 0 = 64 */
     int32_t apply_parallax_clip; /* 1: lnpost's rough parallax prior (fitting.py:976-980) is applied
                                     before thresholding; 0 mimics lnpost(parallax=None) */
-    int32_t reserved;
+    int32_t skip_d2h;       /* bf_sweep_batch: leave the records on the device (device-only timing) */
 } bf_options;
 
 /* Per-call statistics (device times from CUDA events on the handle's stream). */
@@ -103,26 +103,40 @@ int bf_loglike_full(bf_handle* h, const double* flux, const double* err, const u
                     double* lnl, double* chi2, double* scale, double* av, double* rv, double* icov,
                     uint8_t* mask_clean_out, int64_t* diag);
 
+/* Compacted records of the selected models, in pinned host memory OWNED BY THE LIBRARY: valid until
+ * the next bf_sweep_batch on the handle or bf_destroy.  rows is a [nrows][stride] matrix of
+ * float32 (BF_PRECISION_F32 handles) or float64 (BF_PRECISION_F64): row 0 lnl (incl. lnprior_ext),
+ * 1 scale, 2 av, 3 chi2, 4 rv, 5..10 the unique entries (ss, sa, sr, aa, ar, rr) of the symmetric
+ * precision matrix icov_sar (brutus/fitting.py:563-574).  Only the first nrows rows are filled. */
+typedef struct bf_records {
+    int64_t n;                /* records delivered                        */
+    int64_t stride;           /* elements between consecutive rows         */
+    int32_t elem_size;        /* 4 or 8                                    */
+    int32_t nrows;            /* BF_REC_BASIC, BF_REC_FIT or BF_REC_FULL   */
+    const int32_t* model_idx; /* [n], ascending within each star           */
+    const void* rows;
+} bf_records;
+#define BF_REC_BASIC 3   /* lnl, scale, av        */
+#define BF_REC_FIT 5     /* + chi2, rv            */
+#define BF_REC_FULL 11   /* + icov_sar            */
+
 /* B2: many stars, compacted outputs -- the per-star body of BruteForce._fit
  * (brutus/fitting.py:1980-2009: loglike + lnprior_ext) fused with lnpost's first stage (:976-991:
  * rough parallax prior, -1e300 clean-up, selection lnprob > max + ln wt_thresh).
  *   flux, err      [nstar*nfilt] float64;  mask [nstar*nfilt] uint8
  *   parallax, parallax_err [nstar] float64 (NaN = none); either may be NULL (= all NaN)
  *   ext_mean, ext_std [nstar*nlabel] float64 or NULL (lnprior_ext; needs bf_set_labels)
- * per-star outputs (each may be NULL): ndim [nstar] int32, n_iter [nstar*2] int32 (mag, flux loop
- *   iterations), n_surv [nstar] int64 (survivors of the cull), max_lnprob [nstar] float64
- * compacted outputs, CSR over stars: offsets [nstar+1] int64; for k in [offsets[s], offsets[s+1]):
- *   model_idx (int32, ascending), lnl (incl. lnprior_ext), chi2, scale, av, rv float64,
- *   icov6 float64 x6 = (ss, sa, sr, aa, ar, rr) of the symmetric precision matrix (:563-574).
- * capacity = number of records the compacted buffers can hold.  If more are needed the call
- * returns BF_E_CAPACITY with *n_required set; nothing else is valid then. */
+ *   record_rows    BF_REC_*: how much of each record to compute and ship
+ * per-star outputs (each may be NULL except offsets): ndim [nstar] int32, n_iter [nstar*2] int32
+ *   (mag, flux loop iterations), n_surv [nstar] int64 (survivors of the cull), max_lnprob [nstar]
+ *   float64, offsets [nstar+1] int64: records of star s are [offsets[s], offsets[s+1]) of *out.
+ * Stars are processed in batches; the device->host copy of one batch's records (copy stream, pinned
+ * memory) overlaps the next batch's kernels. */
 int bf_sweep_batch(bf_handle* h, int64_t nstar, const double* flux, const double* err,
                    const uint8_t* mask, const double* parallax, const double* parallax_err,
                    const double* ext_mean, const double* ext_std, const bf_options* opt,
-                   int32_t* ndim, int32_t* n_iter, int64_t* n_surv, double* max_lnprob,
-                   int64_t* offsets, int64_t capacity, int64_t* n_required,
-                   int32_t* model_idx, double* lnl, double* chi2, double* scale, double* av,
-                   double* rv, double* icov6);
+                   int32_t record_rows, int32_t* ndim, int32_t* n_iter, int64_t* n_surv,
+                   double* max_lnprob, int64_t* offsets, bf_records* out);
 
 /* Statistics of the most recent bf_loglike_full / bf_sweep_batch call on this handle. */
 int bf_get_stats(const bf_handle* h, bf_stats* out);

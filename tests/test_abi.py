@@ -35,6 +35,7 @@ def test_struct_layout_matches_header(lib):
     assert (o.dim_prior, o.max_iter, o.apply_parallax_clip) == (1, 0, 1)
     assert C.sizeof(_lib.Options) == 8 * 8 + 4 * 8 + 4 * 4
     assert C.sizeof(_lib.Stats) == 4 * 8 + 8 * 8
+    assert C.sizeof(_lib.Records) == 8 + 8 + 4 + 4 + 8 + 8
 
 
 def test_no_cpu_fallback(lib):
