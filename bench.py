@@ -33,6 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "stars/sec (full-grid loglike sweep)"
+GRID_KIND = "locus"   # mock.make_grid kind: "locus" (MIST-like stellar locus) or "tilt" (degenerate stress grid)
 CONFIG_NAMES = {
     1: "C1: 1 star x 10k models x 5 bands",
     2: "C2: 1k stars x 1M models x 8 bands",
@@ -117,7 +118,7 @@ def make_inputs(cfg_id, cfg, rank, need_grid=True):
     from brutus_b200 import mock
     grid = labels = None
     if need_grid:
-        grid, labels = mock.make_grid(cfg["nmodel"], cfg["nfilt"], seed=1000 + cfg_id)
+        grid, labels = mock.make_grid(cfg["nmodel"], cfg["nfilt"], seed=1000 + cfg_id, kind=GRID_KIND)
     return grid, labels
 
 
@@ -167,7 +168,8 @@ def run_reference(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": CONFIG_NAMES[args.config], "nmodel": cfg["nmodel"],
-                       "nfilt": cfg["nfilt"], "stars_per_step": per_step},
+                       "nfilt": cfg["nfilt"], "grid": "mock %s (brutus_b200/mock.py)" % GRID_KIND,
+                       "stars_per_step": per_step},
             "cpu_baseline": {"value": value, "unit": "stars/s", "cores": nt, "kind": "port",
                              "sample": "%d stars per step x %d steps, OpenMP over stars, C port "
                                        "(oracle/loglike_ref.c) of the reference's numba loglike"
@@ -285,8 +287,8 @@ def run_b200(args):
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
         "config": {"workload": CONFIG_NAMES[args.config], "nmodel": cfg["nmodel"], "nfilt": cfg["nfilt"],
-                   "stars_per_step_per_gpu": nstar, "parallelism": "stars sharded x%d, grid replicated" % world,
-                   "l2": "512 MB L2 flush before every step; per-batch state arrays (GBs) stream through L2",
+                   "grid": "mock %s (brutus_b200/mock.py)" % GRID_KIND, "stars_per_step_per_gpu": nstar, "parallelism": "stars sharded x%d, grid replicated" % world,
+                   "l2": "512 MB L2 flush before every step",
                    "grid_stage_s": round(t_stage, 3)},
         "e2e": {"value": e2e, "unit": "stars/s", "ms_per_step": 1e3 * wall_s / args.steps,
                 "h2d_bytes_per_step": int(agg_e["h2d_bytes"] / args.steps),
@@ -305,8 +307,9 @@ def run_b200(args):
                      "ms_per_launch": agg["ms_magfit"] / launches},
         "phases_ms_per_step": {"magfit": agg["ms_magfit"] / args.steps, "flux": agg["ms_flux"] / args.steps,
                                "select": agg["ms_select"] / args.steps},
-        "counts_per_step": {"survivors": agg["survivors"] / args.steps, "selected": agg["selected"] / args.steps,
-                            "resweeps": agg["resweeps"] / args.steps},
+        "counts_per_step": {"candidates": agg["candidates"] / args.steps, "survivors": agg["survivors"] / args.steps,
+                            "selected": agg["selected"] / args.steps, "resweeps": agg["resweeps"] / args.steps,
+                            "fallbacks": agg["fallbacks"] / args.steps},
         "clocks": clocks,
         "region_wall_s": t_region,
     }
@@ -336,7 +339,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--rows", type=int, default=11, choices=[3, 5, 11],
                     help="record rows shipped to the host per selected model (11 = everything)")
+    ap.add_argument("--grid", default="locus", choices=["locus", "tilt"],
+                    help="mock grid family (brutus_b200/mock.py): a stellar locus (default) or the degenerate "
+                         "colour-tilt grid the golden vectors use")
     args = ap.parse_args()
+    global GRID_KIND
+    GRID_KIND = args.grid
     if not args.nstar and args.config in (3, 5):
         args.nstar = 1000
     return run_reference(args) if args.impl == "reference" else run_b200(args)

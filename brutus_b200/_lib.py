@@ -29,7 +29,8 @@ class BrutusCudaError(RuntimeError):
 class Options(C.Structure):
     _fields_ = [("avlim", C.c_double * 2), ("av_gauss", C.c_double * 2), ("rvlim", C.c_double * 2),
                 ("rv_gauss", C.c_double * 2), ("ltol", C.c_double), ("ltol_subthresh", C.c_double),
-                ("init_thresh", C.c_double), ("wt_thresh", C.c_double), ("dim_prior", C.c_int32),
+                ("init_thresh", C.c_double), ("wt_thresh", C.c_double), ("select_slack", C.c_double),
+                ("dim_prior", C.c_int32),
                 ("max_iter", C.c_int32), ("apply_parallax_clip", C.c_int32), ("skip_d2h", C.c_int32)]
 
 
@@ -46,7 +47,8 @@ class Stats(C.Structure):
     _fields_ = [("ms_device", C.c_double), ("ms_magfit", C.c_double), ("ms_flux", C.c_double),
                 ("ms_select", C.c_double), ("kernel_launches", C.c_int64),
                 ("magfit_launches", C.c_int64), ("magfit_star_passes", C.c_int64),
-                ("resweeps", C.c_int64), ("survivors", C.c_int64),
+                ("resweeps", C.c_int64), ("candidates", C.c_int64), ("fallbacks", C.c_int64),
+                ("survivors", C.c_int64),
                 ("selected", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 
     def as_dict(self):
@@ -95,7 +97,7 @@ def _ptr(a, t):
 
 def make_options(avlim=(0., 20.), av_gauss=(0., 1e6), rvlim=(1., 8.), rv_gauss=(3.32, 0.18),
                  dim_prior=True, ltol=3e-2, ltol_subthresh=1e-2, init_thresh=5e-3, wt_thresh=1e-3,
-                 max_iter=0, apply_parallax_clip=True, skip_d2h=False):
+                 max_iter=0, apply_parallax_clip=True, skip_d2h=False, select_slack=1.0):
     if av_gauss is None:  # brutus/fitting.py:695-696
         av_gauss = (0., 1e6)
     o = Options()
@@ -105,6 +107,7 @@ def make_options(avlim=(0., 20.), av_gauss=(0., 1e6), rvlim=(1., 8.), rv_gauss=(
     o.rv_gauss[:] = [float(x) for x in rv_gauss]
     o.ltol, o.ltol_subthresh, o.init_thresh = float(ltol), float(ltol_subthresh), float(init_thresh)
     o.wt_thresh = float(wt_thresh)
+    o.select_slack = float(select_slack)
     o.dim_prior, o.max_iter = int(bool(dim_prior)), int(max_iter)
     o.apply_parallax_clip = int(bool(apply_parallax_clip))
     o.skip_d2h = int(bool(skip_d2h))

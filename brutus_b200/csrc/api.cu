@@ -1,10 +1,13 @@
 // api.cu -- C ABI (include/brutus_b200.h), host orchestration and the band-count-independent
 // kernels of the brute-force likelihood sweep.  See DESIGN.md for the pipeline:
 //
-//   prepare star rows (host, float64)  ->  k_magfit (full grid, speculated iteration count)
-//   -> verify / re-sweep mispredicted stars -> cull (count, scan, ordered write) -> k_flux on the
-//   survivor pool until every star converges -> scatter -> k_lnprob (+max) -> either full-length
-//   outputs (B1, bf_loglike_full) or threshold + ordered compaction + k_records (B2, bf_sweep_batch).
+//   prepare star rows (host, float64)  ->  k_magfit: the full-grid sweep (speculated iteration count);
+//   writes per-star maxima and a 1-bit candidate map, nothing else  ->  verify / re-sweep mispredicted
+//   stars  ->  k_cand_scan + k_expand: candidate map -> ordered candidate records  ->  k_refit: exact
+//   re-fit + exact cull of the candidates  ->  k_flux / k_flux_ctl on the survivors until every star
+//   converges (convergence decided on the device)  ->  k_final: lnlike, lnprob, per-star max  ->
+//   either full-length outputs (B1, bf_loglike_full) or threshold + ordered compaction + k_records
+//   (B2, bf_sweep_batch).
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -34,11 +37,13 @@ template <> const KTable<double>* get_ktable<double>(int nb) { switch (nb) { BF_
 // band-count-independent kernels
 // =================================================================================================
 
-// grid re-tiling: user layout (C or Fortran order of (nmodel, nfilt, 3)) -> [coef][band][npad]
-__global__ void k_retile(const float* __restrict__ src, float* __restrict__ dst, int64_t nmodel,
-                         int64_t npad, int nfilt, int layout) {
+// grid re-tiling: user layout (C or Fortran order of (nmodel, nfilt, 3)) -> the coefficient-major copy
+// [coef][band][npad] read by the sweep and the model-major copy [npad][row_stride] read by the gathers
+__global__ void k_retile(const float* __restrict__ src, float* __restrict__ dst, float* __restrict__ rows,
+                         int64_t nmodel, int64_t npad, int nfilt, int rs, int layout) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npad) return;
+    for (int k = 3 * nfilt; k < rs; k++) rows[i * rs + k] = 0.f;
     for (int j = 0; j < nfilt; j++)
         for (int c = 0; c < 3; c++) {
             float v = 0.f;
@@ -46,6 +51,7 @@ __global__ void k_retile(const float* __restrict__ src, float* __restrict__ dst,
                 v = layout == BF_LAYOUT_C ? src[(i * nfilt + j) * 3 + c]
                                           : src[((int64_t)c * nfilt + j) * nmodel + i];
             dst[((int64_t)c * nfilt + j) * npad + i] = v;
+            rows[i * rs + c * nfilt + j] = v;
         }
 }
 
@@ -63,95 +69,199 @@ __global__ void k_reset_red(typename Enc<T>::U* red, const int* list, int nlist,
     if (mask >> k & 1u) red[(int64_t)list[s] * kNumRed + k] = Enc<T>::enc(Num<T>::neg_inf());
 }
 
-// lnl_p of the cull, same expression as kernels_nb.cuh::cull_lnl
-template <typename T> __device__ __forceinline__ T cull_lnl2(T chi2, T s, const T* __restrict__ srow) {
-    T dp = Num<T>::sqrt_fast(s) - srow[SR_SC + SC_PAR];
-    return T(-0.5) * fma(dp * dp, srow[SR_SC + SC_PIVAR], chi2);
-}
-
-enum { FLAG_CULL = 0, FLAG_SELECT = 1 };
-
-template <typename T> struct FlagParams {
-    const T* stars;
-    StateArrays<T> st;
-    const typename Enc<T>::U* red;
-    DevOpts<T> o;
-    int64_t npad, nmodel;
-    const int* list;
-    int nlist, ntile;
-    int* cnt;            // [batch][ntile]: per-tile count, then (after k_scan_tiles) exclusive offset
-    const int64_t* base; // [batch]: first record of each star in the pool
-    int *out_model, *out_star;
-};
-
-template <typename T, int MODE>
-__device__ __forceinline__ bool eval_flag(const FlagParams<T>& p, int slot, int64_t i) {
-    if (i >= p.nmodel) return false;
-    const int64_t off = (int64_t)slot * p.npad + i;
-    if (MODE == FLAG_CULL) {
-        // brutus/fitting.py:758-759: lnl_p > max(lnl_p) + ln(init_thresh)
-        const T* srow = p.stars + (int64_t)slot * kStarStride;
-        T lmax = Enc<T>::dec(p.red[(int64_t)slot * kNumRed + RED_LP]);
-        return cull_lnl2(p.st.chi2[off], p.st.scale[off], srow) > lmax + p.o.ln_init;
-    } else {
-        // brutus/fitting.py:990-991: lnprob > max(lnprob) + ln(wt_thresh)
-        T lmax = Enc<T>::dec(p.red[(int64_t)slot * kNumRed + RED_LNP]);
-        return p.st.lnprob[off] > lmax + p.o.ln_wt;
+// block-wide exclusive scan helper: returns the exclusive prefix of v within the CTA (1024 threads)
+// and the CTA total through `total`
+__device__ __forceinline__ int block_exscan_1024(int v, int* s_w, int& total) {
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) >= o) x += y;
     }
-}
-
-template <typename T, int MODE> __global__ void __launch_bounds__(kTile) k_count(const FlagParams<T> p) {
-    const int slot = p.list[blockIdx.y];
-    const int64_t i = (int64_t)blockIdx.x * kTile + threadIdx.x;
-    int n = __syncthreads_count(eval_flag<T, MODE>(p, slot, i));
-    if (threadIdx.x == 0) p.cnt[(int64_t)slot * p.ntile + blockIdx.x] = n;
-}
-
-// one CTA per star: in-place exclusive scan of the per-tile counts; total -> tot[slot]
-__global__ void __launch_bounds__(1024) k_scan_tiles(int* cnt, const int* list, int ntile, int64_t* tot) {
-    __shared__ int s_w[32];
-    __shared__ int s_carry;
-    const int slot = list[blockIdx.x];
-    int* c = cnt + (int64_t)slot * ntile;
-    if (threadIdx.x == 0) s_carry = 0;
+    if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = x;
     __syncthreads();
-    for (int b = 0; b < ntile; b += 1024) {
-        int t = b + threadIdx.x;
-        int v = t < ntile ? c[t] : 0;
-        int x = v;
+    if (threadIdx.x < 32) {
+        int w = s_w[threadIdx.x];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            int y = __shfl_up_sync(0xffffffffu, x, o);
-            if ((threadIdx.x & 31) >= o) x += y;
+            int y = __shfl_up_sync(0xffffffffu, w, o);
+            if (threadIdx.x >= o) w += y;
         }
-        if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = x;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            int w = s_w[threadIdx.x];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int y = __shfl_up_sync(0xffffffffu, w, o);
-                if (threadIdx.x >= o) w += y;
-            }
-            s_w[threadIdx.x] = w;
-        }
-        __syncthreads();
-        int carry = s_carry;
-        int incl = x + ((threadIdx.x >> 5) ? s_w[(threadIdx.x >> 5) - 1] : 0);
-        if (t < ntile) c[t] = carry + incl - v;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = carry + incl;
-        __syncthreads();
+        s_w[threadIdx.x] = w;
     }
-    if (threadIdx.x == 0) tot[slot] = s_carry;
+    __syncthreads();
+    int incl = x + ((threadIdx.x >> 5) ? s_w[(threadIdx.x >> 5) - 1] : 0);
+    total = s_w[31];
+    __syncthreads();
+    return incl - v;
 }
 
-// ordered write: records of a star are contiguous and ascending in model index
-template <typename T, int MODE> __global__ void __launch_bounds__(kTile) k_write(const FlagParams<T> p) {
+// one CTA per star: exclusive scan of the popcounts of the star's candidate words -> wpre; total -> ncand
+__global__ void __launch_bounds__(1024) k_cand_scan(const uint32_t* __restrict__ cand, int* __restrict__ wpre,
+                                                    const int* __restrict__ list, int64_t nwords,
+                                                    int64_t* __restrict__ ncand) {
+    __shared__ int s_w[32];
+    const int slot = list[blockIdx.x];
+    const uint32_t* c = cand + (int64_t)slot * nwords;
+    int* w = wpre + (int64_t)slot * nwords;
+    int carry = 0;
+    for (int64_t b = 0; b < nwords; b += 1024) {
+        int64_t t = b + threadIdx.x;
+        int v = t < nwords ? __popc(c[t]) : 0;
+        int tot;
+        int ex = block_exscan_1024(v, s_w, tot);
+        if (t < nwords) w[t] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) ncand[slot] = carry;
+}
+
+// candidate map -> ordered candidate records (model, star); one thread per 32-model word
+template <typename T>
+__global__ void __launch_bounds__(256) k_expand(const uint32_t* __restrict__ cand, const int* __restrict__ wpre,
+                                                const int64_t* __restrict__ base, const int* __restrict__ list,
+                                                int64_t nwords, PoolArrays<T> pool) {
+    const int slot = list[blockIdx.y];
+    const int64_t w = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (w >= nwords) return;
+    uint32_t word = cand[(int64_t)slot * nwords + w];
+    if (!word) return;
+    int64_t pos = base[slot] + wpre[(int64_t)slot * nwords + w];
+    while (word) {
+        const int b = __ffs(word) - 1;
+        word &= word - 1;
+        pool.model[pos] = (int)(w * 32 + b);
+        pool.star[pos] = slot;
+        pos++;
+    }
+}
+
+// start of the flux loops of a group of stars (brutus/fitting.py:778-781)
+__global__ void k_flux_begin(int* star_int, const int* list, int nlist, const int* nsurv) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nlist) return;
+    const int slot = list[t];
+    star_int[slot * SI_COUNT + SI_ACTIVE] = nsurv[slot] > 0 ? 1 : 0;
+    star_int[slot * SI_COUNT + SI_NFLUX] = 0;
+}
+
+// Convergence control of the flux loops, on the device (one CTA): "lerr > ltol" (:781, :798-799) restated
+// on the two max-reductions of the k_flux launch that just ran `nit` iterations.  *any_out = 1 if some
+// star of the group needs another iteration.
+template <typename T>
+__global__ void __launch_bounds__(1024) k_flux_ctl(int* star_int, typename Enc<T>::U* red, const int* list, int nlist,
+                                                   int nit, int max_iter, T ln_sub, int* any_out) {
+    int any = 0;
+    for (int t = threadIdx.x; t < nlist; t += blockDim.x) {
+        const int slot = list[t];
+        int* si = star_int + slot * SI_COUNT;
+        if (si[SI_ACTIVE]) {
+            typename Enc<T>::U* r = red + (int64_t)slot * kNumRed;
+            const int nf = si[SI_NFLUX] + nit;
+            si[SI_NFLUX] = nf;
+            const bool more = Enc<T>::dec(r[RED_FB]) > Enc<T>::dec(r[RED_FL]) + ln_sub;
+            if (more && nf < max_iter) any = 1;
+            else si[SI_ACTIVE] = 0;
+            r[RED_FL] = Enc<T>::enc(Num<T>::neg_inf());
+            r[RED_FB] = Enc<T>::enc(Num<T>::neg_inf());
+        }
+    }
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) *any_out = any;
+}
+
+// brutus/fitting.py:808-810: the survivors' flux-phase results replace the mag-fit values
+template <typename T> __global__ void k_flux_scatter(SurvArrays<T> sv, int64_t n, PoolArrays<T> pool) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int64_t q = sv.q[t];
+    pool.av[q] = sv.av[t];
+    pool.rv[q] = sv.rv[t];
+    pool.chi2[q] = sv.chi2[t];
+    pool.scale[q] = sv.scale[t];
+    pool.sden[q] = sv.sden[t];
+}
+
+template <typename T> struct FinalParams {
+    const T* stars;
+    PoolArrays<T> pool;
+    int64_t ncand;
+    typename Enc<T>::U* red;
+    int dim_prior;
+    int64_t npad;
+    const T* labels;   // [nlabel][npad]
+    const T* ext;      // [batch][nlabel][3]
+    int nlabel;
+};
+
+// lnlike / lnprob of every candidate from its final (chi2, scale, s_den), per-star max(lnprob) (:990)
+template <typename T> __global__ void __launch_bounds__(kTile) k_final(const FinalParams<T> p) {
+    const int64_t q = (int64_t)blockIdx.x * kTile + threadIdx.x;
+    const bool inr = q < p.ncand;
+    int slot = -1;
+    T lp = Num<T>::neg_inf();
+    if (inr) {
+        slot = p.pool.star[q];
+        const T* __restrict__ srow = p.stars + (int64_t)slot * kStarStride;
+        T ext = T(0);
+        if (p.nlabel > 0)
+            ext = ext_prior<T>(p.labels, p.ext + (int64_t)slot * p.nlabel * 3, p.nlabel, p.npad, p.pool.model[q]);
+        T lnl;
+        lnl_lnprob<T>(p.pool.chi2[q], p.pool.sden[q], p.pool.scale[q], (p.pool.flag[q] & kFlagSurv) != 0, srow,
+                      p.dim_prior, ext, lnl, lp);
+        p.pool.lnl[q] = lnl;
+        p.pool.lnprob[q] = lp;
+    }
+    cta_star_max<T>(p.red, RED_LNP, slot, inr, lp);
+}
+
+template <typename T> struct SelParams {
+    PoolArrays<T> pool;
+    int64_t ncand;
+    const typename Enc<T>::U* red;
+    T ln_wt;
+    int* blk;      // per 256-record block: count, then (after k_scan_blocks) exclusive offset
+    int* nsel;     // [batch] per-star selected count
+    int* sel_q;    // ordered list of selected pool entries
+};
+
+// brutus/fitting.py:990-991: lnprob > max(lnprob) + ln(wt_thresh)
+template <typename T> __device__ __forceinline__ bool sel_flag(const SelParams<T>& p, int64_t q, int& slot) {
+    slot = -1;
+    if (q >= p.ncand) return false;
+    slot = p.pool.star[q];
+    return p.pool.lnprob[q] > Enc<T>::dec(p.red[(int64_t)slot * kNumRed + RED_LNP]) + p.ln_wt;
+}
+
+template <typename T> __global__ void __launch_bounds__(kTile) k_sel_count(const SelParams<T> p) {
+    const int64_t q = (int64_t)blockIdx.x * kTile + threadIdx.x;
+    int slot;
+    const bool f = sel_flag(p, q, slot);
+    const int n = __syncthreads_count(f);
+    if (threadIdx.x == 0) p.blk[blockIdx.x] = n;
+    cta_star_count(p.nsel, slot, f);
+}
+
+// in-place exclusive scan of n ints by one CTA; total -> *tot
+__global__ void __launch_bounds__(1024) k_scan_blocks(int* v, int64_t n, int64_t* tot) {
+    __shared__ int s_w[32];
+    int64_t carry = 0;
+    for (int64_t b = 0; b < n; b += 1024) {
+        int64_t t = b + threadIdx.x;
+        int x = t < n ? v[t] : 0;
+        int total;
+        int ex = block_exscan_1024(x, s_w, total);
+        if (t < n) v[t] = (int)(carry + ex);
+        carry += total;
+    }
+    if (threadIdx.x == 0) *tot = carry;
+}
+
+template <typename T> __global__ void __launch_bounds__(kTile) k_sel_write(const SelParams<T> p) {
     __shared__ int s_w[kTile / 32];
-    const int slot = p.list[blockIdx.y];
-    const int64_t i = (int64_t)blockIdx.x * kTile + threadIdx.x;
-    const bool f = eval_flag<T, MODE>(p, slot, i);
+    const int64_t q = (int64_t)blockIdx.x * kTile + threadIdx.x;
+    int slot;
+    const bool f = sel_flag(p, q, slot);
     const unsigned bal = __ballot_sync(0xffffffffu, f);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (lane == 0) s_w[w] = __popc(bal);
@@ -159,92 +269,8 @@ template <typename T, int MODE> __global__ void __launch_bounds__(kTile) k_write
     if (f) {
         int pre = __popc(bal & ((1u << lane) - 1u));
         for (int k = 0; k < w; k++) pre += s_w[k];
-        int64_t pos = p.base[slot] + p.cnt[(int64_t)slot * p.ntile + blockIdx.x] + pre;
-        p.out_model[pos] = (int)i;
-        p.out_star[pos] = slot;
+        p.sel_q[p.blk[blockIdx.x] + pre] = (int)q;
     }
-}
-
-// start of the flux loop: stepsize 1, lnl_old = -1e300 (brutus/fitting.py:778-779)
-template <typename T> __global__ void k_flux_init(PoolArrays<T> pool, int64_t n, StateArrays<T> st, int64_t npad) {
-    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n) return;
-    int64_t off = (int64_t)pool.star[q] * npad + pool.model[q];
-    pool.av[q] = st.av[off];
-    pool.rv[q] = st.rv[off];
-    pool.eta[q] = T(1);
-    pool.lold[q] = Num<T>::kNegBig;
-}
-
-// brutus/fitting.py:808-810: survivors' results replace the mag-fit values.  s_den > 0 always, so its
-// sign bit marks "survived the cull" (needed for the Gaussian constant when dim_prior is off, :806-808).
-template <typename T> __global__ void k_scatter(PoolArrays<T> pool, int64_t n, StateArrays<T> st, int64_t npad) {
-    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n) return;
-    int64_t off = (int64_t)pool.star[q] * npad + pool.model[q];
-    st.chi2[off] = pool.chi2[q];
-    st.scale[off] = pool.scale[q];
-    st.sden[off] = -pool.sden[q];
-    st.av[off] = pool.av[q];
-    st.rv[off] = pool.rv[q];
-}
-
-template <typename T> struct LnprobParams {
-    const T* stars;
-    StateArrays<T> st;
-    typename Enc<T>::U* red;
-    DevOpts<T> o;
-    int64_t npad, nmodel;
-    const int* list;
-    const T* labels;   // [nlabel][npad]
-    const T* ext;      // [batch][nlabel][3] = (mean, 1/std^2, ln(2 pi std^2)); ivar = 0 -> inactive
-    int nlabel;
-};
-
-// lnlike as loglike returns it (brutus/fitting.py:806-815, brutus/utils.py:130-176), the external label
-// priors (:1995-2009), lnpost's rough parallax prior (:976-982, brutus/pdf.py:178-222) and the -1e300
-// clean-up (:983-985); per-star max(lnprob) (:990).
-template <typename T> __global__ void __launch_bounds__(kTile) k_lnprob(const LnprobParams<T> p) {
-    __shared__ typename Enc<T>::U s_max;
-    const int slot = p.list[blockIdx.y];
-    const int64_t i = (int64_t)blockIdx.x * kTile + threadIdx.x;
-    if (threadIdx.x == 0) s_max = Enc<T>::enc(Num<T>::neg_inf());
-    __syncthreads();
-    T v = Num<T>::neg_inf();
-    if (i < p.nmodel) {
-        const T* __restrict__ srow = p.stars + (int64_t)slot * kStarStride;
-        const int64_t off = (int64_t)slot * p.npad + i;
-        const T chi2 = p.st.chi2[off];
-        const T sd = p.st.sden[off];
-        T lnl;
-        if (p.o.dim_prior) {
-            lnl = chi2 <= T(0) ? Num<T>::neg_inf()
-                               : srow[SR_SC + SC_LNORM] + srow[SR_SC + SC_KHM1] * Num<T>::log(chi2) - T(0.5) * chi2;
-        } else {
-            lnl = T(-0.5) * chi2 + (sd < T(0) ? srow[SR_SC + SC_GCONST] : T(0));
-        }
-        for (int l = 0; l < p.nlabel; l++) {
-            const T* x = p.ext + ((int64_t)slot * p.nlabel + l) * 3;
-            if (x[1] > T(0)) {
-                T d = p.labels[(int64_t)l * p.npad + i] - x[0];
-                lnl += T(-0.5) * (d * d * x[1] + x[2]);
-            }
-        }
-        T lp = lnl;
-        if (srow[SR_SC + SC_SPAPPLY] != T(0)) {
-            T svar = srow[SR_SC + SC_SVAR] + T(1) / tabs(sd);
-            T d = p.st.scale[off] - srow[SR_SC + SC_SMEAN];
-            lp = lnl + T(-0.5) * (Num<T>::div(d * d, svar) + Num<T>::log(T(6.283185307179586) * svar));
-        }
-        if (!Num<T>::finite(lp)) lp = Num<T>::kNegBig;
-        p.st.lnl[off] = lnl;
-        p.st.lnprob[off] = lp;
-        v = lp;
-    }
-    v = warp_max(v);
-    if ((threadIdx.x & 31) == 0) atomicMax(&s_max, Enc<T>::enc(v));
-    __syncthreads();
-    if (threadIdx.x == 0) atomicMax(&p.red[(int64_t)slot * kNumRed + RED_LNP], s_max);
 }
 
 // =================================================================================================
@@ -306,7 +332,7 @@ struct StarPrep {
 };
 
 static void prep_star(const double* flux, const double* errv, const uint8_t* mask, int nfilt, double par,
-                      double perr, int apply_clip, StarPrep& sp) {
+                      double perr, int apply_clip, double slack, StarPrep& sp) {
     std::memset(sp.row, 0, sizeof sp.row);
     const double c2 = (2.5 / std::log(10.)) * (2.5 / std::log(10.));
     int ndim = 0, npos = 0;
@@ -362,6 +388,7 @@ static void prep_star(const double* flux, const double* errv, const uint8_t* mas
         sc[SC_SMEAN] = pm * pm + perr * perr;
         sc[SC_SVAR] = 2 * perr * perr * perr * perr + 4 * pm * pm * perr * perr;
     }
+    sc[SC_SLACK] = slack;
     sp.ndim = ndim;
 }
 
@@ -372,30 +399,35 @@ template <typename T> struct Engine : EngineBase {
     cudaEvent_t ev_rec[2] = {nullptr, nullptr}, ev_cp[2] = {nullptr, nullptr};
     char* arena = nullptr;      // pinned host memory holding the records of the last bf_sweep_batch
     int64_t arena_cap = 0;
-    int64_t nmodel = 0, npad = 0;
-    int nfilt = 0, ntile = 0, nlabel = 0;
+    int64_t nmodel = 0, npad = 0, nwords = 0;
+    int nfilt = 0, nlabel = 0, rs = 0;
     int batch_cap = 0;
     int64_t pool_cap = 0;
     const KTable<T>* kt = nullptr;
+    int* h_pin = nullptr;       // small pinned scratch for counters
 
-    DevBuf<float> d_grid;
-    DevBuf<T> d_labels, d_stars, d_ext, d_state, d_poolT;
-    DevBuf<int> d_star_int, d_list, d_cnt, d_poolI;
-    DevBuf<int64_t> d_tot, d_base;
+    DevBuf<float> d_grid, d_rows;
+    DevBuf<T> d_labels, d_stars, d_ext, d_poolT;
+    DevBuf<int> d_star_int, d_list, d_wpre, d_poolI, d_nsurv, d_nsel, d_ctr, d_blk;
+    DevBuf<uint32_t> d_cand;
+    DevBuf<int64_t> d_ncand, d_base, d_tot;
     DevBuf<U> d_red;
     DevBuf<double> d_out;
     DevBuf<char> d_flush, d_stage[2];
 
     std::vector<T> h_stars, h_ext;
-    std::vector<int> h_int, h_list;
+    std::vector<int> h_int, h_list, h_nsurv, h_nsel;
     std::vector<U> h_red;
-    std::vector<int64_t> h_tot, h_base;
+    std::vector<int64_t> h_ncand, h_base;
+
+    enum { CTR_NSV = 0, CTR_ANY = 1, CTR_COUNT = 64 };
 
     ~Engine() override {
         cudaSetDevice(device);
-        d_grid.release(); d_labels.release(); d_stars.release(); d_ext.release(); d_state.release();
-        d_poolT.release(); d_star_int.release(); d_list.release(); d_cnt.release(); d_poolI.release();
-        d_tot.release(); d_base.release(); d_red.release(); d_out.release(); d_flush.release();
+        d_grid.release(); d_rows.release(); d_labels.release(); d_stars.release(); d_ext.release();
+        d_poolT.release(); d_star_int.release(); d_list.release(); d_wpre.release(); d_poolI.release();
+        d_nsurv.release(); d_nsel.release(); d_ctr.release(); d_blk.release(); d_cand.release();
+        d_ncand.release(); d_base.release(); d_tot.release(); d_red.release(); d_out.release(); d_flush.release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (evA) cudaEventDestroy(evA);
@@ -406,6 +438,7 @@ template <typename T> struct Engine : EngineBase {
             if (ev_cp[k]) cudaEventDestroy(ev_cp[k]);
         }
         if (arena) cudaFreeHost(arena);
+        if (h_pin) cudaFreeHost(h_pin);
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -420,39 +453,47 @@ template <typename T> struct Engine : EngineBase {
             CK(cudaEventCreateWithFlags(&ev_rec[k], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&ev_cp[k], cudaEventDisableTiming));
         }
+        CK(cudaHostAlloc((void**)&h_pin, CTR_COUNT * sizeof(int), cudaHostAllocDefault));
+        CK(d_ctr.ensure(CTR_COUNT));
+        CK(d_tot.ensure(2));
         return BF_OK;
     }
 
-    StateArrays<T> state() {
-        StateArrays<T> s;
-        const size_t n = (size_t)batch_cap * npad;
-        s.chi2 = d_state.p; s.scale = d_state.p + n; s.sden = d_state.p + 2 * n; s.av = d_state.p + 3 * n;
-        s.rv = d_state.p + 4 * n; s.lnl = d_state.p + 5 * n; s.lnprob = d_state.p + 6 * n;
-        return s;
-    }
     PoolArrays<T> pool() {
         PoolArrays<T> q;
-        q.model = d_poolI.p; q.star = d_poolI.p + pool_cap;
+        q.model = d_poolI.p; q.star = d_poolI.p + pool_cap; q.flag = d_poolI.p + 2 * pool_cap;
         T* b = d_poolT.p;
-        q.av = b; q.rv = b + pool_cap; q.eta = b + 2 * pool_cap; q.lold = b + 3 * pool_cap;
-        q.chi2 = b + 4 * pool_cap; q.scale = b + 5 * pool_cap; q.sden = b + 6 * pool_cap;
+        q.av = b; q.rv = b + pool_cap; q.chi2 = b + 2 * pool_cap; q.scale = b + 3 * pool_cap;
+        q.sden = b + 4 * pool_cap; q.lnl = b + 5 * pool_cap; q.lnprob = b + 6 * pool_cap;
         return q;
+    }
+    int* selq() { return d_poolI.p + 3 * pool_cap; }
+    SurvArrays<T> surv() {
+        SurvArrays<T> v;
+        int* a = d_poolI.p + 4 * pool_cap;
+        v.q = a; v.model = a + pool_cap; v.star = a + 2 * pool_cap;
+        T* b = d_poolT.p + 7 * pool_cap;
+        v.av = b; v.rv = b + pool_cap; v.eta = b + 2 * pool_cap; v.lold = b + 3 * pool_cap;
+        v.chi2 = b + 4 * pool_cap; v.scale = b + 5 * pool_cap; v.sden = b + 6 * pool_cap;
+        return v;
     }
 
     int set_grid(const float* co, int64_t nm, int nf, int layout, bool on_device) override {
         CK(cudaSetDevice(device));
         if (!co || nm <= 0 || nf <= 0) { err = "bf_set_grid: null grid or non-positive shape"; return BF_E_INVALID; }
         if (nf > kMaxFilt) { err = "bf_set_grid: nfilt exceeds BF_MAX_FILT (16)"; return BF_E_INVALID; }
-        if (nm > (int64_t)2000000000) { err = "bf_set_grid: nmodel too large"; return BF_E_INVALID; }
+        if (nm > (int64_t)1000000000) { err = "bf_set_grid: nmodel too large"; return BF_E_INVALID; }
         if (layout != BF_LAYOUT_C && layout != BF_LAYOUT_F) { err = "bf_set_grid: unknown layout"; return BF_E_INVALID; }
         kt = get_ktable<T>(nf);
         if (!kt) { err = "bf_set_grid: no kernels compiled for this band count"; return BF_E_INVALID; }
         nmodel = nm; nfilt = nf;
         npad = (nm + kTile - 1) / kTile * kTile;
-        ntile = (int)(npad / kTile);
+        nwords = npad / 32;
+        rs = row_stride(nf);
         nlabel = 0;
         const size_t nval = (size_t)nm * nf * 3;
         CK(d_grid.ensure((size_t)3 * nf * npad));
+        CK(d_rows.ensure((size_t)rs * npad));
         const float* src = co;
         DevBuf<float> tmp;
         if (!on_device) {
@@ -461,33 +502,43 @@ template <typename T> struct Engine : EngineBase {
             src = tmp.p;
             stats.h2d_bytes += nval * sizeof(float);
         }
-        k_retile<<<(unsigned)((npad + 255) / 256), 256, 0, stream>>>(src, d_grid.p, nmodel, npad, nfilt, layout);
+        k_retile<<<(unsigned)((npad + 255) / 256), 256, 0, stream>>>(src, d_grid.p, d_rows.p, nmodel, npad, nfilt, rs, layout);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(stream));
         tmp.release();
-        // size the per-(star, model) state for a star batch: at most 256 stars and ~1/5 of free HBM
+        // star batch: bounded by the candidate maps (2 x 4 B per 32 models per star)
         size_t fr = 0, tot = 0;
         CK(cudaMemGetInfo(&fr, &tot));
-        const size_t per_star = (size_t)7 * sizeof(T) * npad;
-        size_t budget = std::min<size_t>(fr / 5, (size_t)24 << 30);
-        batch_cap = (int)std::max<size_t>(1, std::min<size_t>(256, budget / per_star));
-        pool_cap = std::max<int64_t>(npad, std::min<int64_t>((int64_t)64 << 20, (int64_t)batch_cap * npad));
-        CK(d_state.ensure((size_t)7 * batch_cap * npad));
+        int want = 256;
+        if (const char* e = getenv("BRUTUS_B200_BATCH")) want = std::max(1, std::min(4096, atoi(e)));
+        const size_t per_star = (size_t)8 * nwords;
+        batch_cap = (int)std::max<size_t>(1, std::min<size_t>(want, (fr / 8) / per_star));
+        // candidate pool + flux working set: 7 ints + 14 T per record, at most ~1/4 of the free memory
+        const size_t rec = 7 * sizeof(int) + 14 * sizeof(T) + 1;
+        int64_t cap = (int64_t)std::min<size_t>((fr / 4) / rec, (size_t)1 << 30);
+        if (const char* e = getenv("BRUTUS_B200_POOL")) cap = std::max<int64_t>(1, atoll(e));
+        pool_cap = std::max<int64_t>(npad, std::min<int64_t>(cap, (int64_t)batch_cap * npad));
         CK(d_stars.ensure((size_t)batch_cap * kStarStride));
         CK(d_star_int.ensure((size_t)batch_cap * SI_COUNT));
         CK(d_list.ensure((size_t)batch_cap));
-        CK(d_cnt.ensure((size_t)batch_cap * ntile));
-        CK(d_tot.ensure((size_t)batch_cap));
+        CK(d_cand.ensure((size_t)batch_cap * nwords));
+        CK(d_wpre.ensure((size_t)batch_cap * nwords));
+        CK(d_ncand.ensure((size_t)batch_cap));
         CK(d_base.ensure((size_t)batch_cap));
+        CK(d_nsurv.ensure((size_t)batch_cap));
+        CK(d_nsel.ensure((size_t)batch_cap));
         CK(d_red.ensure((size_t)batch_cap * kNumRed));
-        CK(d_poolI.ensure((size_t)2 * pool_cap));
-        CK(d_poolT.ensure((size_t)7 * pool_cap));
+        CK(d_poolI.ensure((size_t)7 * pool_cap));
+        CK(d_poolT.ensure((size_t)14 * pool_cap));
+        CK(d_blk.ensure((size_t)(pool_cap / kTile + 2)));
         h_stars.resize((size_t)batch_cap * kStarStride);
         h_int.resize((size_t)batch_cap * SI_COUNT);
         h_list.resize(batch_cap);
         h_red.resize((size_t)batch_cap * kNumRed);
-        h_tot.resize(batch_cap);
+        h_ncand.resize(batch_cap);
         h_base.resize(batch_cap);
+        h_nsurv.resize(batch_cap);
+        h_nsel.resize(batch_cap);
         return BF_OK;
     }
 
@@ -539,7 +590,7 @@ template <typename T> struct Engine : EngineBase {
     }
 
     void phase_begin() { cudaEventRecord(evA, stream); }
-    double phase_end() {  // call only right before/after a stream sync
+    double phase_end() {  // synchronises the stream
         cudaEventRecord(evB, stream);
         cudaEventSynchronize(evB);
         float ms = 0.f;
@@ -547,64 +598,45 @@ template <typename T> struct Engine : EngineBase {
         return ms;
     }
 
-    // Runs the whole pipeline up to and including k_lnprob for `ns` stars already described by
-    // h_stars/h_int (slots 0..ns-1).  On return the state arrays hold final values.
-    int run_fit(int ns, const DevOpts<T>& o, int max_iter, int* n_mag, int* n_flux, int64_t* n_surv) {
-        const StateArrays<T> st = state();
-        const PoolArrays<T> pl = pool();
-        // initial speculation: 2 mag iterations (what the reference needs in the common case)
-        for (int s = 0; s < ns; s++) {
-            h_int[s * SI_COUNT + SI_KSPEC] = std::min(2, max_iter);
-            h_int[s * SI_COUNT + SI_ACTIVE] = 0;
-            h_list[s] = s;
-        }
-        CK(cudaMemcpyAsync(d_stars.p, h_stars.data(), (size_t)ns * kStarStride * sizeof(T), cudaMemcpyHostToDevice, stream));
-        CK(cudaMemcpyAsync(d_star_int.p, h_int.data(), (size_t)ns * SI_COUNT * sizeof(int), cudaMemcpyHostToDevice, stream));
-        CK(cudaMemcpyAsync(d_list.p, h_list.data(), (size_t)ns * sizeof(int), cudaMemcpyHostToDevice, stream));
-        stats.h2d_bytes += (size_t)ns * (kStarStride * sizeof(T) + (SI_COUNT + 1) * sizeof(int));
-        if (nlabel > 0) {
-            CK(cudaMemcpyAsync(d_ext.p, h_ext.data(), (size_t)ns * nlabel * 3 * sizeof(T), cudaMemcpyHostToDevice, stream));
-            stats.h2d_bytes += (size_t)ns * nlabel * 3 * sizeof(T);
-        }
-        CK(cudaEventRecord(ev0, stream));
-        k_reset_red<T><<<(ns * kNumRed + 255) / 256, 256, 0, stream>>>(d_red.p, d_list.p, ns, 0xffu);
-        stats.kernel_launches++;
-
-        // ---- magnitude fit with verified speculation of the iteration count ----
-        std::vector<int> lst(h_list.begin(), h_list.begin() + ns);
-        std::vector<char> exact(ns, 0);
+    // ---- phase 1: the full-grid sweep for the stars in `lst` (slots), with verified speculation of the
+    // mag-iteration count (skipped for stars whose count is already exact), then the candidate scan.
+    // On return h_ncand / h_red hold the candidate counts and the per-star maxima of those stars.
+    int sweep(int ns, std::vector<int> lst, std::vector<char>& exact, const DevOpts<T>& o, int max_iter, int* n_mag) {
         bool first_pass = true;
         while (!lst.empty()) {
             const int nl = (int)lst.size();
-            if (!first_pass) {
-                for (int k = 0; k < nl; k++) h_list[k] = lst[k];
-                CK(cudaMemcpyAsync(d_list.p, h_list.data(), (size_t)nl * sizeof(int), cudaMemcpyHostToDevice, stream));
-                CK(cudaMemcpyAsync(d_star_int.p, h_int.data(), (size_t)ns * SI_COUNT * sizeof(int), cudaMemcpyHostToDevice, stream));
-                k_reset_red<T><<<(nl * kNumRed + 255) / 256, 256, 0, stream>>>(d_red.p, d_list.p, nl, 0x1fu);
-                stats.kernel_launches++;
-                stats.resweeps += nl;
-            }
+            for (int k = 0; k < nl; k++) h_list[k] = lst[k];
+            CK(cudaMemcpyAsync(d_list.p, h_list.data(), (size_t)nl * sizeof(int), cudaMemcpyHostToDevice, stream));
+            CK(cudaMemcpyAsync(d_star_int.p, h_int.data(), (size_t)ns * SI_COUNT * sizeof(int), cudaMemcpyHostToDevice, stream));
+            k_reset_red<T><<<(nl * kNumRed + 255) / 256, 256, 0, stream>>>(d_red.p, d_list.p, nl, (1u << kNumRed) - 1u);
+            stats.kernel_launches++;
+            if (!first_pass) stats.resweeps += nl;
             SweepParams<T> sp;
             sp.grid = d_grid.p; sp.npad = npad; sp.nmodel = nmodel; sp.stars = d_stars.p;
-            sp.star_int = d_star_int.p; sp.list = d_list.p; sp.nlist = nl; sp.o = o; sp.st = st; sp.red = d_red.p;
+            sp.star_int = d_star_int.p; sp.list = d_list.p; sp.nlist = nl; sp.o = o; sp.red = d_red.p;
+            sp.cand = d_cand.p; sp.nwords = nwords; sp.labels = d_labels.p; sp.ext = d_ext.p; sp.nlabel = nlabel;
             phase_begin();
             kt->magfit(sp, stream);
             CK(cudaGetLastError());
             CK(cudaEventRecord(evB, stream));
             stats.kernel_launches++; stats.magfit_launches++; stats.magfit_star_passes += nl;
+            k_cand_scan<<<nl, 1024, 0, stream>>>(d_cand.p, d_wpre.p, d_list.p, nwords, d_ncand.p);
+            stats.kernel_launches++;
+            CK(cudaGetLastError());
             CK(cudaMemcpyAsync(h_red.data(), d_red.p, (size_t)ns * kNumRed * sizeof(U), cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(h_ncand.data(), d_ncand.p, (size_t)ns * sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));
             {
                 float ms = 0.f;
                 CK(cudaEventElapsedTime(&ms, evA, evB));
                 stats.ms_magfit += ms;
             }
-            stats.d2h_bytes += (size_t)ns * kNumRed * sizeof(U);
+            stats.d2h_bytes += (size_t)ns * (kNumRed * sizeof(U) + sizeof(int64_t));
             std::vector<int> next;
             for (int k = 0; k < nl; k++) {
                 const int s = lst[k];
                 int& ksp = h_int[s * SI_COUNT + SI_KSPEC];
-                n_mag[s] = ksp;
+                if (n_mag) n_mag[s] = ksp;
                 if (exact[s]) continue;
                 const U* r = &h_red[(size_t)s * kNumRed];
                 // brutus/fitting.py:252-263 restated on the two max-reductions
@@ -614,105 +646,115 @@ template <typename T> struct Engine : EngineBase {
                     ksp -= 1; exact[s] = 1; next.push_back(s);
                 } else if (!conv_last && ksp < max_iter) {
                     ksp = std::min(ksp + 2, max_iter); next.push_back(s);
+                } else {
+                    exact[s] = 1;
                 }
             }
             lst.swap(next);
             first_pass = false;
         }
+        return BF_OK;
+    }
 
-        // ---- cull (brutus/fitting.py:758-768): count, scan, ordered write into the survivor pool ----
+    // ---- phase 2 for the stars [g0, g1) whose candidates fit in the pool: expand, re-fit, flux loops,
+    // final lnprob.  Returns the number of candidate records through *tot_out.
+    int fit_group(int ns, int g0, int g1, const DevOpts<T>& o, int max_iter, int64_t* tot_out) {
+        const PoolArrays<T> pl = pool();
+        const int ng = g1 - g0;
+        int64_t tot = 0;
+        for (int s = g0; s < g1; s++) { h_base[s] = tot; tot += h_ncand[s]; }
+        *tot_out = tot;
         for (int s = 0; s < ns; s++) h_list[s] = s;
         CK(cudaMemcpyAsync(d_list.p, h_list.data(), (size_t)ns * sizeof(int), cudaMemcpyHostToDevice, stream));
-        FlagParams<T> fp;
-        fp.stars = d_stars.p; fp.st = st; fp.red = d_red.p; fp.o = o; fp.npad = npad; fp.nmodel = nmodel;
-        fp.list = d_list.p; fp.nlist = ns; fp.ntile = ntile; fp.cnt = d_cnt.p; fp.base = d_base.p;
-        fp.out_model = pl.model; fp.out_star = pl.star;
+        CK(cudaMemcpyAsync(d_base.p + g0, h_base.data() + g0, (size_t)ng * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemsetAsync(d_ctr.p, 0, CTR_COUNT * sizeof(int), stream));
+        CK(cudaMemsetAsync(d_nsurv.p + g0, 0, (size_t)ng * sizeof(int), stream));
+        CK(cudaMemsetAsync(d_nsel.p + g0, 0, (size_t)ng * sizeof(int), stream));
+        const int* glist = d_list.p + g0;
         phase_begin();
-        k_count<T, FLAG_CULL><<<dim3(ntile, ns), kTile, 0, stream>>>(fp);
-        k_scan_tiles<<<ns, 1024, 0, stream>>>(d_cnt.p, d_list.p, ntile, d_tot.p);
-        stats.kernel_launches += 2;
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(h_tot.data(), d_tot.p, (size_t)ns * sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
-        stats.ms_select += phase_end();
-        for (int s = 0; s < ns; s++) { n_surv[s] = h_tot[s]; n_flux[s] = 0; stats.survivors += h_tot[s]; }
-
-        // groups of consecutive stars whose survivors fit in the pool together
-        int g0 = 0;
-        while (g0 < ns) {
-            int g1 = g0;
-            int64_t tot = 0;
-            while (g1 < ns && (g1 == g0 || tot + h_tot[g1] <= pool_cap)) { h_base[g1] = tot; tot += h_tot[g1]; g1++; }
-            const int ng = g1 - g0;
-            if (tot > pool_cap) { err = "internal: survivor pool too small"; return BF_E_NOMEM; }
-            CK(cudaMemcpyAsync(d_base.p + g0, h_base.data() + g0, (size_t)ng * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
-            fp.list = d_list.p + g0; fp.nlist = ng;
-            phase_begin();
-            k_write<T, FLAG_CULL><<<dim3(ntile, ng), kTile, 0, stream>>>(fp);
-            k_flux_init<T><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(pl, tot, st, npad);
+        if (tot > 0) {
+            k_expand<T><<<dim3((unsigned)((nwords + 255) / 256), ng), 256, 0, stream>>>(d_cand.p, d_wpre.p, d_base.p, glist, nwords, pl);
+            RefitParams<T> rp;
+            rp.rows = d_rows.p; rp.stars = d_stars.p; rp.star_int = d_star_int.p; rp.o = o; rp.pool = pl;
+            rp.ncand = tot; rp.red = d_red.p; rp.sv = surv(); rp.nsv = d_ctr.p + CTR_NSV; rp.nsurv = d_nsurv.p;
+            kt->refit(rp, stream);
             stats.kernel_launches += 2;
             CK(cudaGetLastError());
-            // ---- flux-space iterations until every star of the group converges (:781-803) ----
-            std::vector<int> act;
-            for (int s = g0; s < g1; s++) { h_int[s * SI_COUNT + SI_ACTIVE] = 1; act.push_back(s); }
-            bool first = true;
-            while (!act.empty()) {
-                const int na = (int)act.size();
-                for (int k = 0; k < na; k++) h_list[k] = act[k];
-                // d_list is reused for the active list; the group list is restored afterwards
-                CK(cudaMemcpyAsync(d_list.p, h_list.data(), (size_t)na * sizeof(int), cudaMemcpyHostToDevice, stream));
-                CK(cudaMemcpyAsync(d_star_int.p, h_int.data(), (size_t)ns * SI_COUNT * sizeof(int), cudaMemcpyHostToDevice, stream));
-                k_reset_red<T><<<(na * kNumRed + 255) / 256, 256, 0, stream>>>(d_red.p, d_list.p, na, (1u << RED_FL) | (1u << RED_FB));
+        }
+        CK(cudaMemcpyAsync(h_pin, d_ctr.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(h_nsurv.data() + g0, d_nsurv.p + g0, (size_t)ng * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        stats.ms_select += phase_end();
+        const int64_t nsv = h_pin[0];
+        stats.candidates += tot;
+        stats.survivors += nsv;
+        // ---- flux-space iterations until every star of the group converges (:781-803); the per-star
+        // convergence test runs on the device, the host only polls "anything still active?" ----
+        phase_begin();
+        k_flux_begin<<<(ng + 255) / 256, 256, 0, stream>>>(d_star_int.p, glist, ng, d_nsurv.p);
+        k_reset_red<T><<<(ng * kNumRed + 255) / 256, 256, 0, stream>>>(d_red.p, glist, ng, (1u << RED_FL) | (1u << RED_FB) | (1u << RED_LNP));
+        stats.kernel_launches += 2;
+        bool first = true;
+        int done_iter = 0;
+        while (nsv > 0 && done_iter < max_iter) {
+            int any_slot = CTR_ANY;
+            const int rounds = first ? 2 : 3;
+            for (int r = 0; r < rounds && done_iter < max_iter; r++) {
                 FluxParams<T> xp;
-                xp.grid = d_grid.p; xp.npad = npad; xp.nmodel = nmodel; xp.stars = d_stars.p;
-                xp.star_int = d_star_int.p; xp.o = o; xp.pool = pl; xp.nsv = tot; xp.red = d_red.p;
+                xp.rows = d_rows.p; xp.stars = d_stars.p; xp.star_int = d_star_int.p; xp.o = o; xp.sv = surv();
+                xp.nsv = nsv; xp.red = d_red.p;
                 xp.nit = first ? std::min(2, max_iter) : 1;
                 kt->flux(xp, stream);
+                any_slot = CTR_ANY + r;
+                k_flux_ctl<T><<<1, 1024, 0, stream>>>(d_star_int.p, d_red.p, glist, ng, xp.nit, max_iter, o.ln_sub, d_ctr.p + any_slot);
                 stats.kernel_launches += 2;
-                CK(cudaGetLastError());
-                CK(cudaMemcpyAsync(h_red.data(), d_red.p, (size_t)ns * kNumRed * sizeof(U), cudaMemcpyDeviceToHost, stream));
-                CK(cudaStreamSynchronize(stream));
-                stats.d2h_bytes += (size_t)ns * kNumRed * sizeof(U);
-                std::vector<int> next;
-                for (int k = 0; k < na; k++) {
-                    const int s = act[k];
-                    n_flux[s] += xp.nit;
-                    const U* r = &h_red[(size_t)s * kNumRed];
-                    // "lerr > ltol" (:781, :798-799) restated on the two max-reductions
-                    const bool more = Enc<T>::dec(r[RED_FB]) > Enc<T>::dec(r[RED_FL]) + o.ln_sub;
-                    if (more && n_flux[s] < max_iter) next.push_back(s);
-                    else h_int[s * SI_COUNT + SI_ACTIVE] = 0;
-                }
-                act.swap(next);
+                done_iter += xp.nit;
                 first = false;
             }
-            k_scatter<T><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(pl, tot, st, npad);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(h_pin, d_ctr.p + any_slot, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            if (!h_pin[0]) break;
+        }
+        if (nsv > 0) {
+            k_flux_scatter<T><<<(unsigned)((nsv + 255) / 256), 256, 0, stream>>>(surv(), nsv, pl);
+            stats.kernel_launches++;
+        }
+        // ---- lnlike / lnprob of every candidate, per-star max ----
+        if (tot > 0) {
+            FinalParams<T> fp;
+            fp.stars = d_stars.p; fp.pool = pl; fp.ncand = tot; fp.red = d_red.p; fp.dim_prior = o.dim_prior;
+            fp.npad = npad; fp.labels = d_labels.p; fp.ext = d_ext.p; fp.nlabel = nlabel;
+            k_final<T><<<(unsigned)((tot + kTile - 1) / kTile), kTile, 0, stream>>>(fp);
             stats.kernel_launches++;
             CK(cudaGetLastError());
-            stats.ms_flux += phase_end();
-            for (int s = 0; s < ns; s++) h_list[s] = s;
-            CK(cudaMemcpyAsync(d_list.p, h_list.data(), (size_t)ns * sizeof(int), cudaMemcpyHostToDevice, stream));
-            g0 = g1;
         }
+        stats.ms_flux += phase_end();
+        return BF_OK;
+    }
 
-        // ---- lnlike / lnprob for every model, per-star max ----
-        LnprobParams<T> lp;
-        lp.stars = d_stars.p; lp.st = st; lp.red = d_red.p; lp.o = o; lp.npad = npad; lp.nmodel = nmodel;
-        lp.list = d_list.p; lp.labels = d_labels.p; lp.ext = d_ext.p; lp.nlabel = nlabel;
-        k_lnprob<T><<<dim3(ntile, ns), kTile, 0, stream>>>(lp);
-        stats.kernel_launches++;
-        CK(cudaGetLastError());
+    int upload_stars(int ns) {
+        CK(cudaMemcpyAsync(d_stars.p, h_stars.data(), (size_t)ns * kStarStride * sizeof(T), cudaMemcpyHostToDevice, stream));
+        stats.h2d_bytes += (size_t)ns * (kStarStride * sizeof(T) + (SI_COUNT + 1) * sizeof(int));
+        if (nlabel > 0) {
+            CK(cudaMemcpyAsync(d_ext.p, h_ext.data(), (size_t)ns * nlabel * 3 * sizeof(T), cudaMemcpyHostToDevice, stream));
+            stats.h2d_bytes += (size_t)ns * nlabel * 3 * sizeof(T);
+        }
         return BF_OK;
     }
 
     int fill_rows(int ns, const double* flux, const double* errv, const uint8_t* mask, const double* par,
-                  const double* perr, const double* ext_mean, const double* ext_std, int apply_clip,
-                  int32_t* ndim_out, uint8_t* mask_out) {
+                  const double* perr, const double* ext_mean, const double* ext_std, int apply_clip, double slack,
+                  int max_iter, int32_t* ndim_out, uint8_t* mask_out) {
         StarPrep sp;
         for (int s = 0; s < ns; s++) {
             prep_star(flux + (size_t)s * nfilt, errv + (size_t)s * nfilt, mask + (size_t)s * nfilt, nfilt,
-                      par ? par[s] : NAN, perr ? perr[s] : NAN, apply_clip, sp);
+                      par ? par[s] : NAN, perr ? perr[s] : NAN, apply_clip, slack, sp);
             for (int k = 0; k < kStarStride; k++) h_stars[(size_t)s * kStarStride + k] = (T)sp.row[k];
             h_int[s * SI_COUNT + SI_NDIM] = sp.ndim;
+            // initial speculation: 2 mag iterations (what the reference needs in the common case)
+            h_int[s * SI_COUNT + SI_KSPEC] = std::min(2, max_iter);
+            h_int[s * SI_COUNT + SI_ACTIVE] = 0;
+            h_int[s * SI_COUNT + SI_NFLUX] = 0;
             if (ndim_out) ndim_out[s] = sp.ndim;
             if (mask_out) std::memcpy(mask_out + (size_t)s * nfilt, sp.clean, nfilt);
             for (int l = 0; l < nlabel; l++) {
@@ -740,16 +782,23 @@ template <typename T> struct Engine : EngineBase {
         const int saved_labels = nlabel;
         nlabel = 0;  // loglike itself applies no label priors
         int32_t nd;
-        fill_rows(1, flux, errv, mask, &par, &perr, nullptr, nullptr, 0, &nd, mask_out);
-        int nm, nf; int64_t nsv;
-        rc = run_fit(1, o, max_iter, &nm, &nf, &nsv);
+        // slack = +inf: every model is a candidate, so the pool holds the whole grid in model order
+        fill_rows(1, flux, errv, mask, &par, &perr, nullptr, nullptr, 0, INFINITY, max_iter, &nd, mask_out);
+        rc = upload_stars(1);
+        int nm = 0;
+        std::vector<char> exact(1, 0);
+        CK(cudaEventRecord(ev0, stream));
+        if (!rc) rc = sweep(1, std::vector<int>(1, 0), exact, o, max_iter, &nm);
+        int64_t tot = 0;
+        if (!rc) rc = fit_group(1, 0, 1, o, max_iter, &tot);
         nlabel = saved_labels;
         if (rc) return rc;
+        if (tot != nmodel) { err = "internal: full-length pass did not keep every model"; return BF_E_INVALID; }
         const size_t per = icov ? 14 : 5;
         CK(d_out.ensure((size_t)nmodel * per));
         RecordParams<T, double> rp{};
-        rp.grid = d_grid.p; rp.npad = npad; rp.nmodel = nmodel; rp.stars = d_stars.p; rp.o = o; rp.st = state();
-        rp.sel_model = nullptr; rp.sel_star = nullptr; rp.nrec = 0; rp.star_slot = 0; rp.ld = 0; rp.nrows = 11; rp.o_idx = nullptr;
+        rp.rows = d_rows.p; rp.stars = d_stars.p; rp.o = o; rp.pool = pool();
+        rp.sel_q = nullptr; rp.nrec = nmodel; rp.ld = 0; rp.nrows = 11; rp.o_idx = nullptr;
         double* b = d_out.p;
         rp.o_lnl = b; rp.o_chi2 = b + nmodel; rp.o_scale = b + 2 * nmodel; rp.o_av = b + 3 * nmodel; rp.o_rv = b + 4 * nmodel;
         rp.o_icov = icov ? b + 5 * nmodel : nullptr;
@@ -769,8 +818,10 @@ template <typename T> struct Engine : EngineBase {
         CK(cudaMemcpy(av, rp.o_av, nb, cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(rv, rp.o_rv, nb, cudaMemcpyDeviceToHost));
         if (icov) CK(cudaMemcpy(icov, rp.o_icov, nb * 9, cudaMemcpyDeviceToHost));
+        int hi[SI_COUNT];
+        CK(cudaMemcpy(hi, d_star_int.p, sizeof hi, cudaMemcpyDeviceToHost));
         stats.d2h_bytes += nb * per;
-        if (diag) { diag[0] = nd; diag[1] = nm; diag[2] = nf; diag[3] = nsv; }
+        if (diag) { diag[0] = nd; diag[1] = nm; diag[2] = hi[SI_NFLUX]; diag[3] = h_nsurv[0]; }
         return BF_OK;
     }
 
@@ -806,10 +857,10 @@ template <typename T> struct Engine : EngineBase {
         DevOpts<T> o; int max_iter;
         int rc = make_opts(opt, o, max_iter);
         if (rc) return rc;
-        const StateArrays<T> st = state();
         const PoolArrays<T> pl = pool();
-        std::vector<int> nm(batch_cap), nf(batch_cap);
-        std::vector<int64_t> nsv(batch_cap);
+        const double slack = opt->select_slack;
+        std::vector<int> nm(batch_cap);
+        std::vector<char> exact(batch_cap);
         int64_t written = 0;
         int grp = 0;
         offsets[0] = 0;
@@ -818,81 +869,114 @@ template <typename T> struct Engine : EngineBase {
             fill_rows(ns, flux + (size_t)s0 * nfilt, errv + (size_t)s0 * nfilt, mask + (size_t)s0 * nfilt,
                       par ? par + s0 : nullptr, perr ? perr + s0 : nullptr,
                       ext_mean ? ext_mean + (size_t)s0 * nlabel : nullptr,
-                      ext_std ? ext_std + (size_t)s0 * nlabel : nullptr, opt->apply_parallax_clip,
+                      ext_std ? ext_std + (size_t)s0 * nlabel : nullptr, opt->apply_parallax_clip, slack, max_iter,
                       ndim ? ndim + s0 : nullptr, nullptr);
-            rc = run_fit(ns, o, max_iter, nm.data(), nf.data(), nsv.data());
+            rc = upload_stars(ns);
             if (rc) return rc;
-            // ---- first selection of lnpost (brutus/fitting.py:988-991), ordered compaction ----
-            FlagParams<T> fp;
-            fp.stars = d_stars.p; fp.st = st; fp.red = d_red.p; fp.o = o; fp.npad = npad; fp.nmodel = nmodel;
-            fp.list = d_list.p; fp.nlist = ns; fp.ntile = ntile; fp.cnt = d_cnt.p; fp.base = d_base.p;
-            fp.out_model = pl.model; fp.out_star = pl.star;
-            phase_begin();
-            k_count<T, FLAG_SELECT><<<dim3(ntile, ns), kTile, 0, stream>>>(fp);
-            k_scan_tiles<<<ns, 1024, 0, stream>>>(d_cnt.p, d_list.p, ntile, d_tot.p);
-            stats.kernel_launches += 2;
-            CK(cudaGetLastError());
-            CK(cudaMemcpyAsync(h_tot.data(), d_tot.p, (size_t)ns * sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
-            CK(cudaMemcpyAsync(h_red.data(), d_red.p, (size_t)ns * kNumRed * sizeof(U), cudaMemcpyDeviceToHost, stream));
-            stats.ms_select += phase_end();
-            for (int s = 0; s < ns; s++) {
-                if (n_iter) { n_iter[2 * (s0 + s)] = nm[s]; n_iter[2 * (s0 + s) + 1] = nf[s]; }
-                if (n_surv) n_surv[s0 + s] = nsv[s];
-                if (max_lnprob) {
-                    T v = Enc<T>::dec(h_red[(size_t)s * kNumRed + RED_LNP]);
-                    max_lnprob[s0 + s] = (v <= Num<T>::kNegBig) ? -1e300 : (double)v;
-                }
-                offsets[s0 + s + 1] = offsets[s0 + s] + h_tot[s];
-                stats.selected += h_tot[s];
-            }
-            // groups of stars whose records fit in the pool: k_write + k_records into a device staging
-            // buffer, then an asynchronous D2H on the copy stream that overlaps the next batch's compute
+            CK(cudaEventRecord(ev0, stream));
+            std::vector<int> all(ns);
+            for (int s = 0; s < ns; s++) { all[s] = s; exact[s] = 0; }
+            rc = sweep(ns, all, exact, o, max_iter, nm.data());
+            if (rc) return rc;
+            // groups of consecutive stars whose candidates fit in the pool together
             int g0 = 0;
             while (g0 < ns) {
                 int g1 = g0;
-                int64_t tot = 0;
-                while (g1 < ns && (g1 == g0 || tot + h_tot[g1] <= pool_cap)) { h_base[g1] = tot; tot += h_tot[g1]; g1++; }
+                int64_t cnt = 0;
+                while (g1 < ns && (g1 == g0 || cnt + h_ncand[g1] <= pool_cap)) { cnt += h_ncand[g1]; g1++; }
+                if (cnt > pool_cap) { err = "internal: candidate pool too small"; return BF_E_NOMEM; }
                 const int ng = g1 - g0;
+                int64_t tot = 0;
+                rc = fit_group(ns, g0, g1, o, max_iter, &tot);
+                if (rc) return rc;
+                // ---- first selection of lnpost (brutus/fitting.py:988-991): count ----
+                SelParams<T> sp;
+                sp.pool = pl; sp.ncand = tot; sp.red = d_red.p; sp.ln_wt = o.ln_wt; sp.blk = d_blk.p;
+                sp.nsel = d_nsel.p; sp.sel_q = selq();
+                const int64_t nblk = (tot + kTile - 1) / kTile;
+                phase_begin();
                 if (tot > 0) {
+                    k_sel_count<T><<<(unsigned)nblk, kTile, 0, stream>>>(sp);
+                    k_scan_blocks<<<1, 1024, 0, stream>>>(d_blk.p, nblk, d_tot.p);
+                    stats.kernel_launches += 2;
+                    CK(cudaGetLastError());
+                }
+                CK(cudaMemcpyAsync(h_nsel.data() + g0, d_nsel.p + g0, (size_t)ng * sizeof(int), cudaMemcpyDeviceToHost, stream));
+                CK(cudaMemcpyAsync(h_red.data(), d_red.p, (size_t)ns * kNumRed * sizeof(U), cudaMemcpyDeviceToHost, stream));
+                CK(cudaMemcpyAsync(h_int.data(), d_star_int.p, (size_t)ns * SI_COUNT * sizeof(int), cudaMemcpyDeviceToHost, stream));
+                stats.ms_select += phase_end();
+                stats.d2h_bytes += (size_t)ns * (kNumRed * sizeof(U) + SI_COUNT * sizeof(int)) + ng * sizeof(int);
+                // ---- was the sweep's candidate set a superset of the selection?  It is whenever the final
+                // max(lnprob) did not fall more than `slack` below the provisional one; otherwise redo those
+                // stars with every model as a candidate (rare: counted in stats.fallbacks) ----
+                std::vector<int> redo;
+                for (int s = g0; s < g1; s++) {
+                    const double sl = (double)h_stars[(size_t)s * kStarStride + SR_SC + SC_SLACK];
+                    if (!std::isfinite(sl)) continue;
+                    const double M = (double)Enc<T>::dec(h_red[(size_t)s * kNumRed + RED_LNP]);
+                    const double M0 = (double)Enc<T>::dec(h_red[(size_t)s * kNumRed + RED_M0]);
+                    if (!(M >= M0 - sl)) redo.push_back(s);
+                }
+                if (!redo.empty()) {
+                    stats.fallbacks += (int64_t)redo.size();
+                    for (int s : redo) h_stars[(size_t)s * kStarStride + SR_SC + SC_SLACK] = (T)INFINITY;
+                    CK(cudaMemcpyAsync(d_stars.p, h_stars.data(), (size_t)ns * kStarStride * sizeof(T), cudaMemcpyHostToDevice, stream));
+                    rc = sweep(ns, redo, exact, o, max_iter, nullptr);
+                    if (rc) return rc;
+                    continue;  // regroup from g0 with the new candidate counts
+                }
+                int64_t nsel_tot = 0;
+                for (int s = g0; s < g1; s++) {
+                    if (n_iter) { n_iter[2 * (s0 + s)] = nm[s]; n_iter[2 * (s0 + s) + 1] = h_int[s * SI_COUNT + SI_NFLUX]; }
+                    if (n_surv) n_surv[s0 + s] = h_nsurv[s];
+                    if (max_lnprob) {
+                        T v = Enc<T>::dec(h_red[(size_t)s * kNumRed + RED_LNP]);
+                        max_lnprob[s0 + s] = (v <= Num<T>::kNegBig) ? -1e300 : (double)v;
+                    }
+                    offsets[s0 + s + 1] = offsets[s0 + s] + h_nsel[s];
+                    nsel_tot += h_nsel[s];
+                }
+                stats.selected += nsel_tot;
+                // ---- ordered compaction + records into a device staging buffer, then an asynchronous D2H
+                // on the copy stream that overlaps the next group's / batch's kernels ----
+                if (nsel_tot > 0) {
                     const int buf = grp & 1;
                     grp++;
                     CK(cudaStreamWaitEvent(stream, ev_cp[buf], 0));  // staging buffer free again?
-                    CK(cudaMemcpyAsync(d_base.p + g0, h_base.data() + g0, (size_t)ng * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
-                    fp.list = d_list.p + g0; fp.nlist = ng;
                     phase_begin();
-                    k_write<T, FLAG_SELECT><<<dim3(ntile, ng), kTile, 0, stream>>>(fp);
-                    CK(d_stage[buf].ensure((size_t)tot * (sizeof(int) + 11 * sizeof(T))));
+                    k_sel_write<T><<<(unsigned)nblk, kTile, 0, stream>>>(sp);
+                    CK(d_stage[buf].ensure((size_t)nsel_tot * (sizeof(int) + 11 * sizeof(T))));
                     RecordParams<T, T> rp{};
-                    rp.grid = d_grid.p; rp.npad = npad; rp.nmodel = nmodel; rp.stars = d_stars.p; rp.o = o; rp.st = st;
-                    rp.sel_model = pl.model; rp.sel_star = pl.star; rp.nrec = tot; rp.star_slot = 0;
-                    T* b = (T*)d_stage[buf].p;                                   // [11][tot] rows, then idx
-                    rp.o_idx = (int*)(d_stage[buf].p + (size_t)11 * tot * sizeof(T));
-                    rp.ld = tot; rp.nrows = record_rows;
-                    rp.o_lnl = b; rp.o_scale = b + tot; rp.o_av = b + 2 * tot; rp.o_chi2 = b + 3 * tot;
-                    rp.o_rv = b + 4 * tot; rp.o_icov = b + 5 * tot;
+                    rp.rows = d_rows.p; rp.stars = d_stars.p; rp.o = o; rp.pool = pl;
+                    rp.sel_q = selq(); rp.nrec = nsel_tot;
+                    T* b = (T*)d_stage[buf].p;                                   // [11][nsel_tot] rows, then idx
+                    rp.o_idx = (int*)(d_stage[buf].p + (size_t)11 * nsel_tot * sizeof(T));
+                    rp.ld = nsel_tot; rp.nrows = record_rows;
+                    rp.o_lnl = b; rp.o_scale = b + nsel_tot; rp.o_av = b + 2 * nsel_tot; rp.o_chi2 = b + 3 * nsel_tot;
+                    rp.o_rv = b + 4 * nsel_tot; rp.o_icov = b + 5 * nsel_tot;
                     kt->records(rp, stream);
                     stats.kernel_launches += 2;
                     CK(cudaGetLastError());
                     CK(cudaEventRecord(ev_rec[buf], stream));
                     CK(cudaEventRecord(evB, stream));
                     if (!opt->skip_d2h) {
-                    rc = ensure_arena(written + tot, written);
-                    if (rc) return rc;
-                    CK(cudaStreamWaitEvent(copy_stream, ev_rec[buf], 0));
-                    CK(cudaMemcpyAsync(arena + (size_t)11 * arena_cap * sizeof(T) + (size_t)written * sizeof(int),
-                                       rp.o_idx, (size_t)tot * sizeof(int), cudaMemcpyDeviceToHost, copy_stream));
-                    CK(cudaMemcpy2DAsync(arena + (size_t)written * sizeof(T),
-                                         (size_t)arena_cap * sizeof(T), b, (size_t)tot * sizeof(T),
-                                         (size_t)tot * sizeof(T), record_rows, cudaMemcpyDeviceToHost, copy_stream));
-                    CK(cudaEventRecord(ev_cp[buf], copy_stream));
-                    stats.d2h_bytes += (size_t)tot * (sizeof(int) + record_rows * sizeof(T));
+                        rc = ensure_arena(written + nsel_tot, written);
+                        if (rc) return rc;
+                        CK(cudaStreamWaitEvent(copy_stream, ev_rec[buf], 0));
+                        CK(cudaMemcpyAsync(arena + (size_t)11 * arena_cap * sizeof(T) + (size_t)written * sizeof(int),
+                                           rp.o_idx, (size_t)nsel_tot * sizeof(int), cudaMemcpyDeviceToHost, copy_stream));
+                        CK(cudaMemcpy2DAsync(arena + (size_t)written * sizeof(T),
+                                             (size_t)arena_cap * sizeof(T), b, (size_t)nsel_tot * sizeof(T),
+                                             (size_t)nsel_tot * sizeof(T), record_rows, cudaMemcpyDeviceToHost, copy_stream));
+                        CK(cudaEventRecord(ev_cp[buf], copy_stream));
+                        stats.d2h_bytes += (size_t)nsel_tot * (sizeof(int) + record_rows * sizeof(T));
                     }
                     CK(cudaEventSynchronize(evB));
                     float msr = 0.f;
                     CK(cudaEventElapsedTime(&msr, evA, evB));
                     stats.ms_select += msr;
                 }
-                written += tot;
+                written += nsel_tot;
                 g0 = g1;
             }
             CK(cudaEventRecord(ev1, stream));
@@ -930,6 +1014,7 @@ void bf_default_options(bf_options* o) {
     o->rvlim[0] = 1.; o->rvlim[1] = 8.;
     o->rv_gauss[0] = 3.32; o->rv_gauss[1] = 0.18;
     o->ltol = 3e-2; o->ltol_subthresh = 1e-2; o->init_thresh = 5e-3; o->wt_thresh = 1e-3;
+    o->select_slack = 1.0;
     o->dim_prior = 1; o->max_iter = 0; o->apply_parallax_clip = 1; o->skip_d2h = 0;
 }
 

@@ -1,12 +1,18 @@
 // common.cuh -- shared definitions for the brutus_b200 CUDA kernels (sm_100a).
 //
 // Data layout in HBM:
-//   grid   float32 [3][NB][npad]        coefficient-major, then band, model axis contiguous
+//   grid   float32 [3][NB][npad]        coefficient-major, then band, model axis contiguous: the full-grid
+//                                        sweep reads it fully coalesced (thread = model)
 //                                        (c = 0: mag0 @ 1 kpc, 1: R0, 2: dR/dRv; brutus/utils.py:293-298)
-//   stars  T [batch][kStarStride]       per-star normalised photometry, see StarRow below
-//   state  T [batch][npad] x 7          chi2, scale, s_den, av, rv, lnl, lnprob per (star, model)
+//   rows   float32 [npad][row_stride]   the same coefficients model-major ([c][band] inside a row, row padded
+//                                        to 16 B): per-candidate gathers touch 3-4 sectors instead of 3*NB
+//   stars  T [batch][kStarStride]       per-star normalised photometry, see the star row below
+//   cand   u32 [batch][npad/32]         candidate bitmap written by the sweep (superset of everything
+//                                        that can survive the cull or pass the selection threshold)
 //   red    U [batch][kNumRed]           per-star max-reductions, order-preserving unsigned encoding
-//   pool   survivor records (SoA)       models that survive the cull, contiguous per star
+//   pool   candidate records (SoA)      one record per candidate (star, model), ascending (star, model)
+//
+// Nothing of size O(Nmodel x stars) other than the 1-bit candidate map is ever written.
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -36,12 +42,13 @@ enum StarScalar {
     SC_SPAPPLY,    // 1 if the rough scale-parallax prior applies (brutus/pdf.py:209)
     SC_SMEAN,      // brutus/pdf.py:255
     SC_SVAR,       // s_std^2, brutus/pdf.py:256
+    SC_SLACK,      // selection-candidate slack of the sweep (+inf: every model is a candidate)
     SC_COUNT
 };
 constexpr int kStarStride = SR_SC + 16;
 
 // per-star ints
-enum StarInt { SI_NDIM = 0, SI_KSPEC, SI_ACTIVE, SI_COUNT = 4 };
+enum StarInt { SI_NDIM = 0, SI_KSPEC, SI_ACTIVE, SI_NFLUX, SI_COUNT = 4 };
 
 // per-star reductions
 enum Red {
@@ -50,11 +57,16 @@ enum Red {
     RED_L1,      // same two at iteration kspec
     RED_B1,
     RED_LP,      // max lnl_p after the mag fit                 (brutus/fitting.py:758)
+    RED_M0,      // max provisional lnprob (mag-fit values for every model)
     RED_FL,      // max lnl_new in the current flux iteration   (brutus/fitting.py:798)
     RED_FB,      // max lnl_new over survivors with |lnl_new - lnl_old| > ltol
     RED_LNP,     // max lnprob                                  (brutus/fitting.py:990)
     kNumRed
 };
+constexpr int kSweepRed = 6;     // RED_L0 .. RED_M0 are produced by the sweep
+
+// candidate record flags
+constexpr int kFlagSurv = 1;     // survived the cull (brutus/fitting.py:758-759)
 
 // ---- order-preserving float -> unsigned encoding (so atomicMax works on floats) ---------------
 template <typename T> struct Enc;
@@ -139,6 +151,40 @@ template <typename T> __device__ __forceinline__ T tmax(T a, T b) { return a > b
 template <typename T> __device__ __forceinline__ T tmin(T a, T b) { return a < b ? a : b; }
 template <typename T> __device__ __forceinline__ T tabs(T a) { return a < T(0) ? -a : a; }
 
+
+// ---- per-star aggregation inside a CTA of candidate records ------------------------------------------
+// Records are sorted by star, so most CTAs see one or two stars.  Values for the star of the CTA's first
+// record are combined in shared memory and published by ONE global atomic per CTA; records of other
+// stars (CTAs that straddle a star boundary) fall back to warp-level / per-thread global atomics.
+// Without this, the per-star global atomics of a few million consecutive records serialise on one or
+// two L2 addresses.  All threads of the CTA must call these (they contain __syncthreads()).
+template <typename T>
+__device__ __forceinline__ void cta_star_max(typename Enc<T>::U* red, int which, int slot, bool have, T v) {
+    using U = typename Enc<T>::U;
+    __shared__ U s_m;
+    __shared__ int s_slotA;
+    if (threadIdx.x == 0) { s_m = Enc<T>::enc(Num<T>::neg_inf()); s_slotA = slot; }
+    __syncthreads();
+    const int slotA = s_slotA;
+    const bool mine = have && slot == slotA;
+    T w = warp_max((mine && v == v) ? v : Num<T>::neg_inf());
+    if ((threadIdx.x & 31) == 0 && w > Num<T>::neg_inf()) atomicMax(&s_m, Enc<T>::enc(w));
+    if (have && slot != slotA && v == v) atomicMax(&red[(int64_t)slot * kNumRed + which], Enc<T>::enc(v));
+    __syncthreads();
+    if (threadIdx.x == 0 && slotA >= 0) atomicMax(&red[(int64_t)slotA * kNumRed + which], s_m);
+    __syncthreads();
+}
+
+__device__ __forceinline__ void cta_star_count(int* cnt, int slot, bool flag) {
+    __shared__ int s_slotA2;
+    if (threadIdx.x == 0) s_slotA2 = slot;
+    __syncthreads();
+    const int slotA = s_slotA2;
+    const int n = __syncthreads_count(flag && slot == slotA);
+    if (flag && slot != slotA) atomicAdd(&cnt[slot], 1);
+    if (threadIdx.x == 0 && n > 0) atomicAdd(&cnt[slotA], n);
+}
+
 // ---- fit options on the device ------------------------------------------------------------------
 template <typename T> struct DevOpts {
     T Abar, PA, Rbar, PR;          // prior means and precisions   (brutus/fitting.py:146-148)
@@ -152,36 +198,97 @@ template <typename T> struct DevOpts {
 
 constexpr double kC2 = 1.3287712379549449;    // 0.4 * log2(10): 10^(0.4 x) = 2^(kC2 x)
 constexpr double kFac = -0.9210340371976184;  // -0.4 * ln(10), brutus/utils.py:328
+constexpr double kCandMargin = 1e-2;          // the sweep's cull-candidate test is this much looser than
+                                              // the exact test applied when candidates are re-fitted
+
+__host__ __device__ constexpr int row_stride(int nb) { return (3 * nb + 3) / 4 * 4; }
+
+// lnlike as loglike returns it (brutus/fitting.py:806-815, brutus/utils.py:130-176) plus the external
+// label priors `ext` (:1995-2009), and lnprob = lnlike + lnpost's rough parallax prior (:976-982,
+// brutus/pdf.py:178-222) with the -1e300 clean-up (:983-985).
+template <typename T>
+__device__ __forceinline__ void lnl_lnprob(T chi2, T sden, T scale, bool surv, const T* __restrict__ srow,
+                                           int dim_prior, T ext, T& lnl, T& lp) {
+    if (dim_prior) {
+        lnl = chi2 <= T(0) ? Num<T>::neg_inf()
+                           : srow[SR_SC + SC_LNORM] + srow[SR_SC + SC_KHM1] * Num<T>::log(chi2) - T(0.5) * chi2;
+    } else {
+        lnl = T(-0.5) * chi2 + (surv ? srow[SR_SC + SC_GCONST] : T(0));
+    }
+    lnl += ext;
+    lp = lnl;
+    if (srow[SR_SC + SC_SPAPPLY] != T(0)) {
+        T svar = srow[SR_SC + SC_SVAR] + Num<T>::div(T(1), tabs(sden));
+        T d = scale - srow[SR_SC + SC_SMEAN];
+        lp = lnl + T(-0.5) * (Num<T>::div(d * d, svar) + Num<T>::log(T(6.283185307179586) * svar));
+    }
+    if (!Num<T>::finite(lp)) lp = Num<T>::kNegBig;
+}
+
+// sum over the active label constraints of -0.5 ((label - mean)^2 / std^2 + ln 2 pi std^2)
+// ext_row: [nlabel][3] = (mean, 1/std^2, ln(2 pi std^2)); ivar = 0 -> inactive (brutus/fitting.py:1999)
+template <typename T>
+__device__ __forceinline__ T ext_prior(const T* __restrict__ labels, const T* __restrict__ ext_row, int nlabel,
+                                       int64_t npad, int64_t i) {
+    T acc = T(0);
+    for (int l = 0; l < nlabel; l++) {
+        const T* x = ext_row + l * 3;
+        if (x[1] > T(0)) {
+            T d = labels[(int64_t)l * npad + i] - x[0];
+            acc += T(-0.5) * (d * d * x[1] + x[2]);
+        }
+    }
+    return acc;
+}
 
 // ---- kernel parameter blocks ----------------------------------------------------------------------
-template <typename T> struct StateArrays {
-    T *chi2, *scale, *sden, *av, *rv, *lnl, *lnprob;   // each [batch][npad]
-};
-
 template <typename T> struct SweepParams {
-    const float* grid;
+    const float* grid;        // [3][NB][npad]
     int64_t npad, nmodel;
-    const T* stars;          // [batch][kStarStride]
-    const int* star_int;     // [batch][SI_COUNT]
-    const int* list;         // star slots processed by this launch
+    const T* stars;           // [batch][kStarStride]
+    const int* star_int;      // [batch][SI_COUNT]
+    const int* list;          // star slots processed by this launch
     int nlist;
     DevOpts<T> o;
-    StateArrays<T> st;
-    typename Enc<T>::U* red; // [batch][kNumRed]
+    typename Enc<T>::U* red;  // [batch][kNumRed]
+    uint32_t* cand;           // [batch][nwords]
+    int64_t nwords;
+    const T* labels;          // [nlabel][npad]
+    const T* ext;             // [batch][nlabel][3]
+    int nlabel;
 };
 
 template <typename T> struct PoolArrays {
-    int *model, *star;                       // [cap]
+    int *model, *star, *flag;                // [cap]
+    T *av, *rv, *chi2, *scale, *sden, *lnl, *lnprob;
+};
+
+// compact working set of the flux loops: one entry per survivor of the cull, any order
+template <typename T> struct SurvArrays {
+    int *q, *model, *star;                   // q = index of the survivor's candidate record
     T *av, *rv, *eta, *lold, *chi2, *scale, *sden;
 };
 
-template <typename T> struct FluxParams {
-    const float* grid;
-    int64_t npad, nmodel;
+// re-fit of the candidates (exact mag fit of the (star, model) pairs flagged by the sweep)
+template <typename T> struct RefitParams {
+    const float* rows;        // [npad][row_stride]
     const T* stars;
     const int* star_int;
     DevOpts<T> o;
     PoolArrays<T> pool;
+    int64_t ncand;
+    const typename Enc<T>::U* red;
+    SurvArrays<T> sv;         // survivors are appended here (CTA-granular, any order)
+    int* nsv;                 // [1] total survivors appended
+    int* nsurv;               // [batch] per-star survivor count
+};
+
+template <typename T> struct FluxParams {
+    const float* rows;
+    const T* stars;
+    const int* star_int;
+    DevOpts<T> o;
+    SurvArrays<T> sv;
     int64_t nsv;
     int nit;                 // flux iterations executed by this launch (2 first, then 1)
     typename Enc<T>::U* red;
@@ -190,28 +297,26 @@ template <typename T> struct FluxParams {
 // O = element type of the outputs: double for the full-length B1 arrays (the reference returns
 // float64), T for the compacted B2 records (no point shipping more bits than were computed).
 template <typename T, typename O> struct RecordParams {
-    const float* grid;
-    int64_t npad, nmodel;
+    const float* rows;
     const T* stars;
     DevOpts<T> o;
-    StateArrays<T> st;
-    // mode A (compacted records): nrec records (sel_model/sel_star)
-    const int* sel_model;
-    const int* sel_star;
+    PoolArrays<T> pool;
+    // mode A (compacted records): nrec selected pool entries sel_q[0..nrec)
+    // mode B (full-length, one star whose candidates are all models): sel_q == nullptr, nrec = nmodel
+    const int* sel_q;
     int64_t nrec;
-    // mode B (full-length, one star slot): sel_model == nullptr
-    int star_slot;
     // outputs.  Mode A: rows of a [11][ld] matrix: lnl, scale, av, chi2, rv, icov(ss,sa,sr,aa,ar,rr);
     // only the first `nrows` are produced (3, 5 or 11).  Mode B: separate arrays, icov 9 per model.
     O *o_lnl, *o_chi2, *o_scale, *o_av, *o_rv, *o_icov;
     int64_t ld;
     int nrows;
-    int* o_idx;   // mode A: copy of sel_model next to the rows (the pool is reused by the next batch)
+    int* o_idx;   // mode A: model index of each record
 };
 
 // Kernel launchers instantiated once per band count (inst.cu, -DBF_NB=n).
 template <typename T> struct KTable {
     void (*magfit)(const SweepParams<T>&, cudaStream_t);
+    void (*refit)(const RefitParams<T>&, cudaStream_t);
     void (*flux)(const FluxParams<T>&, cudaStream_t);
     void (*records)(const RecordParams<T, T>&, cudaStream_t);          // compacted records (B2)
     void (*records_full)(const RecordParams<T, double>&, cudaStream_t); // full-length float64 (B1)

@@ -18,11 +18,60 @@ CONFIGS = {
 }
 
 
-def make_grid(nmodel, nfilt, seed=1000):
+# effective wavelengths (micron) of the mock filters: PS1 grizy, 2MASS JHKs, then Gaia G/BP/RP, W1, ...
+_WAVE = np.array([0.481, 0.617, 0.752, 0.866, 0.962, 1.235, 1.662, 2.159, 0.622, 0.511, 0.777, 3.353,
+                  4.603, 0.354, 0.440, 0.550])
+
+
+def make_grid_locus(nmodel, nfilt, seed=1000):
+    """Mock grid on a stellar locus, the shape of a real MIST grid: every model is a point of a
+    3-parameter family (initial mass, evolutionary phase, [Fe/H]) whose colours come from a
+    blackbody at the model's Teff plus a metallicity-dependent blanketing term, with absolute
+    magnitudes from L(mass, phase); the reddening vector follows a power-law extinction curve
+    evaluated at the mock filters' effective wavelengths.  Unlike :func:`make_grid` (whose single
+    colour tilt is collinear with the reddening vector, so that a sixth of the grid fits any star),
+    only the models near the star's Teff-A(V) degeneracy track survive, as with real grids.
+    Labels: 'mini', 'eep', 'feh', 'Mr' (``load_models``-like, brutus/utils.py:608-609)."""
+    rs = np.random.RandomState(seed)
+    lam = _WAVE[:nfilt]
+    u1, u2 = rs.uniform(size=nmodel), rs.uniform(size=nmodel)
+    feh = rs.uniform(-2., 0.5, nmodel)
+    mini = 10. ** (-1. + 1.9 * u1)                               # 0.1 .. 8 Msun
+    teff = np.clip(5772. * mini ** 0.57, 2800., 15000.)
+    logl = 3.5 * np.log10(mini) + 0.3 * np.minimum(u2, 0.7) / 0.7   # main-sequence brightening
+    giant = (u2 > 0.7) & (mini > 0.8)
+    x = np.where(giant, (u2 - 0.7) / 0.3, 0.)
+    teff = np.where(giant, np.minimum(teff, 5200.) - 1500. * x, teff)
+    logl = logl + 2.5 * x
+    teff = teff * 10. ** (-0.02 * feh)                           # metal-poor stars are hotter
+    grid = np.empty((nmodel, nfilt, 3), dtype=np.float32)
+    hck = 14387.77  # micron K
+    r0 = (0.55 / lam) ** 1.6                                      # A_lambda / A_V at R(V) = 3.3
+    dr = 0.06 * (1. - (0.55 / lam) ** 0.8)                        # d(A_lambda/A_V)/dR(V)
+    chunk = 1 << 18
+    for lo in range(0, nmodel, chunk):
+        hi = min(nmodel, lo + chunk)
+        t = teff[lo:hi, None]
+        bb = -2.5 * np.log10(lam[None, :] ** -5 / np.expm1(hck / (lam[None, :] * t)))
+        bbv = -2.5 * np.log10(0.55 ** -5 / np.expm1(hck / (0.55 * t)))
+        mv = 4.81 - 2.5 * logl[lo:hi, None]
+        blanket = -0.12 * feh[lo:hi, None] * (0.55 / lam[None, :]) ** 2 * (lam[None, :] < 0.7)
+        grid[lo:hi, :, 0] = mv + (bb - bbv) + blanket
+        grid[lo:hi, :, 1] = (r0 - 3.3 * dr)[None, :]
+        grid[lo:hi, :, 2] = dr[None, :]
+    labels = np.zeros(nmodel, dtype=[("mini", "f8"), ("eep", "f8"), ("feh", "f8"), ("Mr", "f8")])
+    labels["mini"], labels["eep"], labels["feh"] = mini, 200. + 600. * u2, feh
+    labels["Mr"] = grid[:, min(1, nfilt - 1), 0]
+    return grid, labels
+
+
+def make_grid(nmodel, nfilt, seed=1000, kind="tilt"):
     """Mock SED grid: absolute magnitude ~U(-2,12), a one-parameter colour family plus 0.03 mag
     scatter, reddening vector falling from 1.2 to 0.2 across the bands, small dR/dRv.
     Also returns labels (structured: 'Mr', 'feh') like ``load_models`` does
-    (brutus/utils.py:608-609)."""
+    (brutus/utils.py:608-609).  ``kind="locus"`` gives :func:`make_grid_locus` instead."""
+    if kind == "locus":
+        return make_grid_locus(nmodel, nfilt, seed=seed)
     rs = np.random.RandomState(seed)
     mabs = rs.uniform(-2., 12., nmodel)
     col = rs.normal(0., 0.5, nmodel)

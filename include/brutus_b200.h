@@ -51,6 +51,11 @@ typedef struct bf_options {
     double ltol_subthresh;  /* default 1e-2         */
     double init_thresh;     /* default 5e-3         */
     double wt_thresh;       /* default 1e-3 (bf_sweep_batch only) */
+    double select_slack;    /* default 1.0 (bf_sweep_batch only): the sweep keeps as selection candidates the
+                               models whose provisional lnprob is within ln(wt_thresh) - select_slack of the
+                               running maximum.  Results do not depend on it: if the final max(lnprob) falls
+                               more than select_slack below the provisional one the star is redone with every
+                               model as a candidate (bf_stats.fallbacks) */
     int32_t dim_prior;      /* default 1            */
     int32_t max_iter;       /* cap on mag/flux loop iterations (reference: unbounded); 0 = 64 */
     int32_t apply_parallax_clip; /* 1: lnpost's rough parallax prior (fitting.py:976-980) is applied
@@ -62,12 +67,14 @@ typedef struct bf_options {
 typedef struct bf_stats {
     double ms_device;       /* first kernel -> last kernel of the call                */
     double ms_magfit;       /* sum over launches of the full-grid magnitude-fit sweep  */
-    double ms_flux;         /* survivor flux-space refinement                          */
-    double ms_select;       /* threshold / compaction / record kernels                 */
+    double ms_flux;         /* survivor flux-space refinement + final lnprob           */
+    double ms_select;       /* candidate expansion / re-fit, threshold, compaction, record kernels */
     int64_t kernel_launches;
     int64_t magfit_launches;
     int64_t magfit_star_passes; /* stars x full-grid passes done by those launches         */
     int64_t resweeps;       /* stars whose speculated mag-iteration count was wrong    */
+    int64_t candidates;     /* (star, model) pairs the sweep flagged for the exact re-fit          */
+    int64_t fallbacks;      /* stars redone with every model as a candidate (see select_slack)      */
     int64_t survivors;      /* total models that survived the cull (brutus/fitting.py:758-759)  */
     int64_t selected;       /* total models that passed wt_thresh                     */
     int64_t h2d_bytes, d2h_bytes;

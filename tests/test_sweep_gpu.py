@@ -113,3 +113,37 @@ def test_empty_and_errors():
     with pytest.raises(ValueError):
         h.set_grid(np.zeros((10, 17, 3), np.float32))
     h.close()
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_candidate_fallback_is_exact(precision):
+    """The sweep only keeps a candidate superset; a negative slack forces the 'redo with every model
+    as a candidate' path for every star and must reproduce the default path bit for bit, as must a
+    tiny candidate pool (many groups) and a tiny star batch."""
+    import os
+    from brutus_b200 import _lib
+    grid, labels = mock.make_grid(30_000, 7, seed=1500)
+    st = mock.make_stars(grid, 12, seed=2500, dropout=0.1)
+    args = (st["flux"], st["err"], st["mask"], st["parallax"], st["parallax_err"])
+    h = _lib.Handle(0, precision)
+    h.set_grid(grid)
+    a = h.sweep_batch(*args, copy=True)
+    sa = h.stats()
+    b = h.sweep_batch(*args, opts=_lib.make_options(select_slack=-100.), copy=True)
+    sb = h.stats()
+    h.close()
+    assert sa["fallbacks"] == 0 and sb["fallbacks"] == 12
+    assert 0 < sa["candidates"] < 12 * 30_000 < sb["candidates"]
+    os.environ["BRUTUS_B200_BATCH"] = "5"
+    os.environ["BRUTUS_B200_POOL"] = "1"
+    try:
+        h = _lib.Handle(0, precision)
+        h.set_grid(grid)
+        c = h.sweep_batch(*args, copy=True)
+        h.close()
+    finally:
+        del os.environ["BRUTUS_B200_BATCH"], os.environ["BRUTUS_B200_POOL"]
+    for other in (b, c):
+        for k in ("offsets", "model_idx", "lnl", "chi2", "scale", "av", "rv", "icov6", "n_iter", "n_surv",
+                  "max_lnprob", "ndim"):
+            assert np.array_equal(a[k], other[k]), k
