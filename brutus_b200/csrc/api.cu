@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -411,13 +412,13 @@ template <typename T> struct Engine : EngineBase {
     DevBuf<int> d_star_int, d_list, d_wpre, d_poolI, d_nsurv, d_nsel, d_ctr, d_blk;
     DevBuf<uint32_t> d_cand;
     DevBuf<int64_t> d_ncand, d_base, d_tot;
-    DevBuf<U> d_red;
+    DevBuf<U> d_red, d_probe;
     DevBuf<double> d_out;
     DevBuf<char> d_flush, d_stage[2];
 
     std::vector<T> h_stars, h_ext;
     std::vector<int> h_int, h_list, h_nsurv, h_nsel;
-    std::vector<U> h_red;
+    std::vector<U> h_red, h_probe;
     std::vector<int64_t> h_ncand, h_base;
 
     enum { CTR_NSV = 0, CTR_ANY = 1, CTR_COUNT = 64 };
@@ -427,7 +428,7 @@ template <typename T> struct Engine : EngineBase {
         d_grid.release(); d_rows.release(); d_labels.release(); d_stars.release(); d_ext.release();
         d_poolT.release(); d_star_int.release(); d_list.release(); d_wpre.release(); d_poolI.release();
         d_nsurv.release(); d_nsel.release(); d_ctr.release(); d_blk.release(); d_cand.release();
-        d_ncand.release(); d_base.release(); d_tot.release(); d_red.release(); d_out.release(); d_flush.release();
+        d_probe.release(); d_ncand.release(); d_base.release(); d_tot.release(); d_red.release(); d_out.release(); d_flush.release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (evA) cudaEventDestroy(evA);
@@ -528,6 +529,7 @@ template <typename T> struct Engine : EngineBase {
         CK(d_nsurv.ensure((size_t)batch_cap));
         CK(d_nsel.ensure((size_t)batch_cap));
         CK(d_red.ensure((size_t)batch_cap * kNumRed));
+        CK(d_probe.ensure((size_t)batch_cap * 2 * kProbeIter));
         CK(d_poolI.ensure((size_t)7 * pool_cap));
         CK(d_poolT.ensure((size_t)14 * pool_cap));
         CK(d_blk.ensure((size_t)(pool_cap / kTile + 2)));
@@ -535,6 +537,7 @@ template <typename T> struct Engine : EngineBase {
         h_int.resize((size_t)batch_cap * SI_COUNT);
         h_list.resize(batch_cap);
         h_red.resize((size_t)batch_cap * kNumRed);
+        h_probe.resize((size_t)batch_cap * 2 * kProbeIter);
         h_ncand.resize(batch_cap);
         h_base.resize(batch_cap);
         h_nsurv.resize(batch_cap);
@@ -596,6 +599,32 @@ template <typename T> struct Engine : EngineBase {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, evA, evB);
         return ms;
+    }
+
+    // ---- phase 0: speculate the mag-iteration count of each star from a 1/16 subsample of the grid ----
+    int probe_k(int ns, const DevOpts<T>& o, int max_iter) {
+        const int64_t ntile = npad / kTile;
+        if (ntile < 128 || max_iter < 2) return BF_OK;   // small grids: a re-sweep is cheaper than a probe
+        ProbeParams<T> pp;
+        pp.grid = d_grid.p; pp.npad = npad; pp.nmodel = nmodel; pp.stars = d_stars.p; pp.nstar = ns;
+        pp.tile_stride = 16; pp.o = o; pp.out = d_probe.p;
+        for (size_t k = 0; k < (size_t)ns * 2 * kProbeIter; k++) h_probe[k] = Enc<T>::enc(-std::numeric_limits<T>::infinity());
+        CK(cudaMemcpyAsync(d_probe.p, h_probe.data(), (size_t)ns * 2 * kProbeIter * sizeof(U), cudaMemcpyHostToDevice, stream));
+        phase_begin();
+        kt->kprobe(pp, stream);
+        stats.kernel_launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h_probe.data(), d_probe.p, (size_t)ns * 2 * kProbeIter * sizeof(U), cudaMemcpyDeviceToHost, stream));
+        stats.ms_select += phase_end();
+        for (int s = 0; s < ns; s++) {
+            int k = 1;
+            for (; k <= kProbeIter; k++) {
+                const U* r = &h_probe[((size_t)s * kProbeIter + (k - 1)) * 2];
+                if (!(Enc<T>::dec(r[1]) > Enc<T>::dec(r[0]) + o.ln_init)) break;   // err < tol at iteration k
+            }
+            h_int[s * SI_COUNT + SI_KSPEC] = std::min(k, max_iter);
+        }
+        return BF_OK;
     }
 
     // ---- phase 1: the full-grid sweep for the stars in `lst` (slots), with verified speculation of the
@@ -788,6 +817,7 @@ template <typename T> struct Engine : EngineBase {
         int nm = 0;
         std::vector<char> exact(1, 0);
         CK(cudaEventRecord(ev0, stream));
+        if (!rc) rc = probe_k(1, o, max_iter);
         if (!rc) rc = sweep(1, std::vector<int>(1, 0), exact, o, max_iter, &nm);
         int64_t tot = 0;
         if (!rc) rc = fit_group(1, 0, 1, o, max_iter, &tot);
@@ -876,6 +906,8 @@ template <typename T> struct Engine : EngineBase {
             CK(cudaEventRecord(ev0, stream));
             std::vector<int> all(ns);
             for (int s = 0; s < ns; s++) { all[s] = s; exact[s] = 0; }
+            rc = probe_k(ns, o, max_iter);
+            if (rc) return rc;
             rc = sweep(ns, all, exact, o, max_iter, nm.data());
             if (rc) return rc;
             // groups of consecutive stars whose candidates fit in the pool together

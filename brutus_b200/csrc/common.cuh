@@ -314,7 +314,20 @@ template <typename T, typename O> struct RecordParams {
 };
 
 // Kernel launchers instantiated once per band count (inst.cu, -DBF_NB=n).
+// iteration-count probe (k_kprobe)
+constexpr int kProbeIter = 4;
+template <typename T> struct ProbeParams {
+    const float* grid;
+    int64_t npad, nmodel;
+    const T* stars;
+    int nstar;                    // slots 0..nstar-1
+    int tile_stride;
+    DevOpts<T> o;
+    typename Enc<T>::U* out;      // [nstar][2 * kProbeIter]: (L_k, B_k)
+};
+
 template <typename T> struct KTable {
+    void (*kprobe)(const ProbeParams<T>&, cudaStream_t);
     void (*magfit)(const SweepParams<T>&, cudaStream_t);
     void (*refit)(const RefitParams<T>&, cudaStream_t);
     void (*flux)(const FluxParams<T>&, cudaStream_t);

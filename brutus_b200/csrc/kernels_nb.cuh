@@ -148,6 +148,72 @@ __device__ __forceinline__ float warp_max_fast(float v) {
 __device__ __forceinline__ double warp_max_fast(double v) { return warp_max((v == v) ? v : -CUDART_INF); }
 
 
+// =================================================================================================
+// Kernel 0: iteration-count probe.  Runs kProbeIter mag iterations on every `tile_stride`-th model
+// tile and records, per star and iteration k, the two maxima the reference's stopping rule needs
+// (:246-263).  The host turns them into the speculated iteration count of the full sweep, which
+// verifies it on the whole grid (so a wrong guess costs a re-sweep, never a wrong answer).
+// =================================================================================================
+template <typename T, int NB>
+__global__ void __launch_bounds__(kTile) k_kprobe(const ProbeParams<T> p) {
+    using U = typename Enc<T>::U;
+    __shared__ T s_star[kStarChunk][kStarStride];
+    __shared__ U s_red[kStarChunk][2 * kProbeIter];
+    const int first = blockIdx.y * kStarChunk;
+    const int nst = min(kStarChunk, p.nstar - first);
+    for (int t = threadIdx.x; t < nst * kStarStride; t += kTile)
+        s_star[t / kStarStride][t % kStarStride] = p.stars[(int64_t)first * kStarStride + t];
+    for (int t = threadIdx.x; t < kStarChunk * 2 * kProbeIter; t += kTile)
+        s_red[t / (2 * kProbeIter)][t % (2 * kProbeIter)] = Enc<T>::enc(Num<T>::neg_inf());
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * p.tile_stride * kTile + threadIdx.x;
+    const bool valid = i < p.nmodel;
+    const DevOpts<T> o = p.o;
+    ModelRegs<T, NB> m;
+    load_model<T, NB>(p.grid, p.npad, valid ? i : 0, o, m);
+    const int lane = threadIdx.x & 31;
+    const T ninf = Num<T>::neg_inf();
+    T acc[2 * kProbeIter];
+#pragma unroll
+    for (int k = 0; k < 2 * kProbeIter; k++) acc[k] = ninf;
+    for (int s = 0; s < nst; s++) {
+        const T* __restrict__ srow = s_star[s];
+        const T S = srow[SR_SC + SC_S];
+        const T c = srow[SR_SC + SC_MBAR] - m.bbar;
+        T A = o.Abar, rho = o.Rbar;
+        T e[NB], r[NB];
+        T Q = T(0), Tm = T(0), gs = T(0);
+#pragma unroll
+        for (int j = 0; j < NB; j++) {
+            const T u = srow[SR_U + j];
+            e[j] = srow[SR_CM + j] - m.cb[j];
+            r[j] = m.r0[j];
+            T Du = m.D[j] * u;
+            Q = fma(Du, m.D[j], Q);
+            Tm += Du;
+            gs = fma(e[j], u, gs);
+        }
+#pragma unroll
+        for (int k = 0; k < kProbeIter; k++) {
+            T ell, delta;
+            mag_iter<T, NB>(m, o, srow, S, c, Q, Tm, e, r, A, rho, gs, ell, delta);
+            T l = valid ? ell : ninf;
+            T b = (delta >= o.mtol) ? l : ninf;
+            l = warp_max_fast(l);
+            b = warp_max_fast(b);
+            if (lane == s) { acc[2 * k] = l; acc[2 * k + 1] = b; }
+        }
+    }
+    if (lane < nst) {
+#pragma unroll
+        for (int k = 0; k < 2 * kProbeIter; k++)
+            if (acc[k] == acc[k]) atomicMax(&s_red[lane][k], Enc<T>::enc(acc[k]));
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nst * 2 * kProbeIter; t += kTile)
+        atomicMax(&p.out[(int64_t)first * 2 * kProbeIter + t], s_red[t / (2 * kProbeIter)][t % (2 * kProbeIter)]);
+}
+
 // The whole magnitude-space fit of one (model, star) pair: initial residuals (brutus/fitting.py:728-733),
 // `kspec` iterations of _optimize_fit_mag (:173-264), leaving the centred residuals in e.  (l0, b0) and
 // (l1, b1) are the reduction inputs of iterations kspec-1 and kspec: logwt, and logwt where the step
@@ -557,6 +623,11 @@ __global__ void __launch_bounds__(kTile) k_records(const RecordParams<T, O> p) {
 template <typename T, int NB> void launch_magfit(const SweepParams<T>& p, cudaStream_t st) {
     dim3 grid((unsigned)(p.npad / kTile), (unsigned)((p.nlist + kStarChunk - 1) / kStarChunk));
     k_magfit<T, NB><<<grid, kTile, 0, st>>>(p);
+}
+template <typename T, int NB> void launch_kprobe(const ProbeParams<T>& p, cudaStream_t st) {
+    const int64_t ntile = p.npad / kTile;
+    dim3 grid((unsigned)((ntile + p.tile_stride - 1) / p.tile_stride), (unsigned)((p.nstar + kStarChunk - 1) / kStarChunk));
+    k_kprobe<T, NB><<<grid, kTile, 0, st>>>(p);
 }
 template <typename T, int NB> void launch_refit(const RefitParams<T>& p, cudaStream_t st) {
     if (p.ncand <= 0) return;
