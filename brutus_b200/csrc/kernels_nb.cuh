@@ -9,41 +9,127 @@
 //   sigma-normalised model      M_j/sigma_j = shat g_j be_j,  shat = s E,  residual t_j = al_j - shat g_j be_j
 //
 // so  scale s = (sum g be al / sum (g be)^2) / E   and   chi2 = sum t_j^2   (fitting.py:510-518, :745).
+//
+// The kernels are bound by FP32 instruction issue, not by HBM, so the band axis is
+// processed two bands at a time with Blackwell's packed FP32 instructions (PTX fma/mul/add.rn.f32x2 ->
+// SASS FFMA2/FMUL2/FADD2: one issue slot for two lanes' worth of work): bands (2p, 2p+1) live in one
+// 64-bit register pair, per-band sums are kept as (even, odd) partial sums and folded once.  An odd
+// band count is padded with a band of zero weight.  The float64 instantiation (verification path) uses
+// the same code with a plain two-element struct.
 #pragma once
 #include "common.cuh"
 
 namespace bf {
 
+// ---- two-lane values --------------------------------------------------------------------------------
+template <typename T> struct P2;
+template <> struct __align__(8) P2<float> { unsigned long long v; };
+template <> struct __align__(16) P2<double> { double x, y; };
+
+__device__ __forceinline__ P2<float> mk2(float a, float b) {
+    P2<float> r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ P2<double> mk2(double a, double b) { P2<double> r; r.x = a; r.y = b; return r; }
+__device__ __forceinline__ float lo2(P2<float> p) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p.v)); return a; }
+__device__ __forceinline__ float hi2(P2<float> p) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p.v)); return b; }
+__device__ __forceinline__ double lo2(P2<double> p) { return p.x; }
+__device__ __forceinline__ double hi2(P2<double> p) { return p.y; }
+template <typename T> __device__ __forceinline__ P2<T> bc2(T a) { return mk2(a, a); }   // folds into a .F32 broadcast operand
+__device__ __forceinline__ P2<float> fma2(P2<float> a, P2<float> b, P2<float> c) {
+    P2<float> r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r;
+}
+__device__ __forceinline__ P2<float> mul2(P2<float> a, P2<float> b) {
+    P2<float> r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r;
+}
+__device__ __forceinline__ P2<float> add2(P2<float> a, P2<float> b) {
+    P2<float> r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r;
+}
+__device__ __forceinline__ P2<float> sub2(P2<float> a, P2<float> b) {
+    P2<float> r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r;
+}
+__device__ __forceinline__ P2<double> fma2(P2<double> a, P2<double> b, P2<double> c) { return mk2(fma(a.x, b.x, c.x), fma(a.y, b.y, c.y)); }
+__device__ __forceinline__ P2<double> mul2(P2<double> a, P2<double> b) { return mk2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ P2<double> add2(P2<double> a, P2<double> b) { return mk2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ P2<double> sub2(P2<double> a, P2<double> b) { return mk2(a.x - b.x, a.y - b.y); }
+template <typename T> __device__ __forceinline__ T hsum2(P2<T> p) { return lo2(p) + hi2(p); }
+// pair (2p, 2p+1) of a star-row array (shared or global memory, 8/16-byte aligned)
+__device__ __forceinline__ P2<float> ld2(const float* p) { P2<float> r; r.v = *reinterpret_cast<const unsigned long long*>(p); return r; }
+__device__ __forceinline__ P2<double> ld2(const double* p) { return mk2(p[0], p[1]); }
+
 // Star-independent per-model quantities, hoisted out of the star loop.
 template <typename T, int NB> struct ModelRegs {
-    T cb[NB];   // b_j - bbar, b_j = mu_j + Abar r0_j  (model magnitudes at the prior-mean reddening)
-    T r0[NB];   // R_j + Rbar D_j                      (brutus/utils.py:337-338 at rv = rv_gauss[0])
-    T D[NB];    // dR/dRv
+    static constexpr int NP = (NB + 1) / 2;
+    P2<T> ncb[NP];  // -(b_j - bbar), b_j = mu_j + Abar r0_j  (model magnitudes at the prior-mean reddening)
+    P2<T> r0[NP];   // R_j + Rbar D_j                         (brutus/utils.py:337-338 at rv = rv_gauss[0])
+    P2<T> D[NP];    // dR/dRv
     T bbar;
 };
 
 template <typename T, int NB>
-__device__ __forceinline__ void load_model(const float* __restrict__ grid, int64_t npad, int64_t i,
-                                           const DevOpts<T>& o, ModelRegs<T, NB>& m) {
+__device__ __forceinline__ void finish_model(const T (&mu)[NB + 1], const T (&R)[NB + 1], const T (&D)[NB + 1],
+                                             const DevOpts<T>& o, ModelRegs<T, NB>& m) {
+    constexpr int NP = ModelRegs<T, NB>::NP;
+    T r0[2 * NP], cb[2 * NP], Dd[2 * NP];
     T sum = T(0);
 #pragma unroll
-    for (int j = 0; j < NB; j++) {
-        T mu = (T)__ldg(grid + (int64_t)(0 * NB + j) * npad + i);
-        T R = (T)__ldg(grid + (int64_t)(1 * NB + j) * npad + i);
-        T D = (T)__ldg(grid + (int64_t)(2 * NB + j) * npad + i);
-        m.D[j] = D;
-        m.r0[j] = fma(o.Rbar, D, R);
-        m.cb[j] = fma(o.Abar, m.r0[j], mu);
-        sum += m.cb[j];
+    for (int j = 0; j < 2 * NP; j++) {
+        if (j < NB) {
+            Dd[j] = D[j];
+            r0[j] = fma(o.Rbar, D[j], R[j]);
+            cb[j] = fma(o.Abar, r0[j], mu[j]);
+            sum += cb[j];
+        } else {
+            Dd[j] = r0[j] = cb[j] = T(0);   // padding band: zero model terms, zero star weights
+        }
     }
     m.bbar = sum * (T(1) / T(NB));
 #pragma unroll
-    for (int j = 0; j < NB; j++) m.cb[j] -= m.bbar;
+    for (int p = 0; p < NP; p++) {
+        const T c0 = m.bbar - cb[2 * p];
+        const T c1 = (2 * p + 1 < NB) ? m.bbar - cb[2 * p + 1] : T(0);
+        m.ncb[p] = mk2(c0, c1);
+        m.r0[p] = mk2(r0[2 * p], r0[2 * p + 1]);
+        m.D[p] = mk2(Dd[2 * p], Dd[2 * p + 1]);
+    }
+}
+
+// from the coefficient-major grid (fully coalesced: thread = model)
+template <typename T, int NB>
+__device__ __forceinline__ void load_model(const float* __restrict__ grid, int64_t npad, int64_t i,
+                                           const DevOpts<T>& o, ModelRegs<T, NB>& m) {
+    T mu[NB + 1], R[NB + 1], D[NB + 1];
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+        mu[j] = (T)__ldg(grid + (int64_t)(0 * NB + j) * npad + i);
+        R[j] = (T)__ldg(grid + (int64_t)(1 * NB + j) * npad + i);
+        D[j] = (T)__ldg(grid + (int64_t)(2 * NB + j) * npad + i);
+    }
+    finish_model<T, NB>(mu, R, D, o, m);
+}
+
+// from the model-major copy of the grid (3-4 sectors per model: the per-candidate gathers)
+template <typename T, int NB>
+__device__ __forceinline__ void load_model_row(const float* __restrict__ rows, int64_t i, const DevOpts<T>& o,
+                                               ModelRegs<T, NB>& m) {
+    constexpr int RS = row_stride(NB);
+    float v[RS];
+    const float4* __restrict__ p4 = reinterpret_cast<const float4*>(rows + i * RS);
+#pragma unroll
+    for (int k = 0; k < RS / 4; k++) {
+        float4 t = __ldg(p4 + k);
+        v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+    }
+    T mu[NB + 1], R[NB + 1], D[NB + 1];
+#pragma unroll
+    for (int j = 0; j < NB; j++) { mu[j] = (T)v[j]; R[j] = (T)v[NB + j]; D[j] = (T)v[2 * NB + j]; }
+    finish_model<T, NB>(mu, R, D, o, m);
 }
 
 // Result of the flux-space MLE at fixed (A, rho): brutus/fitting.py:430-576 (_get_sed_mle), normalised.
 template <typename T, int NB> struct Mle {
-    T gb[NB];     // g_j be_j
+    P2<T> gb[(NB + 1) / 2];  // g_j be_j
     T shat;       // s E (after the 1e-20 floor on s)
     T s;          // scale                                  (:516-518)
     T E;          // 2^(kC2 c)
@@ -52,33 +138,39 @@ template <typename T, int NB> struct Mle {
 };
 
 template <typename T, int NB>
-__device__ __forceinline__ void mle_from_resid(const T (&e)[NB], T c, const T* __restrict__ srow,
+__device__ __forceinline__ void mle_from_resid(const P2<T> (&e)[(NB + 1) / 2], T c, const T* __restrict__ srow,
                                                Mle<T, NB>& r) {
-    T num = T(0), den = T(0);
+    constexpr int NP = (NB + 1) / 2;
+    P2<T> num = bc2(T(0)), den = bc2(T(0));
+    const P2<T> k2 = bc2(T(kC2));
 #pragma unroll
-    for (int j = 0; j < NB; j++) {
-        T g = Num<T>::exp2(T(kC2) * e[j]);
-        T gb = g * srow[SR_BE + j];
-        r.gb[j] = gb;
-        num = fma(gb, srow[SR_AL + j], num);
-        den = fma(gb, gb, den);
+    for (int p = 0; p < NP; p++) {
+        const P2<T> x = mul2(e[p], k2);
+        const T g0 = Num<T>::exp2(lo2(x));
+        const T g1 = (2 * p + 1 < NB) ? Num<T>::exp2(hi2(x)) : T(0);
+        const P2<T> gb = mul2(mk2(g0, g1), ld2(srow + SR_BE + 2 * p));
+        r.gb[p] = gb;
+        num = fma2(gb, ld2(srow + SR_AL + 2 * p), num);
+        den = fma2(gb, gb, den);
     }
     // shat = num/den may use the approximate reciprocal: chi2 is stationary in shat at the MLE
     // (sum t_j gb_j = 0), so a 2-ulp error in shat enters chi2 only at second order.
     const T E = Num<T>::exp2(T(kC2) * c);
     const T Einv = Num<T>::exp2(T(-kC2) * c);
-    T shat = Num<T>::div_fast(num, den);
+    const T dens = hsum2(den);
+    T shat = Num<T>::div_fast(hsum2(num), dens);
     T s = shat * Einv;
     const bool floor_s = s <= T(1e-20);  // brutus/fitting.py:517-518
     s = floor_s ? T(1e-20) : s;
     shat = floor_s ? T(1e-20) * E : shat;
-    T chi2 = T(0);
+    P2<T> chi = bc2(T(0));
+    const P2<T> nsh = bc2(-shat);
 #pragma unroll
-    for (int j = 0; j < NB; j++) {
-        T t = fma(-shat, r.gb[j], srow[SR_AL + j]);
-        chi2 = fma(t, t, chi2);
+    for (int p = 0; p < NP; p++) {
+        const P2<T> t = fma2(nsh, r.gb[p], ld2(srow + SR_AL + 2 * p));
+        chi = fma2(t, t, chi);
     }
-    r.shat = shat; r.s = s; r.E = E; r.den = den; r.chi2 = chi2;
+    r.shat = shat; r.s = s; r.E = E; r.den = dens; r.chi2 = hsum2(chi);
 }
 
 // lnl_p of the cull (brutus/fitting.py:747-756): -chi2/2 - (sqrt(s) - parallax)^2 / (2 parallax_err^2)
@@ -93,30 +185,35 @@ __device__ __forceinline__ T cull_lnl(T chi2, T s, const T* __restrict__ srow) {
 // the updates (e' -= dA r; e' -= A dR D) instead of being re-summed over the bands.
 template <typename T, int NB>
 __device__ __forceinline__ void mag_iter(const ModelRegs<T, NB>& m, const DevOpts<T>& o,
-                                         const T* __restrict__ srow, T S, T c, T Q, T Tm, T (&e)[NB],
-                                         T (&r)[NB], T& A, T& rho, T& gs, T& ell, T& delta) {
+                                         const P2<T> (&u)[(NB + 1) / 2], T S, T c, T Q, T Tm,
+                                         P2<T> (&e)[(NB + 1) / 2], P2<T> (&r)[(NB + 1) / 2], T& A, T& rho,
+                                         T& gs, T& ell, T& delta) {
+    constexpr int NP = (NB + 1) / 2;
     // --- solve for Av (:176-204) ---
-    T a = o.PA, b = T(0), ga = (o.Abar - A) * o.PA;
+    P2<T> a2 = bc2(T(0)), b2 = bc2(T(0)), ga2 = bc2(T(0));
 #pragma unroll
-    for (int j = 0; j < NB; j++) {
-        T ru = r[j] * srow[SR_U + j];
-        a = fma(ru, r[j], a);
-        b += ru;
-        ga = fma(ru, e[j], ga);
+    for (int p = 0; p < NP; p++) {
+        const P2<T> ru = mul2(r[p], u[p]);
+        a2 = fma2(ru, r[p], a2);
+        b2 = add2(b2, ru);
+        ga2 = fma2(ru, e[p], ga2);
     }
+    const T a = hsum2(a2) + o.PA, b = hsum2(b2);
+    const T ga = fma(o.Abar - A, o.PA, hsum2(ga2));
     T dA = Num<T>::div_fast(S * ga - b * gs, S * a - b * b);
     dA = Num<T>::max(dA, o.avmin - A);
     dA = Num<T>::min(dA, o.avmax - A);
     A += dA;
     // --- solve for Rv (:206-237) ---
     const T gs2 = fma(-dA, b, gs);             // sum (e' - dA r) u
-    T gr = T(0);
+    const P2<T> ndA = bc2(-dA);
+    P2<T> gr2 = bc2(T(0));
 #pragma unroll
-    for (int j = 0; j < NB; j++) {
-        e[j] = fma(-dA, r[j], e[j]);
-        gr = fma(e[j] * srow[SR_U + j], m.D[j], gr);
+    for (int p = 0; p < NP; p++) {
+        e[p] = fma2(ndA, r[p], e[p]);
+        gr2 = fma2(mul2(e[p], u[p]), m.D[p], gr2);
     }
-    gr = fma(gr, A, (o.Rbar - rho) * o.PR);
+    const T gr = fma(hsum2(gr2), A, (o.Rbar - rho) * o.PR);
     const T q = fma(Q * A, A, o.PR);
     const T tt = Tm * A;
     T dR = Num<T>::div_fast(S * gr - tt * gs2, S * q - tt * tt);
@@ -126,15 +223,16 @@ __device__ __forceinline__ void mag_iter(const ModelRegs<T, NB>& m, const DevOpt
     // --- update residuals / reddening vector, chi2 in magnitudes (:235-243) ---
     const T AdR = A * dR;
     gs = fma(-AdR, Tm, gs2);                   // sum (e' - A dR D) u
-    T chi = T(0);
+    const P2<T> nAdR = bc2(-AdR), dR2 = bc2(dR);
+    P2<T> chi = bc2(T(0));
 #pragma unroll
-    for (int j = 0; j < NB; j++) {
-        e[j] = fma(-AdR, m.D[j], e[j]);
-        r[j] = fma(dR, m.D[j], r[j]);
-        chi = fma(e[j] * srow[SR_U + j], e[j], chi);
+    for (int p = 0; p < NP; p++) {
+        e[p] = fma2(nAdR, m.D[p], e[p]);
+        r[p] = fma2(dR2, m.D[p], r[p]);
+        chi = fma2(mul2(e[p], u[p]), e[p], chi);
     }
     // logwt uses the un-centred residual e = e' + c (reference quirk)
-    ell = T(-0.5) * (chi + c * (T(2) * gs + c * S));
+    ell = T(-0.5) * (hsum2(chi) + c * (T(2) * gs + c * S));
     delta = Num<T>::max(tabs(dA), tabs(dR));
 }
 
@@ -147,6 +245,61 @@ __device__ __forceinline__ float warp_max_fast(float v) {
 }
 __device__ __forceinline__ double warp_max_fast(double v) { return warp_max((v == v) ? v : -CUDART_INF); }
 
+// initial residuals (brutus/fitting.py:728-733) and the star-weighted model sums of :158-164
+template <typename T, int NB>
+__device__ __forceinline__ void mag_init(const ModelRegs<T, NB>& m, const T* __restrict__ srow,
+                                         P2<T> (&u)[(NB + 1) / 2], P2<T> (&e)[(NB + 1) / 2],
+                                         P2<T> (&r)[(NB + 1) / 2], T& Q, T& Tm, T& gs) {
+    constexpr int NP = (NB + 1) / 2;
+    P2<T> Q2 = bc2(T(0)), T2 = bc2(T(0)), g2 = bc2(T(0));
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        u[p] = ld2(srow + SR_U + 2 * p);
+        e[p] = add2(ld2(srow + SR_CM + 2 * p), m.ncb[p]);
+        r[p] = m.r0[p];
+        const P2<T> Du = mul2(m.D[p], u[p]);
+        Q2 = fma2(Du, m.D[p], Q2);
+        T2 = add2(T2, Du);
+        g2 = fma2(e[p], u[p], g2);
+    }
+    Q = hsum2(Q2); Tm = hsum2(T2); gs = hsum2(g2);
+}
+
+// The whole magnitude-space fit of one (model, star) pair: initial residuals (brutus/fitting.py:728-733),
+// `kspec` iterations of _optimize_fit_mag (:173-264), leaving the centred residuals in e.  (l0, b0) and
+// (l1, b1) are the reduction inputs of iterations kspec-1 and kspec: logwt, and logwt where the step
+// max(|dAv|, |dRv|) is still >= tol (else -inf).  Shared by the sweep and the candidate re-fit so that
+// both evaluate bit-identical arithmetic.
+template <typename T, int NB>
+__device__ __forceinline__ void magfit_one(const ModelRegs<T, NB>& m, const DevOpts<T>& o,
+                                           const T* __restrict__ srow, int kspec, T c,
+                                           P2<T> (&e)[(NB + 1) / 2], T& A, T& rho, T& l0, T& b0, T& l1, T& b1) {
+    constexpr int NP = (NB + 1) / 2;
+    const T ninf = Num<T>::neg_inf();
+    const T S = srow[SR_SC + SC_S];
+    A = o.Abar; rho = o.Rbar;
+    P2<T> u[NP], r[NP];
+    T Q, Tm, gs;
+    mag_init<T, NB>(m, srow, u, e, r, Q, Tm, gs);
+    T ell = T(0), delta = T(0);
+    l0 = ninf; b0 = ninf;
+    if (kspec == 2) {   // the common case, fully unrolled
+        mag_iter<T, NB>(m, o, u, S, c, Q, Tm, e, r, A, rho, gs, ell, delta);
+        l0 = ell;
+        b0 = (delta >= o.mtol) ? l0 : ninf;
+        mag_iter<T, NB>(m, o, u, S, c, Q, Tm, e, r, A, rho, gs, ell, delta);
+    } else {
+        for (int k = 1; k <= kspec; k++) {
+            mag_iter<T, NB>(m, o, u, S, c, Q, Tm, e, r, A, rho, gs, ell, delta);
+            if (k == kspec - 1) {
+                l0 = ell;
+                b0 = (delta >= o.mtol) ? l0 : ninf;
+            }
+        }
+    }
+    l1 = ell;
+    b1 = (delta >= o.mtol) ? l1 : ninf;
+}
 
 // =================================================================================================
 // Kernel 0: iteration-count probe.  Runs kProbeIter mag iterations on every `tile_stride`-th model
@@ -157,7 +310,8 @@ __device__ __forceinline__ double warp_max_fast(double v) { return warp_max((v =
 template <typename T, int NB>
 __global__ void __launch_bounds__(kTile) k_kprobe(const ProbeParams<T> p) {
     using U = typename Enc<T>::U;
-    __shared__ T s_star[kStarChunk][kStarStride];
+    constexpr int NP = (NB + 1) / 2;
+    __shared__ __align__(16) T s_star[kStarChunk][kStarStride];
     __shared__ U s_red[kStarChunk][2 * kProbeIter];
     const int first = blockIdx.y * kStarChunk;
     const int nst = min(kStarChunk, p.nstar - first);
@@ -181,22 +335,13 @@ __global__ void __launch_bounds__(kTile) k_kprobe(const ProbeParams<T> p) {
         const T S = srow[SR_SC + SC_S];
         const T c = srow[SR_SC + SC_MBAR] - m.bbar;
         T A = o.Abar, rho = o.Rbar;
-        T e[NB], r[NB];
-        T Q = T(0), Tm = T(0), gs = T(0);
-#pragma unroll
-        for (int j = 0; j < NB; j++) {
-            const T u = srow[SR_U + j];
-            e[j] = srow[SR_CM + j] - m.cb[j];
-            r[j] = m.r0[j];
-            T Du = m.D[j] * u;
-            Q = fma(Du, m.D[j], Q);
-            Tm += Du;
-            gs = fma(e[j], u, gs);
-        }
+        P2<T> u[NP], e[NP], r[NP];
+        T Q, Tm, gs;
+        mag_init<T, NB>(m, srow, u, e, r, Q, Tm, gs);
 #pragma unroll
         for (int k = 0; k < kProbeIter; k++) {
             T ell, delta;
-            mag_iter<T, NB>(m, o, srow, S, c, Q, Tm, e, r, A, rho, gs, ell, delta);
+            mag_iter<T, NB>(m, o, u, S, c, Q, Tm, e, r, A, rho, gs, ell, delta);
             T l = valid ? ell : ninf;
             T b = (delta >= o.mtol) ? l : ninf;
             l = warp_max_fast(l);
@@ -212,51 +357,6 @@ __global__ void __launch_bounds__(kTile) k_kprobe(const ProbeParams<T> p) {
     __syncthreads();
     for (int t = threadIdx.x; t < nst * 2 * kProbeIter; t += kTile)
         atomicMax(&p.out[(int64_t)first * 2 * kProbeIter + t], s_red[t / (2 * kProbeIter)][t % (2 * kProbeIter)]);
-}
-
-// The whole magnitude-space fit of one (model, star) pair: initial residuals (brutus/fitting.py:728-733),
-// `kspec` iterations of _optimize_fit_mag (:173-264), leaving the centred residuals in e.  (l0, b0) and
-// (l1, b1) are the reduction inputs of iterations kspec-1 and kspec: logwt, and logwt where the step
-// max(|dAv|, |dRv|) is still >= tol (else -inf).  Shared by the sweep and the candidate re-fit so that
-// both evaluate bit-identical arithmetic.
-template <typename T, int NB>
-__device__ __forceinline__ void magfit_one(const ModelRegs<T, NB>& m, const DevOpts<T>& o,
-                                           const T* __restrict__ srow, int kspec, T c, T (&e)[NB], T& A,
-                                           T& rho, T& l0, T& b0, T& l1, T& b1) {
-    const T ninf = Num<T>::neg_inf();
-    const T S = srow[SR_SC + SC_S];
-    A = o.Abar; rho = o.Rbar;
-    T r[NB];
-    T Q = T(0), Tm = T(0), gs = T(0);
-    // brutus/fitting.py:158-164 (rp_den, srp_mix) and the initial residuals (:733)
-#pragma unroll
-    for (int j = 0; j < NB; j++) {
-        const T u = srow[SR_U + j];
-        e[j] = srow[SR_CM + j] - m.cb[j];
-        r[j] = m.r0[j];
-        T Du = m.D[j] * u;
-        Q = fma(Du, m.D[j], Q);
-        Tm += Du;
-        gs = fma(e[j], u, gs);
-    }
-    T ell = T(0), delta = T(0);
-    l0 = ninf; b0 = ninf;
-    if (kspec == 2) {   // the common case, fully unrolled
-        mag_iter<T, NB>(m, o, srow, S, c, Q, Tm, e, r, A, rho, gs, ell, delta);
-        l0 = ell;
-        b0 = (delta >= o.mtol) ? l0 : ninf;
-        mag_iter<T, NB>(m, o, srow, S, c, Q, Tm, e, r, A, rho, gs, ell, delta);
-    } else {
-        for (int k = 1; k <= kspec; k++) {
-            mag_iter<T, NB>(m, o, srow, S, c, Q, Tm, e, r, A, rho, gs, ell, delta);
-            if (k == kspec - 1) {
-                l0 = ell;
-                b0 = (delta >= o.mtol) ? l0 : ninf;
-            }
-        }
-    }
-    l1 = ell;
-    b1 = (delta >= o.mtol) ? l1 : ninf;
 }
 
 // =================================================================================================
@@ -283,8 +383,9 @@ __device__ __forceinline__ void magfit_one(const ModelRegs<T, NB>& m, const DevO
 template <typename T, int NB>
 __global__ void __launch_bounds__(kTile) k_magfit(const SweepParams<T> p) {
     using U = typename Enc<T>::U;
+    constexpr int NP = (NB + 1) / 2;
     static_assert(kStarChunk == 32, "lane <-> star mapping of the reductions");
-    __shared__ T s_star[kStarChunk][kStarStride];
+    __shared__ __align__(16) T s_star[kStarChunk][kStarStride];
     __shared__ int s_slot[kStarChunk];
     __shared__ int s_kspec[kStarChunk];
     __shared__ T s_snap[kStarChunk][2];
@@ -324,7 +425,7 @@ __global__ void __launch_bounds__(kTile) k_magfit(const SweepParams<T> p) {
         const T* __restrict__ srow = s_star[s];
         const T c = srow[SR_SC + SC_MBAR] - m.bbar;
         T A, rho, l0, b0, l1, b1;
-        T e[NB];
+        P2<T> e[NP];
         magfit_one<T, NB>(m, o, srow, s_kspec[s], c, e, A, rho, l0, b0, l1, b1);
         // --- _get_sed_mle at the fitted (Av, Rv) (:267) and the cull statistic (:745-756) ---
         Mle<T, NB> r4;
@@ -369,40 +470,15 @@ __global__ void __launch_bounds__(kTile) k_magfit(const SweepParams<T> p) {
     }
 }
 
-// Model coefficients of one model from the model-major copy of the grid (3-4 sectors per model).
-template <typename T, int NB>
-__device__ __forceinline__ void load_model_row(const float* __restrict__ rows, int64_t i, const DevOpts<T>& o,
-                                               ModelRegs<T, NB>& m) {
-    constexpr int RS = row_stride(NB);
-    float v[RS];
-    const float4* __restrict__ p4 = reinterpret_cast<const float4*>(rows + i * RS);
-#pragma unroll
-    for (int k = 0; k < RS / 4; k++) {
-        float4 t = __ldg(p4 + k);
-        v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
-    }
-    T sum = T(0);
-#pragma unroll
-    for (int j = 0; j < NB; j++) {
-        T mu = (T)v[j], R = (T)v[NB + j], D = (T)v[2 * NB + j];
-        m.D[j] = D;
-        m.r0[j] = fma(o.Rbar, D, R);
-        m.cb[j] = fma(o.Abar, m.r0[j], mu);
-        sum += m.cb[j];
-    }
-    m.bbar = sum * (T(1) / T(NB));
-#pragma unroll
-    for (int j = 0; j < NB; j++) m.cb[j] -= m.bbar;
-}
-
 // =================================================================================================
 // Kernel 2: exact re-fit of the candidates.  One thread per candidate record (star, model): repeats the
 // sweep's arithmetic for the pair, applies the exact cull test (:758-759) against the now final
-// per-star maximum, initialises the record (stepsize 1, lnl_old = -1e300, :778-779) and appends the
-// survivors to the flux work list.
+// per-star maximum, initialises the record and appends the survivors to the compact flux working set
+// (stepsize 1, lnl_old = -1e300, :778-779).
 // =================================================================================================
 template <typename T, int NB>
 __global__ void __launch_bounds__(kTile) k_refit(const RefitParams<T> p) {
+    constexpr int NP = (NB + 1) / 2;
     const int64_t q = (int64_t)blockIdx.x * kTile + threadIdx.x;
     const bool inr = q < p.ncand;
     bool surv = false;
@@ -417,7 +493,7 @@ __global__ void __launch_bounds__(kTile) k_refit(const RefitParams<T> p) {
         load_model_row<T, NB>(p.rows, i, o, m);
         const T c = srow[SR_SC + SC_MBAR] - m.bbar;
         T A, rho, l0, b0, l1, b1;
-        T e[NB];
+        P2<T> e[NP];
         magfit_one<T, NB>(m, o, srow, p.star_int[slot * SI_COUNT + SI_KSPEC], c, e, A, rho, l0, b0, l1, b1);
         Mle<T, NB> r4;
         mle_from_resid<T, NB>(e, c, srow, r4);
@@ -464,13 +540,15 @@ __global__ void __launch_bounds__(kTile) k_refit(const RefitParams<T> p) {
 // residuals at an arbitrary (A, rho): e'_j = cm_j - cb_j - (A r_j - Abar r0_j), r_j = r0_j + (rho - Rbar) D_j
 template <typename T, int NB>
 __device__ __forceinline__ void resid_at(const ModelRegs<T, NB>& m, const DevOpts<T>& o,
-                                         const T* __restrict__ srow, T A, T rho, T (&e)[NB], T (&r)[NB]) {
-    const T drho = rho - o.Rbar;
+                                         const T* __restrict__ srow, T A, T rho, P2<T> (&e)[(NB + 1) / 2],
+                                         P2<T> (&r)[(NB + 1) / 2]) {
+    constexpr int NP = (NB + 1) / 2;
+    const P2<T> drho = bc2(rho - o.Rbar), A2 = bc2(A), nAbar = bc2(-o.Abar);
 #pragma unroll
-    for (int j = 0; j < NB; j++) {
-        r[j] = fma(drho, m.D[j], m.r0[j]);
-        T red = fma(A, r[j], -o.Abar * m.r0[j]);
-        e[j] = (srow[SR_CM + j] - m.cb[j]) - red;
+    for (int p = 0; p < NP; p++) {
+        r[p] = fma2(drho, m.D[p], m.r0[p]);
+        const P2<T> red = fma2(A2, r[p], mul2(nAbar, m.r0[p]));
+        e[p] = sub2(add2(ld2(srow + SR_CM + 2 * p), m.ncb[p]), red);
     }
 }
 
@@ -483,6 +561,7 @@ __device__ __forceinline__ void resid_at(const ModelRegs<T, NB>& m, const DevOpt
 // =================================================================================================
 template <typename T, int NB>
 __global__ void __launch_bounds__(kTile) k_flux(const FluxParams<T> p) {
+    constexpr int NP = (NB + 1) / 2;
     const int64_t t = (int64_t)blockIdx.x * kTile + threadIdx.x;
     const bool inrange = t < p.nsv;
     int slot = inrange ? p.sv.star[t] : -1;
@@ -496,26 +575,27 @@ __global__ void __launch_bounds__(kTile) k_flux(const FluxParams<T> p) {
         load_model_row<T, NB>(p.rows, i, o, m);
         const T c = srow[SR_SC + SC_MBAR] - m.bbar;
         T A = p.sv.av[t], rho = p.sv.rv[t], eta = p.sv.eta[t], lold = p.sv.lold[t];
-        T e[NB], r[NB];
+        P2<T> e[NP], r[NP];
         Mle<T, NB> r4;
         resid_at<T, NB>(m, o, srow, A, rho, e, r);
         mle_from_resid<T, NB>(e, c, srow, r4);
         T lnew = lold;
         for (int it = 0; it < p.nit; it++) {
             // one (dAv, dRv) step from the current model / residuals (:385-420)
-            T an = T(0), ad = T(0), rn = T(0), rd = T(0);
+            P2<T> an = bc2(T(0)), ad = bc2(T(0)), rn = bc2(T(0)), rd = bc2(T(0));
+            const P2<T> sh = bc2(r4.shat);
 #pragma unroll
-            for (int j = 0; j < NB; j++) {
-                T Ms = r4.shat * r4.gb[j];                 // M_j / sigma_j
-                T tj = srow[SR_AL + j] - Ms;               // resid_j / sigma_j
-                T rM = r[j] * Ms, DM = m.D[j] * Ms;
-                an = fma(rM, tj, an);
-                ad = fma(rM, rM, ad);
-                rn = fma(DM, tj, rn);
-                rd = fma(DM, DM, rd);
+            for (int pp = 0; pp < NP; pp++) {
+                const P2<T> Ms = mul2(sh, r4.gb[pp]);                        // M_j / sigma_j
+                const P2<T> tj = sub2(ld2(srow + SR_AL + 2 * pp), Ms);       // resid_j / sigma_j
+                const P2<T> rM = mul2(r[pp], Ms), DM = mul2(m.D[pp], Ms);
+                an = fma2(rM, tj, an);
+                ad = fma2(rM, rM, ad);
+                rn = fma2(DM, tj, rn);
+                rd = fma2(DM, DM, rd);
             }
-            T dA = Num<T>::div(fma(T(kFac), an, (o.Abar - A) * o.PA), fma(T(kFac * kFac), ad, o.PA)) * eta;
-            T dR = Num<T>::div(fma(T(kFac), rn, (o.Rbar - rho) * o.PR), fma(T(kFac * kFac), rd, o.PR)) * eta;
+            T dA = Num<T>::div(fma(T(kFac), hsum2(an), (o.Abar - A) * o.PA), fma(T(kFac * kFac), hsum2(ad), o.PA)) * eta;
+            T dR = Num<T>::div(fma(T(kFac), hsum2(rn), (o.Rbar - rho) * o.PR), fma(T(kFac * kFac), hsum2(rd), o.PR)) * eta;
             dA = tmax(dA, o.avmin - A);
             dA = tmin(dA, o.avmax - A);
             A += dA;
@@ -555,6 +635,7 @@ __global__ void __launch_bounds__(kTile) k_flux(const FluxParams<T> p) {
 // =================================================================================================
 template <typename T, int NB, typename O>
 __global__ void __launch_bounds__(kTile) k_records(const RecordParams<T, O> p) {
+    constexpr int NP = (NB + 1) / 2;
     const int64_t t = (int64_t)blockIdx.x * kTile + threadIdx.x;
     if (t >= p.nrec) return;
     const bool modeA = p.sel_q != nullptr;
@@ -585,31 +666,33 @@ __global__ void __launch_bounds__(kTile) k_records(const RecordParams<T, O> p) {
     ModelRegs<T, NB> m;
     load_model_row<T, NB>(p.rows, i, o, m);
     const T c = srow[SR_SC + SC_MBAR] - m.bbar;
-    T e[NB], r[NB];
+    P2<T> e[NP], r[NP];
     Mle<T, NB> r4;
     resid_at<T, NB>(m, o, srow, A, rho, e, r);
     mle_from_resid<T, NB>(e, c, srow, r4);
     // cross terms (:526-561) in sigma-normalised units; see the header comment and DESIGN.md
-    T sa = T(0), sr = T(0), ar = T(0), aden = T(0), rden = T(0);
+    P2<T> sa = bc2(T(0)), sr = bc2(T(0)), ar = bc2(T(0)), aden = bc2(T(0)), rden = bc2(T(0));
+    const P2<T> sh = bc2(r4.shat), kA = bc2(T(kC2) * A), one = bc2(T(1));
 #pragma unroll
-    for (int j = 0; j < NB; j++) {
-        T Ms = r4.shat * r4.gb[j];
-        T tj = srow[SR_AL + j] - Ms;
-        T h = Num<T>::exp2(T(kC2) * A * r[j]);     // F0_j / F_j = 10^(0.4 A r_j)   (:529-530)
-        T mmr = Ms - tj;                           // (models - resid)/sigma         (:539-542)
-        sa = fma(r[j] * r4.gb[j], mmr, sa);
-        sr = fma(m.D[j] * r4.gb[j], mmr, sr);
-        T DM = m.D[j] * Ms, rM = r[j] * Ms;
-        ar = fma(DM, fma(Ms, T(1) - h, -tj), ar);  // drvecs (reddening - resid)/var (:550-551)
-        aden = fma(rM, rM, aden);
-        rden = fma(DM, DM, rden);
+    for (int pp = 0; pp < NP; pp++) {
+        const P2<T> Ms = mul2(sh, r4.gb[pp]);
+        const P2<T> tj = sub2(ld2(srow + SR_AL + 2 * pp), Ms);
+        const P2<T> x = mul2(kA, r[pp]);
+        const P2<T> h = mk2(Num<T>::exp2(lo2(x)), Num<T>::exp2(hi2(x)));   // F0_j / F_j = 10^(0.4 A r_j)   (:529-530)
+        const P2<T> mmr = sub2(Ms, tj);                                     // (models - resid)/sigma         (:539-542)
+        sa = fma2(mul2(r[pp], r4.gb[pp]), mmr, sa);
+        sr = fma2(mul2(m.D[pp], r4.gb[pp]), mmr, sr);
+        const P2<T> DM = mul2(m.D[pp], Ms), rM = mul2(r[pp], Ms);
+        ar = fma2(DM, sub2(mul2(Ms, sub2(one, h)), tj), ar);                // drvecs (reddening - resid)/var (:550-551)
+        aden = fma2(rM, rM, aden);
+        rden = fma2(DM, DM, rden);
     }
     const O f = (O)kFac, E = (O)r4.E;
     const O ss = (O)r4.den * E * E;
-    const O dsa = f * E * (O)sa, dsr = f * E * (O)sr;
-    const O dar = f * (O)ar;
-    const O daa = f * f * (O)aden + (O)o.PA + (O)(1. / (0.05 * 0.05));
-    const O drr = f * f * (O)rden + (O)o.PR + (O)(1. / (0.1 * 0.1));
+    const O dsa = f * E * (O)hsum2(sa), dsr = f * E * (O)hsum2(sr);
+    const O dar = f * (O)hsum2(ar);
+    const O daa = f * f * (O)hsum2(aden) + (O)o.PA + (O)(1. / (0.05 * 0.05));
+    const O drr = f * f * (O)hsum2(rden) + (O)o.PR + (O)(1. / (0.1 * 0.1));
     if (modeA) {
         O* w = p.o_icov + t;
         w[0] = ss; w[p.ld] = dsa; w[2 * p.ld] = dsr; w[3 * p.ld] = daa; w[4 * p.ld] = dar; w[5 * p.ld] = drr;
@@ -620,14 +703,14 @@ __global__ void __launch_bounds__(kTile) k_records(const RecordParams<T, O> p) {
 }
 
 // ---- launchers -------------------------------------------------------------------------------------
-template <typename T, int NB> void launch_magfit(const SweepParams<T>& p, cudaStream_t st) {
-    dim3 grid((unsigned)(p.npad / kTile), (unsigned)((p.nlist + kStarChunk - 1) / kStarChunk));
-    k_magfit<T, NB><<<grid, kTile, 0, st>>>(p);
-}
 template <typename T, int NB> void launch_kprobe(const ProbeParams<T>& p, cudaStream_t st) {
     const int64_t ntile = p.npad / kTile;
     dim3 grid((unsigned)((ntile + p.tile_stride - 1) / p.tile_stride), (unsigned)((p.nstar + kStarChunk - 1) / kStarChunk));
     k_kprobe<T, NB><<<grid, kTile, 0, st>>>(p);
+}
+template <typename T, int NB> void launch_magfit(const SweepParams<T>& p, cudaStream_t st) {
+    dim3 grid((unsigned)(p.npad / kTile), (unsigned)((p.nlist + kStarChunk - 1) / kStarChunk));
+    k_magfit<T, NB><<<grid, kTile, 0, st>>>(p);
 }
 template <typename T, int NB> void launch_refit(const RefitParams<T>& p, cudaStream_t st) {
     if (p.ncand <= 0) return;
