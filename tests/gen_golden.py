@@ -35,6 +35,9 @@ LOGLIKE_CASES = {
     "avlim6_rvprior": dict(grid=dict(nmodel=2_000, nfilt=12, seed=1012),
                            stars=dict(nstar=3, seed=2012, av_max=6.0, dropout=0.1),
                            kw=dict(avlim=(0., 6.), rv_gauss=(3.1, 0.3), av_gauss=(1.0, 2.0))),
+    # stellar-locus mock (the bench workload's grid family): K_mag = 1 and 2 both occur
+    "locus_8band": dict(grid=dict(nmodel=3_000, nfilt=8, seed=1014, kind="locus"),
+                        stars=dict(nstar=5, seed=2014, dropout=0.05), kw={}),
     "loose_tol": dict(grid=dict(nmodel=2_000, nfilt=6, seed=1013),
                       stars=dict(nstar=3, seed=2013, snr_range=(5., 20.)),
                       kw=dict(ltol=1e-3, ltol_subthresh=5e-2, init_thresh=1e-4)),
@@ -50,8 +53,10 @@ def build_case(name):
     return grid, labels, st, spec["kw"]
 
 
-def gen_loglike(fit):
+def gen_loglike(fit, only=None):
     for name in LOGLIKE_CASES:
+        if only and name not in only:
+            continue
         grid, labels, st, kw = build_case(name)
         gF = np.array(grid, order="F")  # as _fit does, brutus/fitting.py:1964
         out = {}
@@ -95,5 +100,7 @@ def gen_fit(fit):
 if __name__ == "__main__":
     fit = ref_import.import_reference()
     os.makedirs(GOLD, exist_ok=True)
-    gen_loglike(fit)
-    gen_fit(fit)
+    only = [a for a in sys.argv[1:] if a in LOGLIKE_CASES]
+    gen_loglike(fit, only=only)
+    if not only:
+        gen_fit(fit)
