@@ -128,11 +128,20 @@ def make_stars(cfg_id, cfg, grid, rank):
                            dropout=cfg["dropout"])
 
 
+def host_cores():
+    """Cores this process may run on.  torchrun exports OMP_NUM_THREADS=1, which would make the CPU
+    arm single-threaded: the thread count is therefore passed to the oracle explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_sample(cfg, grid, stars, nthreads, nsample):
     """Times the oracle (port of the reference loglike) on `nsample` stars with `nthreads` threads."""
     from oracle import oracle
     oracle.build()
-    nt = nthreads or oracle.num_threads()
+    nt = nthreads or host_cores()
     sl = slice(0, nsample)
     t0 = time.perf_counter()
     oracle.loglike_batch(stars["flux"][sl], stars["err"][sl], stars["mask"][sl], grid,
@@ -150,7 +159,7 @@ def run_reference(args):
     grid, _ = make_inputs(args.config, cfg, 0)
     from oracle import oracle
     oracle.build()
-    nt = oracle.num_threads()
+    nt = host_cores()
     per_step = max(nt, 8) if cfg["nmodel"] <= 1_000_000 else max(nt // 2, 4)
     cfg_s = dict(cfg, nstar=per_step * (args.steps + args.warmup))
     stars = make_stars(args.config, cfg_s, grid, 0)
@@ -314,7 +323,7 @@ def run_b200(args):
         "region_wall_s": t_region,
     }
     if world == 1 and not args.no_cpu:
-        nt_probe = os.cpu_count() or 1
+        nt_probe = host_cores()
         nsample = max(8, min(2 * nt_probe, 64)) if cfg["nmodel"] <= 1_000_000 else max(4, min(nt_probe, 32))
         rate, nt, dt = cpu_sample(cfg, grid, stars, 0, min(nsample, nstar))
         line["cpu_baseline"] = {"value": rate, "unit": "stars/s", "cores": nt, "kind": "port",

@@ -6,8 +6,12 @@ Tolerances (stated, per output):
                    and identical cull sets.
   float32 kernels: chi2, lnl  |d| <= 2e-3 + 2e-5 |x|   (S/N 100 photometry amplifies 1e-7 model
                                                        errors to ~1e-5 sigma residual errors)
-                   av   |d| <= 2e-4 ; rv |d| <= 2e-3 ; scale rel 2e-5 ; icov rel 2e-3 of the
-                   matrix scale sqrt(|ii||jj|)
+                   av   |d| <= 2e-4 ; rv |d| <= 2e-3 ; icov rel 2e-3 of the matrix scale
+                   sqrt(|ii||jj|)
+                   scale rel 2e-5 + 0.92 (1.3 |d av| + 0.06 Av |d rv|): the scale is the conditional
+                   MLE at the fitted (Av, Rv), d ln s / d Av = 0.4 ln10 <r_j> with r_j <= 1.3 and
+                   d ln s / d Rv = 0.4 ln10 Av <dR_j> with |dR_j| <= 0.06, so an (allowed) Av error
+                   of a badly fitting, high-Av model (chi2 ~ 100, Av ~ 7.5) propagates one to one
   for models whose cull membership matches; membership may differ only within 1e-3 of the
   threshold, and the mag/flux iteration counts must match the oracle's.
 """
@@ -57,7 +61,10 @@ def _compare_f32(out, ref, tag, strict_idx=None):
     close(np.where(fin, lnl, 0), np.where(fin, rlnl, 0), 2e-3, 2e-5, "lnl")
     close(av, rav, 2e-4, 0, "av")
     close(rv, rrv, 2e-3, 0, "rv")
-    close(sc, rsc, 0, 2e-5, "scale")
+    prop = 0.92 * (1.3 * np.abs(av - rav) + 0.06 * np.abs(rav) * np.abs(rv - rrv))
+    dsc = np.abs(sc[sel] - rsc[sel]) / np.abs(rsc[sel])
+    bad = dsc > 2e-5 + prop[sel]
+    assert not bad.any(), (tag, "scale", int(bad.sum()), float(dsc[bad].max()))
     d = np.abs(ic - ric) / _icov_scale(ric)
     assert d[sel].max() < 2e-3, (tag, "icov", float(d[sel].max()))
 
