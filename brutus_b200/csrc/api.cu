@@ -310,6 +310,34 @@ struct EngineBase {
         }                                                                                      \
     } while (0)
 
+// Small control read-backs (per-star maxima, counters) do NOT go through the copy engines: a D2H
+// cudaMemcpyAsync on the compute stream queues behind the record copies in flight on the copy stream
+// (hundreds of MB each), which serialised the kernels of batch g+1 with the record D2H of batch g.
+// Instead a tiny kernel stores the words into mapped pinned host memory (SM-issued PCIe writes).
+__global__ void k_publish(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst_host, size_t nwords) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nwords) dst_host[t] = src[t];
+}
+
+// host array in mapped pinned memory (cudaHostAllocMapped; with UVA the same pointer is valid in kernels)
+template <typename P> struct PinVec {
+    P* p = nullptr;
+    size_t n = 0;
+    cudaError_t resize(size_t want) {
+        if (want <= n) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaHostAlloc((void**)&p, want * sizeof(P), cudaHostAllocMapped | cudaHostAllocPortable);
+        if (e == cudaSuccess) { n = want; std::memset(p, 0, want * sizeof(P)); }
+        return e;
+    }
+    P* data() { return p; }
+    const P* data() const { return p; }
+    P& operator[](size_t i) { return p[i]; }
+    const P& operator[](size_t i) const { return p[i]; }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; n = 0; }
+};
+
 template <typename P> struct DevBuf {
     P* p = nullptr;
     size_t n = 0;
@@ -417,9 +445,18 @@ template <typename T> struct Engine : EngineBase {
     DevBuf<char> d_flush, d_stage[2];
 
     std::vector<T> h_stars, h_ext;
-    std::vector<int> h_int, h_list, h_nsurv, h_nsel;
-    std::vector<U> h_red, h_probe;
-    std::vector<int64_t> h_ncand, h_base;
+    std::vector<int> h_list;
+    std::vector<int64_t> h_base;
+    PinVec<int> h_int, h_nsurv, h_nsel;      // control read-backs: mapped pinned memory (k_publish)
+    PinVec<U> h_red, h_probe;
+    PinVec<int64_t> h_ncand;
+
+    // device -> mapped pinned host, on the compute stream, without touching a copy engine
+    void publish(void* host_dst, const void* dev_src, size_t bytes) {
+        const size_t nw = bytes / 4;
+        if (!nw) return;
+        k_publish<<<(unsigned)((nw + 255) / 256), 256, 0, stream>>>((const uint32_t*)dev_src, (uint32_t*)host_dst, nw);
+    }
 
     enum { CTR_NSV = 0, CTR_ANY = 1, CTR_COUNT = 64 };
 
@@ -440,6 +477,7 @@ template <typename T> struct Engine : EngineBase {
         }
         if (arena) cudaFreeHost(arena);
         if (h_pin) cudaFreeHost(h_pin);
+        h_int.release(); h_nsurv.release(); h_nsel.release(); h_red.release(); h_probe.release(); h_ncand.release();
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -454,7 +492,7 @@ template <typename T> struct Engine : EngineBase {
             CK(cudaEventCreateWithFlags(&ev_rec[k], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&ev_cp[k], cudaEventDisableTiming));
         }
-        CK(cudaHostAlloc((void**)&h_pin, CTR_COUNT * sizeof(int), cudaHostAllocDefault));
+        CK(cudaHostAlloc((void**)&h_pin, CTR_COUNT * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
         CK(d_ctr.ensure(CTR_COUNT));
         CK(d_tot.ensure(2));
         return BF_OK;
@@ -534,14 +572,14 @@ template <typename T> struct Engine : EngineBase {
         CK(d_poolT.ensure((size_t)14 * pool_cap));
         CK(d_blk.ensure((size_t)(pool_cap / kTile + 2)));
         h_stars.resize((size_t)batch_cap * kStarStride);
-        h_int.resize((size_t)batch_cap * SI_COUNT);
+        CK(h_int.resize((size_t)batch_cap * SI_COUNT));
         h_list.resize(batch_cap);
-        h_red.resize((size_t)batch_cap * kNumRed);
-        h_probe.resize((size_t)batch_cap * 2 * kProbeIter);
-        h_ncand.resize(batch_cap);
+        CK(h_red.resize((size_t)batch_cap * kNumRed));
+        CK(h_probe.resize((size_t)batch_cap * 2 * kProbeIter));
+        CK(h_ncand.resize(batch_cap));
         h_base.resize(batch_cap);
-        h_nsurv.resize(batch_cap);
-        h_nsel.resize(batch_cap);
+        CK(h_nsurv.resize(batch_cap));
+        CK(h_nsel.resize(batch_cap));
         return BF_OK;
     }
 
@@ -614,7 +652,7 @@ template <typename T> struct Engine : EngineBase {
         kt->kprobe(pp, stream);
         stats.kernel_launches++;
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(h_probe.data(), d_probe.p, (size_t)ns * 2 * kProbeIter * sizeof(U), cudaMemcpyDeviceToHost, stream));
+        publish(h_probe.data(), d_probe.p, (size_t)ns * 2 * kProbeIter * sizeof(U));
         stats.ms_select += phase_end();
         for (int s = 0; s < ns; s++) {
             int k = 1;
@@ -652,8 +690,8 @@ template <typename T> struct Engine : EngineBase {
             k_cand_scan<<<nl, 1024, 0, stream>>>(d_cand.p, d_wpre.p, d_list.p, nwords, d_ncand.p);
             stats.kernel_launches++;
             CK(cudaGetLastError());
-            CK(cudaMemcpyAsync(h_red.data(), d_red.p, (size_t)ns * kNumRed * sizeof(U), cudaMemcpyDeviceToHost, stream));
-            CK(cudaMemcpyAsync(h_ncand.data(), d_ncand.p, (size_t)ns * sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+            publish(h_red.data(), d_red.p, (size_t)ns * kNumRed * sizeof(U));
+            publish(h_ncand.data(), d_ncand.p, (size_t)ns * sizeof(int64_t));
             CK(cudaStreamSynchronize(stream));
             {
                 float ms = 0.f;
@@ -710,8 +748,8 @@ template <typename T> struct Engine : EngineBase {
             stats.kernel_launches += 2;
             CK(cudaGetLastError());
         }
-        CK(cudaMemcpyAsync(h_pin, d_ctr.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
-        CK(cudaMemcpyAsync(h_nsurv.data() + g0, d_nsurv.p + g0, (size_t)ng * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        publish(h_pin, d_ctr.p, sizeof(int));
+        publish(h_nsurv.data() + g0, d_nsurv.p + g0, (size_t)ng * sizeof(int));
         stats.ms_select += phase_end();
         const int64_t nsv = h_pin[0];
         stats.candidates += tot;
@@ -740,7 +778,7 @@ template <typename T> struct Engine : EngineBase {
                 first = false;
             }
             CK(cudaGetLastError());
-            CK(cudaMemcpyAsync(h_pin, d_ctr.p + any_slot, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            publish(h_pin, d_ctr.p + any_slot, sizeof(int));
             CK(cudaStreamSynchronize(stream));
             if (!h_pin[0]) break;
         }
@@ -933,9 +971,9 @@ template <typename T> struct Engine : EngineBase {
                     stats.kernel_launches += 2;
                     CK(cudaGetLastError());
                 }
-                CK(cudaMemcpyAsync(h_nsel.data() + g0, d_nsel.p + g0, (size_t)ng * sizeof(int), cudaMemcpyDeviceToHost, stream));
-                CK(cudaMemcpyAsync(h_red.data(), d_red.p, (size_t)ns * kNumRed * sizeof(U), cudaMemcpyDeviceToHost, stream));
-                CK(cudaMemcpyAsync(h_int.data(), d_star_int.p, (size_t)ns * SI_COUNT * sizeof(int), cudaMemcpyDeviceToHost, stream));
+                publish(h_nsel.data() + g0, d_nsel.p + g0, (size_t)ng * sizeof(int));
+                publish(h_red.data(), d_red.p, (size_t)ns * kNumRed * sizeof(U));
+                publish(h_int.data(), d_star_int.p, (size_t)ns * SI_COUNT * sizeof(int));
                 stats.ms_select += phase_end();
                 stats.d2h_bytes += (size_t)ns * (kNumRed * sizeof(U) + SI_COUNT * sizeof(int)) + ng * sizeof(int);
                 // ---- was the sweep's candidate set a superset of the selection?  It is whenever the final
@@ -997,9 +1035,12 @@ template <typename T> struct Engine : EngineBase {
                         CK(cudaStreamWaitEvent(copy_stream, ev_rec[buf], 0));
                         CK(cudaMemcpyAsync(arena + (size_t)11 * arena_cap * sizeof(T) + (size_t)written * sizeof(int),
                                            rp.o_idx, (size_t)nsel_tot * sizeof(int), cudaMemcpyDeviceToHost, copy_stream));
-                        CK(cudaMemcpy2DAsync(arena + (size_t)written * sizeof(T),
-                                             (size_t)arena_cap * sizeof(T), b, (size_t)nsel_tot * sizeof(T),
-                                             (size_t)nsel_tot * sizeof(T), record_rows, cudaMemcpyDeviceToHost, copy_stream));
+                        // one plain 1-D copy per record row (each 100+ MB): the pitched 2-D copy ran at
+                        // ~42 GB/s on the PCIe Gen5 link, 1-D copies reach the measured ~57 GB/s
+                        for (int r = 0; r < record_rows; r++)
+                            CK(cudaMemcpyAsync(arena + ((size_t)r * arena_cap + (size_t)written) * sizeof(T),
+                                               b + (size_t)r * nsel_tot, (size_t)nsel_tot * sizeof(T),
+                                               cudaMemcpyDeviceToHost, copy_stream));
                         CK(cudaEventRecord(ev_cp[buf], copy_stream));
                         stats.d2h_bytes += (size_t)nsel_tot * (sizeof(int) + record_rows * sizeof(T));
                     }
