@@ -97,10 +97,52 @@ def gen_fit(fit):
     print("wrote fit_generator")
 
 
+def gen_galprior(fit):
+    """Golden values of the reference's default Galactic prior (brutus/pdf.py:476-749).  astropy is not
+    installed, so `SkyCoord(...).galactocentric...represent_as(CylRep)` (:630-635) is served by a
+    stand-in that applies oracle.galprior.galactic_to_cyl; every other line is the reference's own."""
+    import types
+    from brutus import pdf as rpdf  # the reference module
+    from oracle import galprior as gp
+
+    class _Val(object):
+        def __init__(self, v):
+            self.value = v
+
+    class _Sky(object):
+        def __init__(self, l=None, b=None, distance=None, frame=None):
+            self.R, self.Z = gp.galactic_to_cyl(np.asarray(distance), (np.asarray(l).flat[0], np.asarray(b).flat[0]))
+            self.galactocentric = self
+            self.cartesian = self
+
+        def represent_as(self, _):
+            return types.SimpleNamespace(rho=_Val(self.R), z=_Val(self.Z))
+
+    rpdf.SkyCoord = _Sky
+    rpdf.units = types.SimpleNamespace(deg=1.0, kpc=1.0)
+    rs = np.random.RandomState(4242)
+    n = 400
+    dists = 10. ** rs.uniform(-2., 1.7, n)
+    lab = np.zeros(n, dtype=[("feh", "f8"), ("loga", "f8")])
+    lab["feh"] = rs.uniform(-3., 0.6, n)
+    lab["loga"] = rs.uniform(6.5, 10.2, n)          # a few ages beyond 13.8 Gyr -> -inf
+    out = dict(dists=dists, feh=lab["feh"], loga=lab["loga"])
+    coords = [(0., 0.), (30., 5.), (180., -60.), (271.3, 89.), (95., -1.5)]
+    out["coords"] = np.array(coords)
+    for k, c in enumerate(coords):
+        out["full_%d" % k] = rpdf.gal_lnprior(dists, c, labels=lab)
+        out["feh_only_%d" % k] = rpdf.gal_lnprior(dists, c, labels=lab[["feh"]])
+        out["nolabels_%d" % k] = rpdf.gal_lnprior(dists, c)
+    np.savez_compressed(os.path.join(GOLD, "galprior.npz"), **out)
+    print("wrote galprior")
+
+
 if __name__ == "__main__":
     fit = ref_import.import_reference()
     os.makedirs(GOLD, exist_ok=True)
-    only = [a for a in sys.argv[1:] if a in LOGLIKE_CASES]
+    only = [a for a in sys.argv[1:] if a in LOGLIKE_CASES or a == "galprior"]
     gen_loglike(fit, only=only)
     if not only:
         gen_fit(fit)
+    if not only or "galprior" in sys.argv[1:]:
+        gen_galprior(fit)
