@@ -19,7 +19,8 @@ MAX_FILT = 16
 # every symbol include/brutus_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = ("bf_default_options", "bf_create", "bf_destroy", "bf_last_error", "bf_set_grid",
            "bf_set_grid_device", "bf_set_labels", "bf_loglike_full", "bf_sweep_batch",
-           "bf_get_stats", "bf_flush_l2", "bf_device_count", "bf_version")
+           "bf_get_stats", "bf_flush_l2", "bf_device_count", "bf_version",
+           "bf_default_gal_params", "bf_default_post_options", "bf_set_model_priors", "bf_fit_batch")
 
 
 class BrutusCudaError(RuntimeError):
@@ -49,10 +50,36 @@ class Stats(C.Structure):
                 ("magfit_launches", C.c_int64), ("magfit_star_passes", C.c_int64),
                 ("resweeps", C.c_int64), ("candidates", C.c_int64), ("fallbacks", C.c_int64),
                 ("survivors", C.c_int64),
-                ("selected", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+                ("selected", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("ms_post", C.c_double), ("selected2", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+GAL_FIELDS = ("R_solar", "Z_solar", "R_thin", "Z_thin", "Rs_thin", "R_thick", "Z_thick", "f_thick",
+              "Rs_thick", "Rs_halo", "q_halo_ctr", "q_halo_inf", "r_q_halo", "eta_halo", "f_halo",
+              "feh_thin", "feh_thin_sigma", "feh_thick", "feh_thick_sigma", "feh_halo", "feh_halo_sigma",
+              "max_age", "min_age", "feh_age_ctr", "feh_age_scale", "nsigma_from_max_age", "max_sigma",
+              "min_sigma", "galcen_distance", "z_sun")
+
+
+class GalParams(C.Structure):
+    """bf_gal_params: keyword arguments of gal_lnprior (brutus/pdf.py:476-486) + frame constants."""
+    _fields_ = [(k, C.c_double) for k in GAL_FIELDS]
+
+
+class PostOptions(C.Structure):
+    _fields_ = [("nmc_prior", C.c_int32), ("ndraws", C.c_int32), ("seed", C.c_uint64),
+                ("use_gal_prior", C.c_int32), ("reserved", C.c_int32), ("star_base", C.c_int64),
+                ("gal", GalParams),
+                ("z_override", C.c_void_p), ("u_override", C.c_void_p)]
+
+
+class Draws(C.Structure):
+    _fields_ = [("model_idx", C.c_void_p)] + [(k, C.c_void_p) for k in
+                                              ("scale", "av", "rv", "cov_sar", "lnprob", "dist", "red",
+                                               "dred", "logwt")]
 
 
 _lib = None
@@ -83,6 +110,13 @@ def load():
                                     dp, dp, dp, dp, dp, dp, u8p, i64p]
     lib.bf_sweep_batch.argtypes = [vp, C.c_int64, dp, dp, u8p, dp, dp, dp, dp, op, C.c_int32,
                                    i32p, i32p, i64p, dp, i64p, C.POINTER(Records)]
+    lib.bf_default_gal_params.argtypes = [C.POINTER(GalParams)]
+    lib.bf_default_gal_params.restype = None
+    lib.bf_default_post_options.argtypes = [C.POINTER(PostOptions)]
+    lib.bf_default_post_options.restype = None
+    lib.bf_set_model_priors.argtypes = [vp, dp, dp, dp]
+    lib.bf_fit_batch.argtypes = [vp, C.c_int64, dp, dp, u8p, dp, dp, dp, dp, dp, op,
+                                 C.POINTER(PostOptions), i32p, i32p, i64p, dp, dp, C.POINTER(Draws)]
     lib.bf_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.bf_flush_l2.argtypes = [vp]
     lib.bf_device_count.restype = C.c_int
@@ -252,4 +286,90 @@ class Handle:
         for k, name in enumerate(ROW_NAMES[:min(5, rec.nrows)]):
             out[name] = mat[k]
         out["icov6"] = mat[5:11] if rec.nrows >= 11 else None
+        return out
+
+    def set_model_priors(self, lnprior=None, feh=None, loga=None):
+        """Stage the static inputs of lnpost: the `lnprior` grid (brutus/fitting.py:1004) and the label
+        columns 'feh' / 'loga' of the Galactic prior (brutus/pdf.py:669, :694).  None = absent."""
+        arrs = []
+        for a in (lnprior, feh, loga):
+            if a is not None:
+                a = np.ascontiguousarray(a, dtype=np.float64)
+                if a.shape != (self.nmodel,):
+                    raise ValueError("per-model priors / labels must have shape (Nmodel,)")
+            arrs.append(a)
+        self._check(self._lib.bf_set_model_priors(self._h, *[_ptr(a, C.c_double) for a in arrs]))
+
+    def fit_batch(self, flux, err, mask, parallax=None, parallax_err=None, coords=None, ext_mean=None,
+                  ext_std=None, opts=None, nmc_prior=50, ndraws=250, seed=0, use_gal_prior=True,
+                  gal=None, star_base=0, z_override=None, u_override=None):
+        """The per-object body of ``BruteForce._fit`` on the device (``bf_fit_batch``): returns a dict
+        with the reference's 13-tuple members as (Ndata, Ndraws) arrays (``sidxs, scales, avs, rvs,
+        cov_sar, lnprob, dists, reds, dreds, logwts``) and per-object ``ndim, levid, chi2min, nsel,
+        n_iter``."""
+        f = np.ascontiguousarray(flux, dtype=np.float64)
+        e = np.ascontiguousarray(err, dtype=np.float64)
+        m = np.ascontiguousarray(mask).astype(np.uint8)
+        ns = f.shape[0]
+        if not self.nfilt:
+            raise BrutusCudaError("no grid staged (call set_grid first)")
+        if f.ndim != 2 or f.shape[1] != self.nfilt or e.shape != f.shape or m.shape != f.shape:
+            raise ValueError("data, data_err and data_mask must have shape (Ndata, Nfilt)")
+        par = None if parallax is None else np.ascontiguousarray(parallax, dtype=np.float64)
+        perr = None if parallax_err is None else np.ascontiguousarray(parallax_err, dtype=np.float64)
+        co = None if coords is None else np.ascontiguousarray(coords, dtype=np.float64)
+        if co is not None and co.shape != (ns, 2):
+            raise ValueError("data_coords must have shape (Ndata, 2)")
+        em = es = None
+        if ext_mean is not None and self.nlabel:
+            em = np.ascontiguousarray(ext_mean, dtype=np.float64)
+            es = np.ascontiguousarray(ext_std, dtype=np.float64)
+        if opts is None:
+            opts = make_options()
+        po = PostOptions()
+        self._lib.bf_default_post_options(C.byref(po))
+        po.nmc_prior, po.ndraws, po.seed = int(nmc_prior), int(ndraws), int(seed) & (2 ** 64 - 1)
+        po.use_gal_prior = int(bool(use_gal_prior))
+        po.star_base = int(star_base)
+        for k, v in (gal or {}).items():
+            if k not in GAL_FIELDS:
+                raise ValueError("unknown Galactic prior parameter %r" % k)
+            setattr(po.gal, k, float(v))
+        keep = []
+        if z_override is not None:
+            z = np.ascontiguousarray(z_override, dtype=np.float64)
+            if z.shape != (self.nmodel, 3, po.nmc_prior):
+                raise ValueError("z_override must have shape (Nmodel, 3, Nmc_prior)")
+            po.z_override = z.ctypes.data
+            keep.append(z)
+        if u_override is not None:
+            u = np.ascontiguousarray(u_override, dtype=np.float64)
+            if u.shape != (ns, 2, po.ndraws):
+                raise ValueError("u_override must have shape (Ndata, 2, Ndraws)")
+            po.u_override = u.ctypes.data
+            keep.append(u)
+        nd = po.ndraws
+        out = dict(sidxs=np.full((ns, nd), -99, dtype=np.int32), scales=np.zeros((ns, nd)),
+                   avs=np.zeros((ns, nd)), rvs=np.zeros((ns, nd)), cov_sar=np.zeros((ns, nd, 3, 3)),
+                   lnprob=np.zeros((ns, nd)), dists=np.zeros((ns, nd)), reds=np.zeros((ns, nd)),
+                   dreds=np.zeros((ns, nd)), logwts=np.zeros((ns, nd)))
+        dr = Draws()
+        dr.model_idx = out["sidxs"].ctypes.data
+        for cname, key in (("scale", "scales"), ("av", "avs"), ("rv", "rvs"), ("cov_sar", "cov_sar"),
+                           ("lnprob", "lnprob"), ("dist", "dists"), ("red", "reds"), ("dred", "dreds"),
+                           ("logwt", "logwts")):
+            setattr(dr, cname, out[key].ctypes.data)
+        ndim = np.zeros(ns, dtype=np.int32)
+        nit = np.zeros((ns, 2), dtype=np.int32)
+        nsel = np.zeros(ns, dtype=np.int64)
+        levid = np.zeros(ns)
+        chi2min = np.zeros(ns)
+        self._check(self._lib.bf_fit_batch(
+            self._h, ns, _ptr(f, C.c_double), _ptr(e, C.c_double), _ptr(m, C.c_uint8),
+            _ptr(par, C.c_double), _ptr(perr, C.c_double), _ptr(co, C.c_double), _ptr(em, C.c_double),
+            _ptr(es, C.c_double), C.byref(opts), C.byref(po), _ptr(ndim, C.c_int32),
+            _ptr(nit, C.c_int32), _ptr(nsel, C.c_int64), _ptr(levid, C.c_double),
+            _ptr(chi2min, C.c_double), C.byref(dr)))
+        del keep
+        out.update(ndim=ndim, n_iter=nit, nsel=nsel, levid=levid, chi2min=chi2min)
         return out

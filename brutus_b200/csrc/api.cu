@@ -18,6 +18,7 @@
 
 #include "../../include/brutus_b200.h"
 #include "common.cuh"
+#include "posterior.cuh"
 
 namespace bf {
 
@@ -297,6 +298,11 @@ struct EngineBase {
                             const double* ext_std, const bf_options* opt, int record_rows, int32_t* ndim,
                             int32_t* n_iter, int64_t* n_surv, double* max_lnprob, int64_t* offsets,
                             bf_records* out) = 0;
+    virtual int set_model_priors(const double* lnprior, const double* feh, const double* loga) = 0;
+    virtual int fit_batch(int64_t nstar, const double* flux, const double* errv, const uint8_t* mask,
+                          const double* par, const double* perr, const double* coords, const double* ext_mean,
+                          const double* ext_std, const bf_options* opt, const bf_post_options* po, int32_t* ndim,
+                          int32_t* n_iter, int64_t* nsel, double* levid, double* chi2min, bf_draws* out) = 0;
 };
 
 #define CK(call)                                                                               \
@@ -443,6 +449,15 @@ template <typename T> struct Engine : EngineBase {
     DevBuf<U> d_red, d_probe;
     DevBuf<double> d_out;
     DevBuf<char> d_flush, d_stage[2];
+    // device posterior (bf_fit_batch)
+    cudaEvent_t evP0 = nullptr, evP1 = nullptr;
+    bool have_prior[3] = {false, false, false};   // lnprior, feh, loga staged?
+    DevBuf<T> d_lnprior, d_feh, d_loga, d_lnp1, d_lnp2;
+    DevBuf<GalStar<T>> d_gstar;
+    DevBuf<int> d_rstar, d_nsel2, d_sel2, d_oidx;
+    DevBuf<int64_t> d_off2;
+    DevBuf<double> d_cdf, d_ptot, d_odbl;
+    PinVec<int> h_nsel2;
 
     std::vector<T> h_stars, h_ext;
     std::vector<int> h_list;
@@ -456,6 +471,7 @@ template <typename T> struct Engine : EngineBase {
         const size_t nw = bytes / 4;
         if (!nw) return;
         k_publish<<<(unsigned)((nw + 255) / 256), 256, 0, stream>>>((const uint32_t*)dev_src, (uint32_t*)host_dst, nw);
+        stats.kernel_launches++;
     }
 
     enum { CTR_NSV = 0, CTR_ANY = 1, CTR_COUNT = 64 };
@@ -466,6 +482,11 @@ template <typename T> struct Engine : EngineBase {
         d_poolT.release(); d_star_int.release(); d_list.release(); d_wpre.release(); d_poolI.release();
         d_nsurv.release(); d_nsel.release(); d_ctr.release(); d_blk.release(); d_cand.release();
         d_probe.release(); d_ncand.release(); d_base.release(); d_tot.release(); d_red.release(); d_out.release(); d_flush.release();
+        d_lnprior.release(); d_feh.release(); d_loga.release(); d_lnp1.release(); d_lnp2.release(); d_gstar.release();
+        d_rstar.release(); d_nsel2.release(); d_sel2.release(); d_oidx.release(); d_off2.release(); d_cdf.release();
+        d_ptot.release(); d_odbl.release(); h_nsel2.release();
+        if (evP0) cudaEventDestroy(evP0);
+        if (evP1) cudaEventDestroy(evP1);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (evA) cudaEventDestroy(evA);
@@ -487,6 +508,7 @@ template <typename T> struct Engine : EngineBase {
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
         CK(cudaEventCreate(&evA)); CK(cudaEventCreate(&evB));
+        CK(cudaEventCreate(&evP0)); CK(cudaEventCreate(&evP1));
         CK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
         for (int k = 0; k < 2; k++) {
             CK(cudaEventCreateWithFlags(&ev_rec[k], cudaEventDisableTiming));
@@ -530,6 +552,7 @@ template <typename T> struct Engine : EngineBase {
         nwords = npad / 32;
         rs = row_stride(nf);
         nlabel = 0;
+        have_prior[0] = have_prior[1] = have_prior[2] = false;
         const size_t nval = (size_t)nm * nf * 3;
         CK(d_grid.ensure((size_t)3 * nf * npad));
         CK(d_rows.ensure((size_t)rs * npad));
@@ -913,15 +936,25 @@ template <typename T> struct Engine : EngineBase {
         return BF_OK;
     }
 
-    int sweep_batch(int64_t nstar, const double* flux, const double* errv, const uint8_t* mask,
-                    const double* par, const double* perr, const double* ext_mean, const double* ext_std,
-                    const bf_options* opt, int record_rows, int32_t* ndim, int32_t* n_iter, int64_t* n_surv,
-                    double* max_lnprob, int64_t* offsets, bf_records* out) override {
-        CK(cudaSetDevice(device));
-        if (!kt) { err = "bf_sweep_batch: no grid (call bf_set_grid)"; return BF_E_NOGRID; }
-        if (nstar < 0 || (nstar > 0 && (!flux || !errv || !mask)) || !opt || !offsets || !out) { err = "bf_sweep_batch: null argument"; return BF_E_INVALID; }
-        if (record_rows != 3 && record_rows != 5 && record_rows != 11) { err = "bf_sweep_batch: record_rows must be 3, 5 or 11"; return BF_E_INVALID; }
-        stats = bf_stats{};
+    // ---- the catalogue pipeline shared by bf_sweep_batch and bf_fit_batch: star batches -> sweep -> groups of
+    // stars whose candidates fit in the pool -> flux loops -> first selection -> ordered records in a device
+    // staging buffer; `consume` then ships them (B2) or integrates the priors over them (device posterior).
+    struct GroupCtx {
+        int64_t s0;          // catalogue index of slot 0 of the batch
+        int ns, g0, g1;      // stars in the batch; slots [g0, g1) of this group
+        int64_t nsel_tot;    // records of the group (first selection)
+        int buf;             // staging buffer used
+        T* rows;             // [11][nsel_tot]
+        int* idx;            // [nsel_tot] model index
+        int* rstar;          // [nsel_tot] star slot (only when requested)
+        DevOpts<T> o;
+    };
+
+    template <typename Consumer>
+    int run_catalogue(int64_t nstar, const double* flux, const double* errv, const uint8_t* mask,
+                      const double* par, const double* perr, const double* ext_mean, const double* ext_std,
+                      const bf_options* opt, int record_rows, bool want_rstar, int32_t* ndim, int32_t* n_iter,
+                      int64_t* n_surv, double* max_lnprob, int64_t* offsets, Consumer&& consume) {
         DevOpts<T> o; int max_iter;
         int rc = make_opts(opt, o, max_iter);
         if (rc) return rc;
@@ -929,7 +962,6 @@ template <typename T> struct Engine : EngineBase {
         const double slack = opt->select_slack;
         std::vector<int> nm(batch_cap);
         std::vector<char> exact(batch_cap);
-        int64_t written = 0;
         int grp = 0;
         offsets[0] = 0;
         for (int64_t s0 = 0; s0 < nstar; s0 += batch_cap) {
@@ -1007,8 +1039,9 @@ template <typename T> struct Engine : EngineBase {
                     nsel_tot += h_nsel[s];
                 }
                 stats.selected += nsel_tot;
-                // ---- ordered compaction + records into a device staging buffer, then an asynchronous D2H
-                // on the copy stream that overlaps the next group's / batch's kernels ----
+                // ---- ordered compaction + records into a device staging buffer ----
+                GroupCtx gc{};
+                gc.s0 = s0; gc.ns = ns; gc.g0 = g0; gc.g1 = g1; gc.nsel_tot = nsel_tot; gc.o = o;
                 if (nsel_tot > 0) {
                     const int buf = grp & 1;
                     grp++;
@@ -1016,11 +1049,13 @@ template <typename T> struct Engine : EngineBase {
                     phase_begin();
                     k_sel_write<T><<<(unsigned)nblk, kTile, 0, stream>>>(sp);
                     CK(d_stage[buf].ensure((size_t)nsel_tot * (sizeof(int) + 11 * sizeof(T))));
+                    if (want_rstar) CK(d_rstar.ensure((size_t)nsel_tot));
                     RecordParams<T, T> rp{};
                     rp.rows = d_rows.p; rp.stars = d_stars.p; rp.o = o; rp.pool = pl;
                     rp.sel_q = selq(); rp.nrec = nsel_tot;
                     T* b = (T*)d_stage[buf].p;                                   // [11][nsel_tot] rows, then idx
                     rp.o_idx = (int*)(d_stage[buf].p + (size_t)11 * nsel_tot * sizeof(T));
+                    rp.o_star = want_rstar ? d_rstar.p : nullptr;
                     rp.ld = nsel_tot; rp.nrows = record_rows;
                     rp.o_lnl = b; rp.o_scale = b + nsel_tot; rp.o_av = b + 2 * nsel_tot; rp.o_chi2 = b + 3 * nsel_tot;
                     rp.o_rv = b + 4 * nsel_tot; rp.o_icov = b + 5 * nsel_tot;
@@ -1029,27 +1064,16 @@ template <typename T> struct Engine : EngineBase {
                     CK(cudaGetLastError());
                     CK(cudaEventRecord(ev_rec[buf], stream));
                     CK(cudaEventRecord(evB, stream));
-                    if (!opt->skip_d2h) {
-                        rc = ensure_arena(written + nsel_tot, written);
-                        if (rc) return rc;
-                        CK(cudaStreamWaitEvent(copy_stream, ev_rec[buf], 0));
-                        CK(cudaMemcpyAsync(arena + (size_t)11 * arena_cap * sizeof(T) + (size_t)written * sizeof(int),
-                                           rp.o_idx, (size_t)nsel_tot * sizeof(int), cudaMemcpyDeviceToHost, copy_stream));
-                        // one plain 1-D copy per record row (each 100+ MB): the pitched 2-D copy ran at
-                        // ~42 GB/s on the PCIe Gen5 link, 1-D copies reach the measured ~57 GB/s
-                        for (int r = 0; r < record_rows; r++)
-                            CK(cudaMemcpyAsync(arena + ((size_t)r * arena_cap + (size_t)written) * sizeof(T),
-                                               b + (size_t)r * nsel_tot, (size_t)nsel_tot * sizeof(T),
-                                               cudaMemcpyDeviceToHost, copy_stream));
-                        CK(cudaEventRecord(ev_cp[buf], copy_stream));
-                        stats.d2h_bytes += (size_t)nsel_tot * (sizeof(int) + record_rows * sizeof(T));
-                    }
+                    gc.buf = buf; gc.rows = b; gc.idx = rp.o_idx; gc.rstar = rp.o_star;
+                }
+                rc = consume(gc);
+                if (rc) return rc;
+                if (nsel_tot > 0) {
                     CK(cudaEventSynchronize(evB));
                     float msr = 0.f;
                     CK(cudaEventElapsedTime(&msr, evA, evB));
                     stats.ms_select += msr;
                 }
-                written += nsel_tot;
                 g0 = g1;
             }
             CK(cudaEventRecord(ev1, stream));
@@ -1058,6 +1082,42 @@ template <typename T> struct Engine : EngineBase {
             CK(cudaEventElapsedTime(&ms, ev0, ev1));
             stats.ms_device += ms;
         }
+        return BF_OK;
+    }
+
+    int sweep_batch(int64_t nstar, const double* flux, const double* errv, const uint8_t* mask,
+                    const double* par, const double* perr, const double* ext_mean, const double* ext_std,
+                    const bf_options* opt, int record_rows, int32_t* ndim, int32_t* n_iter, int64_t* n_surv,
+                    double* max_lnprob, int64_t* offsets, bf_records* out) override {
+        CK(cudaSetDevice(device));
+        if (!kt) { err = "bf_sweep_batch: no grid (call bf_set_grid)"; return BF_E_NOGRID; }
+        if (nstar < 0 || (nstar > 0 && (!flux || !errv || !mask)) || !opt || !offsets || !out) { err = "bf_sweep_batch: null argument"; return BF_E_INVALID; }
+        if (record_rows != 3 && record_rows != 5 && record_rows != 11) { err = "bf_sweep_batch: record_rows must be 3, 5 or 11"; return BF_E_INVALID; }
+        stats = bf_stats{};
+        int64_t written = 0;
+        // asynchronous D2H of each group's records on the copy stream: overlaps the next group's / batch's kernels
+        auto ship = [&](GroupCtx& g) -> int {
+            if (g.nsel_tot > 0 && !opt->skip_d2h) {
+                int rc = ensure_arena(written + g.nsel_tot, written);
+                if (rc) return rc;
+                CK(cudaStreamWaitEvent(copy_stream, ev_rec[g.buf], 0));
+                CK(cudaMemcpyAsync(arena + (size_t)11 * arena_cap * sizeof(T) + (size_t)written * sizeof(int),
+                                   g.idx, (size_t)g.nsel_tot * sizeof(int), cudaMemcpyDeviceToHost, copy_stream));
+                // one plain 1-D copy per record row (each 100+ MB): the pitched 2-D copy ran at
+                // ~42 GB/s on the PCIe Gen5 link, 1-D copies reach the measured ~57 GB/s
+                for (int r = 0; r < record_rows; r++)
+                    CK(cudaMemcpyAsync(arena + ((size_t)r * arena_cap + (size_t)written) * sizeof(T),
+                                       g.rows + (size_t)r * g.nsel_tot, (size_t)g.nsel_tot * sizeof(T),
+                                       cudaMemcpyDeviceToHost, copy_stream));
+                CK(cudaEventRecord(ev_cp[g.buf], copy_stream));
+                stats.d2h_bytes += (size_t)g.nsel_tot * (sizeof(int) + record_rows * sizeof(T));
+            }
+            written += g.nsel_tot;
+            return BF_OK;
+        };
+        int rc = run_catalogue(nstar, flux, errv, mask, par, perr, ext_mean, ext_std, opt, record_rows, false, ndim,
+                               n_iter, n_surv, max_lnprob, offsets, ship);
+        if (rc) return rc;
         CK(cudaStreamSynchronize(copy_stream));
         out->n = opt->skip_d2h ? 0 : written;
         out->stride = arena_cap;
@@ -1065,6 +1125,196 @@ template <typename T> struct Engine : EngineBase {
         out->nrows = record_rows;
         out->model_idx = arena ? (const int32_t*)(arena + (size_t)11 * arena_cap * sizeof(T)) : nullptr;
         out->rows = (const void*)arena;
+        return BF_OK;
+    }
+
+    // ---- static per-model priors / labels of lnpost (bf_set_model_priors) ----
+    int set_model_priors(const double* lnprior, const double* feh, const double* loga) override {
+        CK(cudaSetDevice(device));
+        if (!kt) { err = "bf_set_model_priors: call bf_set_grid first"; return BF_E_NOGRID; }
+        const double* src[3] = {lnprior, feh, loga};
+        DevBuf<T>* dst[3] = {&d_lnprior, &d_feh, &d_loga};
+        DevBuf<double> tmp;
+        for (int k = 0; k < 3; k++) {
+            have_prior[k] = src[k] != nullptr;
+            if (!src[k]) continue;
+            CK(tmp.ensure((size_t)nmodel));
+            CK(cudaMemcpyAsync(tmp.p, src[k], (size_t)nmodel * sizeof(double), cudaMemcpyHostToDevice, stream));
+            CK(dst[k]->ensure((size_t)npad));
+            k_convert_labels<T><<<(unsigned)((npad + 255) / 256), 256, 0, stream>>>(tmp.p, dst[k]->p, nmodel, npad, 1);
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(stream));
+            stats.h2d_bytes += (size_t)nmodel * sizeof(double);
+        }
+        tmp.release();
+        return BF_OK;
+    }
+
+    // constants of the Galactic prior (brutus/pdf.py:476-749) in the form posterior.cuh consumes
+    GalDev<T> make_gal(const bf_post_options* po) const {
+        GalDev<T> G{};
+        const bf_gal_params& g = po->gal;
+        G.use = po->use_gal_prior ? 1 : 0;
+        G.has_feh = have_prior[1] ? 1 : 0;
+        G.has_age = have_prior[2] ? 1 : 0;
+        G.Rs_thin2 = (T)(g.Rs_thin * g.Rs_thin); G.Rs_thick2 = (T)(g.Rs_thick * g.Rs_thick); G.Rs_halo2 = (T)(g.Rs_halo * g.Rs_halo);
+        G.R_solar = (T)g.R_solar; G.aZ_solar = (T)std::fabs(g.Z_solar);
+        G.iR_thin = (T)(1. / g.R_thin); G.iZ_thin = (T)(1. / g.Z_thin);
+        G.iR_thick = (T)(1. / g.R_thick); G.iZ_thick = (T)(1. / g.Z_thick);
+        G.ln_f_thick = (T)std::log(g.f_thick); G.ln_f_halo = (T)std::log(g.f_halo);
+        G.rq2 = (T)(g.r_q_halo * g.r_q_halo); G.irq = (T)(1. / g.r_q_halo);
+        G.q_inf = (T)g.q_halo_inf; G.dq = (T)(g.q_halo_inf - g.q_halo_ctr); G.eta = (T)g.eta_halo;
+        const double rp_s = std::sqrt(g.R_solar * g.R_solar + g.Z_solar * g.Z_solar + g.r_q_halo * g.r_q_halo);
+        const double q_s = g.q_halo_inf - (g.q_halo_inf - g.q_halo_ctr) * std::exp(1. - rp_s / g.r_q_halo);
+        G.ln_Reff_solar = (T)(0.5 * std::log(g.R_solar * g.R_solar + (g.Z_solar / q_s) * (g.Z_solar / q_s) + g.Rs_halo * g.Rs_halo));
+        const double mu[3] = {g.feh_thin, g.feh_thick, g.feh_halo};
+        const double sg[3] = {g.feh_thin_sigma, g.feh_thick_sigma, g.feh_halo_sigma};
+        for (int x = 0; x < 3; x++) {
+            G.feh_mu[x] = (T)mu[x];
+            G.feh_isig2[x] = (T)(1. / (sg[x] * sg[x]));
+            G.feh_lnorm[x] = (T)std::log(2. * M_PI * sg[x] * sg[x]);
+            // age prior of the component: truncated normal on [min_age, max_age] (brutus/pdf.py:455-470)
+            const double am = (g.max_age - g.min_age) / (1. + std::exp((mu[x] - g.feh_age_ctr) / g.feh_age_scale)) + g.min_age;
+            double as = (g.max_age - am) / g.nsigma_from_max_age;
+            as = std::min(std::max(as, g.min_sigma), g.max_sigma);
+            const double a = (g.min_age - am) / as, b = (g.max_age - am) / as;
+            G.age_mu[x] = (T)am;
+            G.age_isig[x] = (T)(1. / as);
+            G.age_lnden[x] = (T)(std::log(as / 2.) + std::log(std::erf(b / std::sqrt(2.)) - std::erf(a / std::sqrt(2.))));
+        }
+        G.min_age = (T)g.min_age; G.max_age = (T)g.max_age;
+        return G;
+    }
+
+    // ---- the per-star body of BruteForce._fit on the device (brutus/fitting.py:1980-2061) ----
+    int fit_batch(int64_t nstar, const double* flux, const double* errv, const uint8_t* mask, const double* par,
+                  const double* perr, const double* coords, const double* ext_mean, const double* ext_std,
+                  const bf_options* opt, const bf_post_options* po, int32_t* ndim, int32_t* n_iter, int64_t* nsel,
+                  double* levid, double* chi2min, bf_draws* out) override {
+        CK(cudaSetDevice(device));
+        if (!kt) { err = "bf_fit_batch: no grid (call bf_set_grid)"; return BF_E_NOGRID; }
+        if (nstar < 0 || (nstar > 0 && (!flux || !errv || !mask)) || !opt || !po || !out || !levid || !chi2min) { err = "bf_fit_batch: null argument"; return BF_E_INVALID; }
+        if (!out->model_idx || !out->scale || !out->av || !out->rv || !out->cov_sar || !out->lnprob || !out->dist ||
+            !out->red || !out->dred || !out->logwt) { err = "bf_fit_batch: null output array"; return BF_E_INVALID; }
+        if (po->nmc_prior < 1 || po->ndraws < 1) { err = "bf_fit_batch: nmc_prior and ndraws must be >= 1"; return BF_E_INVALID; }
+        if (po->use_gal_prior && !coords) { err = "`coord` must be provided if using the default Galactic model prior."; return BF_E_INVALID; }
+        stats = bf_stats{};
+        const int nd = po->ndraws, nmc = po->nmc_prior;
+        const GalDev<T> G = make_gal(po);
+        // test hooks: host-supplied normals / uniforms
+        DevBuf<double> d_zov, d_uov;
+        if (po->z_override) {
+            CK(d_zov.ensure((size_t)nmodel * 3 * nmc));
+            CK(cudaMemcpyAsync(d_zov.p, po->z_override, (size_t)nmodel * 3 * nmc * sizeof(double), cudaMemcpyHostToDevice, stream));
+        }
+        CK(d_gstar.ensure((size_t)batch_cap));
+        CK(d_nsel2.ensure((size_t)batch_cap));
+        CK(d_off2.ensure((size_t)batch_cap + 1));
+        CK(d_ptot.ensure((size_t)batch_cap));
+        CK(d_oidx.ensure((size_t)batch_cap * nd));
+        CK(d_odbl.ensure((size_t)batch_cap * nd * 17 + 2 * (size_t)batch_cap));
+        CK(h_nsel2.resize(batch_cap));
+        if (po->u_override) CK(d_uov.ensure((size_t)batch_cap * 2 * nd));
+        std::vector<GalStar<T>> h_gstar(batch_cap);
+        std::vector<int64_t> h_off2(batch_cap + 1);
+        std::vector<int64_t> offsets(nstar + 1);
+        int64_t last_s0 = -1;
+        auto post = [&](GroupCtx& g) -> int {
+            const int ng = g.g1 - g.g0;
+            if (g.s0 != last_s0) {   // first group of a batch: per-star geometry, random-number overrides
+                last_s0 = g.s0;
+                const double st = po->gal.z_sun / po->gal.galcen_distance, ct = std::sqrt(1. - st * st);
+                for (int s = 0; s < g.ns; s++) {
+                    GalStar<T> q{};
+                    if (coords) {
+                        const double l = coords[2 * (g.s0 + s)] * M_PI / 180., b = coords[2 * (g.s0 + s) + 1] * M_PI / 180.;
+                        const double cl = std::cos(l), sl = std::sin(l), cb = std::cos(b), sb = std::sin(b);
+                        q.ax = (T)(cb * cl * ct + sb * st); q.ay = (T)(cb * sl); q.az = (T)(sb * ct - cb * cl * st);
+                        q.x0 = (T)(-po->gal.galcen_distance * ct); q.z0 = (T)(po->gal.galcen_distance * st);
+                    }
+                    h_gstar[s] = q;
+                }
+                CK(cudaMemcpyAsync(d_gstar.p, h_gstar.data(), (size_t)g.ns * sizeof(GalStar<T>), cudaMemcpyHostToDevice, stream));
+                if (po->u_override)
+                    CK(cudaMemcpyAsync(d_uov.p, po->u_override + (size_t)g.s0 * 2 * nd, (size_t)g.ns * 2 * nd * sizeof(double), cudaMemcpyHostToDevice, stream));
+            }
+            const int64_t n1 = g.nsel_tot;
+            PostParams<T> pp{};
+            pp.rows = g.rows; pp.ld = n1; pp.idx = g.idx; pp.rstar = g.rstar; pp.n1 = n1;
+            pp.lnprior = have_prior[0] ? d_lnprior.p : nullptr;
+            pp.feh = have_prior[1] ? d_feh.p : nullptr;
+            pp.loga = have_prior[2] ? d_loga.p : nullptr;
+            pp.G = G; pp.gstar = d_gstar.p; pp.stars = d_stars.p; pp.red = d_red.p; pp.ln_wt = g.o.ln_wt;
+            pp.avmin = g.o.avmin; pp.avmax = g.o.avmax; pp.rvmin = g.o.rvmin; pp.rvmax = g.o.rvmax;
+            pp.nmc = nmc; pp.ndraws = nd; pp.seed = po->seed; pp.star_base = po->star_base + g.s0;
+            pp.zov = po->z_override ? d_zov.p : nullptr;
+            pp.uov = po->u_override ? d_uov.p : nullptr;
+            pp.g0 = g.g0;
+            pp.nsel2 = d_nsel2.p; pp.off2 = d_off2.p; pp.tot = d_ptot.p; pp.blk = d_blk.p;
+            double* ob = d_odbl.p;
+            const size_t per = (size_t)batch_cap * nd;
+            pp.o_idx = d_oidx.p;
+            pp.o_scale = ob; pp.o_av = ob + per; pp.o_rv = ob + 2 * per; pp.o_lnprob = ob + 3 * per; pp.o_dist = ob + 4 * per;
+            pp.o_red = ob + 5 * per; pp.o_dred = ob + 6 * per; pp.o_logwt = ob + 7 * per; pp.o_cov = ob + 8 * per;
+            pp.o_levid = ob + 17 * per; pp.o_chi2min = pp.o_levid + batch_cap;
+            CK(cudaEventRecord(evP0, stream));
+            CK(cudaMemsetAsync(d_nsel2.p + g.g0, 0, (size_t)ng * sizeof(int), stream));
+            int64_t n2 = 0;
+            if (n1 > 0) {
+                CK(d_lnp1.ensure((size_t)n1)); CK(d_lnp2.ensure((size_t)n1)); CK(d_sel2.ensure((size_t)n1)); CK(d_cdf.ensure((size_t)n1));
+                pp.lnp1 = d_lnp1.p; pp.lnp2 = d_lnp2.p; pp.sel2 = d_sel2.p; pp.cdf = d_cdf.p;
+                const unsigned nb1 = (unsigned)((n1 + kTile - 1) / kTile);
+                k_post_mle<T><<<nb1, kTile, 0, stream>>>(pp);
+                k_post_count<T><<<nb1, kTile, 0, stream>>>(pp);
+                k_scan_blocks<<<1, 1024, 0, stream>>>(d_blk.p, nb1, d_tot.p);
+                stats.kernel_launches += 3;
+                CK(cudaGetLastError());
+            }
+            publish(h_nsel2.data() + g.g0, d_nsel2.p + g.g0, (size_t)ng * sizeof(int));
+            CK(cudaStreamSynchronize(stream));
+            h_off2[g.g0] = 0;
+            for (int s = g.g0; s < g.g1; s++) {
+                h_off2[s + 1] = h_off2[s] + h_nsel2[s];
+                if (nsel) nsel[g.s0 + s] = h_nsel2[s];
+            }
+            n2 = h_off2[g.g1];
+            stats.selected2 += n2;
+            pp.n2 = n2;
+            CK(cudaMemcpyAsync(d_off2.p + g.g0, h_off2.data() + g.g0, (size_t)(ng + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+            if (n2 > 0) {
+                const unsigned nb1 = (unsigned)((n1 + kTile - 1) / kTile);
+                k_post_write<T><<<nb1, kTile, 0, stream>>>(pp);
+                k_post_mc<T><<<(unsigned)((n2 + kTile - 1) / kTile), kTile, 0, stream>>>(pp);
+                stats.kernel_launches += 2;
+            }
+            k_post_cdf<T><<<ng, 1024, 0, stream>>>(pp);
+            k_post_draw<T><<<ng, std::min(1024, (nd + 31) / 32 * 32), 0, stream>>>(pp);
+            stats.kernel_launches += 2;
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(evP1, stream));
+            // ---- ndraws samples per star back to the caller's arrays ----
+            const size_t off = (size_t)g.g0 * nd, cnt = (size_t)ng * nd, dst = (size_t)(g.s0 + g.g0) * nd;
+            CK(cudaMemcpyAsync(out->model_idx + dst, pp.o_idx + off, cnt * sizeof(int), cudaMemcpyDeviceToHost, stream));
+            double* hdst[8] = {out->scale, out->av, out->rv, out->lnprob, out->dist, out->red, out->dred, out->logwt};
+            for (int k = 0; k < 8; k++)
+                CK(cudaMemcpyAsync(hdst[k] + dst, ob + k * per + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(out->cov_sar + dst * 9, pp.o_cov + off * 9, cnt * 9 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(levid + g.s0 + g.g0, pp.o_levid + g.g0, (size_t)ng * sizeof(double), cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(chi2min + g.s0 + g.g0, pp.o_chi2min + g.g0, (size_t)ng * sizeof(double), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, evP0, evP1));
+            stats.ms_post += ms;
+            stats.d2h_bytes += cnt * (sizeof(int) + 17 * sizeof(double)) + 2 * (size_t)ng * sizeof(double);
+            return BF_OK;
+        };
+        int rc = run_catalogue(nstar, flux, errv, mask, par, perr, ext_mean, ext_std, opt, 11, true, ndim, n_iter,
+                               nullptr, nullptr, offsets.data(), post);
+        d_zov.release(); d_uov.release();
+        if (rc) return rc;
+        if (ndim && par && perr)   // the parallax counts as one more datum (brutus/fitting.py:2028-2030)
+            for (int64_t s = 0; s < nstar; s++)
+                if (std::isfinite(par[s]) && std::isfinite(perr[s])) ndim[s] += 1;
         return BF_OK;
     }
 };
@@ -1161,6 +1411,40 @@ int bf_sweep_batch(bf_handle* h, int64_t nstar, const double* flux, const double
     if (!h) return BF_E_INVALID;
     return h->eng->sweep_batch(nstar, flux, err, mask, parallax, parallax_err, ext_mean, ext_std, opt,
                                record_rows, ndim, n_iter, n_surv, max_lnprob, offsets, out);
+}
+
+void bf_default_gal_params(bf_gal_params* g) {   /* defaults of gal_lnprior, brutus/pdf.py:476-486 */
+    if (!g) return;
+    g->R_solar = 8.2; g->Z_solar = 0.025; g->R_thin = 2.6; g->Z_thin = 0.3; g->Rs_thin = 2.0;
+    g->R_thick = 2.0; g->Z_thick = 0.9; g->f_thick = 0.04; g->Rs_thick = 2.0;
+    g->Rs_halo = 2.0; g->q_halo_ctr = 0.2; g->q_halo_inf = 0.8; g->r_q_halo = 6.0; g->eta_halo = 4.2; g->f_halo = 0.005;
+    g->feh_thin = -0.2; g->feh_thin_sigma = 0.3; g->feh_thick = -0.7; g->feh_thick_sigma = 0.4;
+    g->feh_halo = -1.6; g->feh_halo_sigma = 0.5;
+    g->max_age = 13.8; g->min_age = 0.; g->feh_age_ctr = -0.5; g->feh_age_scale = 0.5;
+    g->nsigma_from_max_age = 2.; g->max_sigma = 4.; g->min_sigma = 1.;
+    g->galcen_distance = 8.122; g->z_sun = 0.0208;
+}
+
+void bf_default_post_options(bf_post_options* o) {
+    if (!o) return;
+    o->nmc_prior = 50; o->ndraws = 250; o->seed = 0; o->use_gal_prior = 1; o->reserved = 0; o->star_base = 0;
+    bf_default_gal_params(&o->gal);
+    o->z_override = nullptr; o->u_override = nullptr;
+}
+
+int bf_set_model_priors(bf_handle* h, const double* lnprior, const double* feh, const double* loga) {
+    if (!h) return BF_E_INVALID;
+    return h->eng->set_model_priors(lnprior, feh, loga);
+}
+
+int bf_fit_batch(bf_handle* h, int64_t nstar, const double* flux, const double* err, const uint8_t* mask,
+                 const double* parallax, const double* parallax_err, const double* coords,
+                 const double* ext_mean, const double* ext_std, const bf_options* opt,
+                 const bf_post_options* post, int32_t* ndim, int32_t* n_iter, int64_t* nsel,
+                 double* levid, double* chi2min, bf_draws* out) {
+    if (!h) return BF_E_INVALID;
+    return h->eng->fit_batch(nstar, flux, err, mask, parallax, parallax_err, coords, ext_mean, ext_std, opt, post,
+                             ndim, n_iter, nsel, levid, chi2min, out);
 }
 
 int bf_flush_l2(bf_handle* h) {

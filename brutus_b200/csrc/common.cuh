@@ -61,6 +61,9 @@ enum Red {
     RED_FL,      // max lnl_new in the current flux iteration   (brutus/fitting.py:798)
     RED_FB,      // max lnl_new over survivors with |lnl_new - lnl_old| > ltol
     RED_LNP,     // max lnprob                                  (brutus/fitting.py:990)
+    RED_P1,      // max of lnlike + priors at the MLE over the first selection   (brutus/fitting.py:1015)
+    RED_P2,      // max final lnprob over the second selection                    (brutus/fitting.py:2034)
+    RED_NCHI,    // max of -chi2 (incl. the parallax term) over the second selection (:2030, :2035)
     kNumRed
 };
 constexpr int kSweepRed = 6;     // RED_L0 .. RED_M0 are produced by the sweep
@@ -311,6 +314,7 @@ template <typename T, typename O> struct RecordParams {
     int64_t ld;
     int nrows;
     int* o_idx;   // mode A: model index of each record
+    int* o_star;  // mode A, optional: star slot of each record (device posterior)
 };
 
 // Kernel launchers instantiated once per band count (inst.cu, -DBF_NB=n).

@@ -647,6 +647,7 @@ __global__ void __launch_bounds__(kTile) k_records(const RecordParams<T, O> p) {
     const T A = p.pool.av[q], rho = p.pool.rv[q];
     if (modeA) {
         p.o_idx[t] = (int)i;
+        if (p.o_star) p.o_star[t] = slot;
         p.o_lnl[t] = (O)p.pool.lnl[q];
         p.o_scale[t] = (O)p.pool.scale[q];
         p.o_av[t] = (O)A;

@@ -1,0 +1,499 @@
+// posterior.cuh -- the part of the reference's `lnpost` that follows the first selection, the evidence
+// and the posterior resampling of `BruteForce._fit`, on the device:
+//
+//   k_post_mle    priors at the MLE: lnlike + lnprior[model] + Galactic prior(1/sqrt(scale))   brutus/fitting.py:999-1010
+//   k_post_count / k_post_write   second threshold lnp > max + ln(wt_thresh), ordered compaction  :1012-1026
+//   k_post_mc     covariance = inverse of icov_sar, regularised until positive definite           :1038-1065
+//                 Nmc draws of (s, Av, Rv), Galactic + parallax prior at each, in-bounds mask,
+//                 lnp += logsumexp - ln(Neff)                                                      :1068-1101
+//   k_post_cdf    evidence logsumexp(lnp) and the cumulative weights of the selected models        :2032-2040
+//   k_post_draw   Ndraws models by inverse CDF, then one of the model's Nmc (dist, Av, Rv) draws   :2040-2053
+//
+// The reference draws its normals / uniforms from the caller's numpy RandomState; here they come from a
+// counter-based generator (Philox4x32-10) keyed by (seed, star, model, draw), so results do not depend on
+// batching or on the number of GPUs.  Parity with the reference is therefore distributional -- except in
+// the test mode where the host supplies the normals and uniforms (bf_post_options.z_override /
+// u_override): then every number is comparable with the NumPy restatement draw for draw.
+#pragma once
+#include "common.cuh"
+
+namespace bf {
+
+// ---- Philox4x32-10 (Salmon et al. 2011) --------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// uniform in (0, 1) from 32 random bits (24 bits used: exact in float)
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 5.9604645e-8f + 2.9802322e-8f; }
+// uniform in [0, 1) with 53 bits
+__device__ __forceinline__ double u01d(uint32_t a, uint32_t b) {
+    return (double)((((uint64_t)a << 32) | b) >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// ---- math in T -----------------------------------------------------------------------------------------
+__device__ __forceinline__ float pexp(float x) { return __expf(x); }
+__device__ __forceinline__ double pexp(double x) { return exp(x); }
+__device__ __forceinline__ float plog(float x) { return __logf(x); }
+__device__ __forceinline__ double plog(double x) { return log(x); }
+__device__ __forceinline__ float psqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ double psqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ float pexp10(float x) { return exp2f(x * 3.3219281f); }
+__device__ __forceinline__ double pexp10(double x) { return exp10(x); }
+
+// three standard normals for (star, model, draw j): Box-Muller on one Philox block
+template <typename T>
+__device__ __forceinline__ void normals3(uint64_t seed, uint64_t star, uint32_t model, uint32_t j, T (&z)[3]) {
+    uint32_t r[4];
+    philox4x32_10(model, j, (uint32_t)star, (uint32_t)(star >> 32) ^ 0x4D435A31u, (uint32_t)seed,
+                  (uint32_t)(seed >> 32), r);
+    const float r0 = sqrtf(-2.f * __logf(u01(r[0]))), r1 = sqrtf(-2.f * __logf(u01(r[2])));
+    float s0, c0, s1, c1;
+    __sincosf(6.2831853f * u01(r[1]), &s0, &c0);
+    __sincosf(6.2831853f * u01(r[3]), &s1, &c1);
+    z[0] = (T)(r0 * c0); z[1] = (T)(r0 * s0); z[2] = (T)(r1 * c1);
+    (void)s1;
+}
+
+// ---- the Galactic prior (brutus/pdf.py:476-749) --------------------------------------------------------
+// constants prepared on the host (api.cu, make_gal) from bf_gal_params
+template <typename T> struct GalDev {
+    int use;                                  // 0: no distance prior
+    int has_feh, has_age;
+    T Rs_thin2, Rs_thick2, Rs_halo2;          // smoothing radii squared          (:301, :363)
+    T R_solar, aZ_solar;
+    T iR_thin, iZ_thin, iR_thick, iZ_thick;   // inverse scale lengths            (:303-304)
+    T ln_f_thick, ln_f_halo;                  // (:647, :654)
+    T rq2, irq, q_inf, dq, eta, ln_Reff_solar;  // halo oblateness + normalisation (:358-374)
+    T feh_mu[3], feh_isig2[3], feh_lnorm[3];  // thin, thick, halo                (:380-408)
+    T age_mu[3], age_isig[3], age_lnden[3];   // truncated normals                (:455-470, brutus/utils.py:232-284)
+    T min_age, max_age;
+};
+// heliocentric -> galactocentric, linear in the distance d: x = d ax + x0, y = d ay, z = d az + z0
+template <typename T> struct GalStar { T ax, ay, az, x0, z0; };
+// exp(log-prior) of the model's labels in each component; 1 when the label is absent
+template <typename T> struct ModelW { T f[3], g[3]; };
+
+template <typename T>
+__device__ __forceinline__ void model_weights(const GalDev<T>& G, const T* __restrict__ feh,
+                                              const T* __restrict__ loga, int64_t i, ModelW<T>& w) {
+#pragma unroll
+    for (int x = 0; x < 3; x++) { w.f[x] = T(1); w.g[x] = T(1); }
+    if (!G.use) return;
+    if (G.has_feh) {
+        const T v = feh[i];
+#pragma unroll
+        for (int x = 0; x < 3; x++) {
+            const T d = G.feh_mu[x] - v;
+            w.f[x] = pexp(T(-0.5) * (d * d * G.feh_isig2[x] + G.feh_lnorm[x]));
+        }
+    }
+    if (G.has_age) {
+        const T age = pexp10(loga[i] - T(9));                                   // Gyr (:694)
+        const bool out = age < G.min_age || age > G.max_age;                    // brutus/utils.py:275-277
+#pragma unroll
+        for (int x = 0; x < 3; x++) {
+            const T xi = (age - G.age_mu[x]) * G.age_isig[x];
+            w.g[x] = out ? T(0) : pexp(T(-0.9189385332046727) - T(0.5) * xi * xi - G.age_lnden[x]);
+        }
+    }
+}
+
+// ln prior(d) = 2 ln d + ln sum_X n_X + ln(sum f_X n_X / sum n_X) + ln(sum g_X n_X / sum n_X)
+// with n_X the thin / thick / halo number densities (:622-745; the three logsumexp of the reference
+// share the same exponentials)
+template <typename T>
+__device__ __forceinline__ T gal_lnprior(const GalDev<T>& G, const GalStar<T>& gs, const ModelW<T>& w, T d) {
+    if (!G.use) return T(0);
+    const T vol = T(2) * plog(d);
+    const T x = fma(d, gs.ax, gs.x0), y = d * gs.ay, z = fma(d, gs.az, gs.z0);
+    const T R2 = x * x + y * y, aZ = tabs(z);
+    const T lt = -((psqrt(R2 + G.Rs_thin2) - G.R_solar) * G.iR_thin + (aZ - G.aZ_solar) * G.iZ_thin);
+    const T lk = -((psqrt(R2 + G.Rs_thick2) - G.R_solar) * G.iR_thick + (aZ - G.aZ_solar) * G.iZ_thick) + G.ln_f_thick;
+    const T rp = psqrt(R2 + z * z + G.rq2);
+    const T q = G.q_inf - G.dq * pexp(T(1) - rp * G.irq);
+    const T zq = z / q;
+    const T lh = -G.eta * (T(0.5) * plog(R2 + zq * zq + G.Rs_halo2) - G.ln_Reff_solar) + G.ln_f_halo;
+    const T m = tmax(lt, tmax(lk, lh));
+    const T nt = pexp(lt - m), nk = pexp(lk - m), nh = pexp(lh - m);
+    const T s0 = nt + nk + nh;
+    const T s1 = w.f[0] * nt + w.f[1] * nk + w.f[2] * nh;
+    const T s2 = w.g[0] * nt + w.g[1] * nk + w.g[2] * nh;
+    return vol + m + plog(s1 * s2 / s0);
+}
+
+// ---- parameters shared by the posterior kernels ------------------------------------------------------------
+template <typename T> struct PostParams {
+    // records of the first selection (device staging written by k_records, mode A, 11 rows)
+    const T* rows;           // [11][ld]: lnl, scale, av, chi2, rv, icov(ss, sa, sr, aa, ar, rr)
+    int64_t ld;
+    const int* idx;          // model index per record
+    const int* rstar;        // star slot per record
+    int64_t n1;
+    // static per-model priors / labels ([npad], any may be null)
+    const T* lnprior;
+    const T* feh;
+    const T* loga;
+    GalDev<T> G;
+    const GalStar<T>* gstar; // [batch]
+    const T* stars;          // star rows (parallax, 1/parallax_err^2)
+    typename Enc<T>::U* red; // [batch][kNumRed]
+    T ln_wt;
+    T avmin, avmax, rvmin, rvmax;
+    // second selection
+    T* lnp1;                 // [n1]
+    int* blk;                // per 256-record block counts -> offsets
+    int* nsel2;              // [batch]
+    int* sel2;               // [n2] -> record index t
+    int64_t n2;
+    const int64_t* off2;     // [batch+1] star -> first entry of sel2 (slots g0..g1 of the current group)
+    T* lnp2;                 // [n2]
+    double* cdf;             // [n2]
+    double* tot;             // [batch] sum of the weights
+    // Monte Carlo
+    int nmc, ndraws;
+    uint64_t seed;
+    int64_t star_base;       // catalogue index of slot 0 (keys the generator)
+    const double* zov;       // [nmodel][3][nmc] or null
+    const double* uov;       // [batch][2][ndraws] (slot-indexed) or null
+    // outputs, [batch][ndraws] (slot-indexed)
+    int g0;                  // first slot of the group
+    int* o_idx;
+    double *o_scale, *o_av, *o_rv, *o_cov, *o_lnprob, *o_dist, *o_red, *o_dred, *o_logwt;
+    double *o_levid, *o_chi2min;   // [batch]
+};
+
+// (:999-1010)
+template <typename T> __global__ void __launch_bounds__(kTile) k_post_mle(const PostParams<T> p) {
+    const int64_t t = (int64_t)blockIdx.x * kTile + threadIdx.x;
+    const bool in = t < p.n1;
+    int slot = -1;
+    T lp = Num<T>::neg_inf();
+    if (in) {
+        slot = p.rstar[t];
+        const int64_t i = p.idx[t];
+        ModelW<T> w;
+        model_weights<T>(p.G, p.feh, p.loga, i, w);
+        const T scale = p.rows[p.ld + t];
+        lp = p.rows[t] + (p.lnprior ? p.lnprior[i] : T(0)) + gal_lnprior<T>(p.G, p.gstar[slot], w, T(1) / psqrt(scale));
+        p.lnp1[t] = lp;
+    }
+    cta_star_max<T>(p.red, RED_P1, slot, in, lp);
+}
+
+template <typename T> __device__ __forceinline__ bool post_flag(const PostParams<T>& p, int64_t t, int& slot) {
+    slot = -1;
+    if (t >= p.n1) return false;
+    slot = p.rstar[t];
+    return p.lnp1[t] > Enc<T>::dec(p.red[(int64_t)slot * kNumRed + RED_P1]) + p.ln_wt;   // (:1013-1016)
+}
+
+template <typename T> __global__ void __launch_bounds__(kTile) k_post_count(const PostParams<T> p) {
+    const int64_t t = (int64_t)blockIdx.x * kTile + threadIdx.x;
+    int slot;
+    const bool f = post_flag(p, t, slot);
+    const int n = __syncthreads_count(f);
+    if (threadIdx.x == 0) p.blk[blockIdx.x] = n;
+    cta_star_count(p.nsel2, slot, f);
+}
+
+template <typename T> __global__ void __launch_bounds__(kTile) k_post_write(const PostParams<T> p) {
+    __shared__ int s_w[kTile / 32];
+    const int64_t t = (int64_t)blockIdx.x * kTile + threadIdx.x;
+    int slot;
+    const bool f = post_flag(p, t, slot);
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) s_w[w] = __popc(bal);
+    __syncthreads();
+    if (f) {
+        int pre = __popc(bal & ((1u << lane) - 1u));
+        for (int k = 0; k < w; k++) pre += s_w[k];
+        p.sel2[p.blk[blockIdx.x] + pre] = (int)t;
+    }
+}
+
+// Covariance of (s, Av, Rv) in RELATIVE scale units (s' = s / scale, so that the matrix is O(1) whatever
+// the star's flux level): inverse of icov_sar by the adjugate (brutus/utils.py:71-114), regularised until
+// positive definite exactly as brutus/fitting.py:1042-1065 (the tests there are invariant under the
+// rescaling), then its Cholesky factor (brutus/utils.py:893-894).  float64 throughout: 3x3 algebra is
+// negligible next to the Nmc prior evaluations.
+struct Cov3 {
+    double c[6];   // cov' (00, 01, 02, 11, 12, 22), relative units
+    double L[6];   // Cholesky factor (00, 10, 11, 20, 21, 22)
+};
+
+__device__ __forceinline__ bool inv_sym3(const double (&a)[6], double (&c)[6]) {
+    const double a00 = a[0], a01 = a[1], a02 = a[2], a11 = a[3], a12 = a[4], a22 = a[5];
+    const double m00 = a11 * a22 - a12 * a12, m01 = a02 * a12 - a01 * a22, m02 = a01 * a12 - a02 * a11;
+    const double m11 = a00 * a22 - a02 * a02, m12 = a01 * a02 - a00 * a12, m22 = a00 * a11 - a01 * a01;
+    // determinant as the mean of the three row expansions (brutus/utils.py:100)
+    const double det = ((a00 * m00 + a01 * m01 + a02 * m02) + (a01 * m01 + a11 * m11 + a12 * m12) +
+                        (a02 * m02 + a12 * m12 + a22 * m22)) * (1.0 / 3.0);
+    const double id = 1.0 / det;
+    c[0] = m00 * id; c[1] = m01 * id; c[2] = m02 * id; c[3] = m11 * id; c[4] = m12 * id; c[5] = m22 * id;
+    // positive definite?  (np.linalg.eigvals(cov) > 0 for a symmetric matrix <=> Sylvester)
+    const double d2 = c[0] * c[3] - c[1] * c[1];
+    const double d3 = c[0] * (c[3] * c[5] - c[4] * c[4]) - c[1] * (c[1] * c[5] - c[4] * c[2]) + c[2] * (c[1] * c[4] - c[3] * c[2]);
+    return c[0] > 0. && d2 > 0. && d3 > 0.;
+}
+
+template <typename T>
+__device__ __forceinline__ void make_cov(const T* __restrict__ rows, int64_t ld, int64_t t, double scale, Cov3& cv) {
+    double a[6];
+    a[0] = (double)rows[5 * ld + t] * scale * scale;
+    a[1] = (double)rows[6 * ld + t] * scale;
+    a[2] = (double)rows[7 * ld + t] * scale;
+    a[3] = (double)rows[8 * ld + t];
+    a[4] = (double)rows[9 * ld + t];
+    a[5] = (double)rows[10 * ld + t];
+    bool ok = inv_sym3(a, cv.c);
+    const double iw2 = 1.0 / (0.02 * 0.02);   // 2 % Gaussian prior (:1044)
+    double count = 1.0;
+    for (int it = 0; it < 80 && !ok; it++) {
+        const bool i1 = cv.c[0] <= 0., i2 = cv.c[3] <= 0., i3 = cv.c[5] <= 0.;
+        const bool s1 = i1 || (!i2 && !i3), s2 = i2 || (!i1 && !i3), s3 = i3 || (!i1 && !i2);   // (:1054-1056)
+        if (s1) a[0] += count * iw2;        // count / (scale * width)^2 in absolute units
+        if (s2) a[3] += count * iw2;
+        if (s3) a[5] += count * iw2;
+        ok = inv_sym3(a, cv.c);
+        count *= 2.0;
+    }
+    const double* c = cv.c;
+    const double l00 = sqrt(c[0] > 0. ? c[0] : 0.);
+    const double l10 = l00 > 0. ? c[1] / l00 : 0., l20 = l00 > 0. ? c[2] / l00 : 0.;
+    const double t11 = c[3] - l10 * l10;
+    const double l11 = sqrt(t11 > 0. ? t11 : 0.);
+    const double l21 = l11 > 0. ? (c[4] - l20 * l10) / l11 : 0.;
+    const double t22 = c[5] - l20 * l20 - l21 * l21;
+    cv.L[0] = l00; cv.L[1] = l10; cv.L[2] = l11; cv.L[3] = l20; cv.L[4] = l21; cv.L[5] = sqrt(t22 > 0. ? t22 : 0.);
+}
+
+// one Monte Carlo draw of a selected model and its log-prior (:1070-1095)
+template <typename T> struct McCtx {
+    T scale, av, rv;
+    T L[6];
+    ModelW<T> w;
+    GalStar<T> gs;
+    T par, pivar, lnorm_par;   // parallax prior (brutus/pdf.py:144-175); pivar = 0: none
+    uint32_t model;
+    uint64_t star;
+};
+
+template <typename T>
+__device__ __forceinline__ void mc_draw(const PostParams<T>& p, const McCtx<T>& c, int j, T& s, T& a, T& r, T& lp, bool& inb) {
+    T z[3];
+    if (p.zov) {
+        const double* zz = p.zov + (size_t)c.model * 3 * p.nmc + j;
+        z[0] = (T)zz[0]; z[1] = (T)zz[p.nmc]; z[2] = (T)zz[2 * p.nmc];
+    } else {
+        normals3<T>(p.seed, c.star, c.model, (uint32_t)j, z);
+    }
+    s = c.scale * (T(1) + c.L[0] * z[0]);
+    a = c.av + c.L[1] * z[0] + c.L[2] * z[1];
+    r = c.rv + c.L[3] * z[0] + c.L[4] * z[1] + c.L[5] * z[2];
+    inb = s >= T(1e-20) && a >= p.avmin && a <= p.avmax && r >= p.rvmin && r <= p.rvmax;   // (:1090-1092)
+    lp = Num<T>::kNegBig;
+    if (inb) {
+        const T par = psqrt(s);
+        lp = gal_lnprior<T>(p.G, c.gs, c.w, T(1) / par);
+        if (c.pivar > T(0)) {
+            const T d = par - c.par;
+            lp += T(-0.5) * (d * d * c.pivar + c.lnorm_par);
+        }
+        if (lp != lp) lp = Num<T>::neg_inf();
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void mc_setup(const PostParams<T>& p, int64_t t, int slot, McCtx<T>& c, Cov3& cv) {
+    const int64_t i = p.idx[t];
+    c.scale = p.rows[p.ld + t];
+    c.av = p.rows[2 * p.ld + t];
+    c.rv = p.rows[4 * p.ld + t];
+    make_cov<T>(p.rows, p.ld, t, (double)c.scale, cv);
+#pragma unroll
+    for (int k = 0; k < 6; k++) c.L[k] = (T)cv.L[k];
+    model_weights<T>(p.G, p.feh, p.loga, i, c.w);
+    c.gs = p.gstar[slot];
+    const T* __restrict__ srow = p.stars + (int64_t)slot * kStarStride;
+    c.par = srow[SR_SC + SC_PAR];
+    c.pivar = srow[SR_SC + SC_PIVAR];
+    c.lnorm_par = c.pivar > T(0) ? T(1.8378770664093453) - plog(c.pivar) : T(0);
+    c.model = (uint32_t)i;
+    c.star = (uint64_t)(p.star_base + slot);
+}
+
+// log-sum-exp accumulator over the draws; -inf terms contribute nothing, kNegBig terms (out of bounds,
+// the reference's -1e300) contribute exp(kNegBig - max) = 0 unless every term is kNegBig
+template <typename T> struct Lse {
+    T m, s;
+    __device__ Lse() : m(Num<T>::neg_inf()), s(T(0)) {}
+    __device__ void add(T x) {
+        if (!(x > Num<T>::neg_inf())) return;
+        if (x > m) { s = s * pexp(m - x) + T(1); m = x; }
+        else s += pexp(x - m);
+    }
+    __device__ T value() const { return s > T(0) ? m + plog(s) : Num<T>::neg_inf(); }
+};
+
+// (:1038-1106) one thread per model of the second selection
+template <typename T> __global__ void __launch_bounds__(kTile) k_post_mc(const PostParams<T> p) {
+    const int64_t u = (int64_t)blockIdx.x * kTile + threadIdx.x;
+    const bool in = u < p.n2;
+    int slot = -1;
+    T lnp = Num<T>::neg_inf(), nchi = Num<T>::neg_inf();
+    if (in) {
+        const int64_t t = p.sel2[u];
+        slot = p.rstar[t];
+        McCtx<T> c;
+        Cov3 cv;
+        mc_setup<T>(p, t, slot, c, cv);
+        Lse<T> acc;
+        int neff = 0;
+        for (int j = 0; j < p.nmc; j++) {
+            T s, a, r, lp; bool inb;
+            mc_draw<T>(p, c, j, s, a, r, lp, inb);
+            acc.add(lp);
+            neff += inb ? 1 : 0;
+        }
+        const int64_t i = p.idx[t];
+        lnp = p.rows[t] + (p.lnprior ? p.lnprior[i] : T(0));                 // lnlike + lnprior (:1024)
+        lnp = neff > 0 ? lnp + acc.value() - plog((T)neff) : Num<T>::kNegBig;  // (:1098-1100; Neff = 0 -> +inf -> -1e300)
+        if (!Num<T>::finite(lnp) || lnp < Num<T>::kNegBig) lnp = Num<T>::kNegBig;   // (:1103-1105)
+        p.lnp2[u] = lnp;
+        // chi2 with the parallax term (:2025-2030), for chi2min
+        T chi2 = p.rows[3 * p.ld + t];
+        if (c.pivar > T(0)) { const T d = psqrt(c.scale) - c.par; chi2 += d * d * c.pivar; }
+        nchi = -chi2;
+    }
+    cta_star_max<T>(p.red, RED_P2, slot, in, lnp);
+    cta_star_max<T>(p.red, RED_NCHI, slot, in, nchi);
+}
+
+// block-wide inclusive scan of doubles (1024 threads); returns the inclusive prefix, total through `total`
+__device__ __forceinline__ double block_incscan_1024(double v, double* s_w, double& total) {
+    double x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double y = __shfl_up_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double w = s_w[threadIdx.x];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            double y = __shfl_up_sync(0xffffffffu, w, o);
+            if (threadIdx.x >= o) w += y;
+        }
+        s_w[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const double incl = x + ((threadIdx.x >> 5) ? s_w[(threadIdx.x >> 5) - 1] : 0.);
+    total = s_w[31];
+    __syncthreads();
+    return incl;
+}
+
+// one CTA per star of the group: cumulative weights exp(lnp - max) of its selected models, evidence (:2032-2039)
+template <typename T> __global__ void __launch_bounds__(1024) k_post_cdf(const PostParams<T> p) {
+    __shared__ double s_w[32];
+    const int slot = p.g0 + blockIdx.x;
+    const int64_t lo = p.off2[slot], hi = p.off2[slot + 1];
+    const T M = Enc<T>::dec(p.red[(int64_t)slot * kNumRed + RED_P2]);
+    double carry = 0.;
+    for (int64_t b = lo; b < hi; b += 1024) {
+        const int64_t u = b + threadIdx.x;
+        const double w = u < hi ? exp((double)p.lnp2[u] - (double)M) : 0.;
+        double tot;
+        const double inc = block_incscan_1024(w, s_w, tot);
+        if (u < hi) p.cdf[u] = carry + inc;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) {
+        p.tot[slot] = carry;
+        const bool bad = !(M > Num<T>::kNegBig);
+        p.o_levid[slot] = bad ? -1e300 + log(carry > 0. ? carry : 1.) : (double)M + log(carry);
+        const T nchi = Enc<T>::dec(p.red[(int64_t)slot * kNumRed + RED_NCHI]);
+        p.o_chi2min[slot] = -(double)nchi;
+    }
+}
+
+// one CTA per star, one thread per posterior draw (:2040-2061)
+template <typename T> __global__ void k_post_draw(const PostParams<T> p) {
+    const int slot = p.g0 + blockIdx.x;
+    const int64_t lo = p.off2[slot], hi = p.off2[slot + 1];
+    for (int d = threadIdx.x; d < p.ndraws; d += blockDim.x) {
+    const int64_t o = (int64_t)slot * p.ndraws + d;
+    if (hi <= lo) { p.o_idx[o] = -99; continue; }
+    double u1, u2;
+    if (p.uov) {
+        u1 = p.uov[((size_t)slot * 2 + 0) * p.ndraws + d];
+        u2 = p.uov[((size_t)slot * 2 + 1) * p.ndraws + d];
+    } else {
+        uint32_t r[4];
+        const uint64_t star = (uint64_t)(p.star_base + slot);
+        philox4x32_10((uint32_t)d, 0x44524157u, (uint32_t)star, (uint32_t)(star >> 32) ^ 0x52455331u, (uint32_t)p.seed,
+                      (uint32_t)(p.seed >> 32), r);
+        u1 = u01d(r[0], r[1]);
+        u2 = u01d(r[2], r[3]);
+    }
+    // numpy's choice: cdf /= cdf[-1]; searchsorted(cdf, u, side='right') = first entry with cdf > u
+    const double tot = p.tot[slot];
+    int64_t a = lo, b = hi;
+    while (a < b) {
+        const int64_t mid = (a + b) >> 1;
+        if (p.cdf[mid] / tot > u1) b = mid; else a = mid + 1;
+    }
+    const int64_t u = a < hi ? a : hi - 1;
+    const int64_t t = p.sel2[u];
+    McCtx<T> c;
+    Cov3 cv;
+    mc_setup<T>(p, t, slot, c, cv);
+    const double sc = (double)c.scale;
+    p.o_idx[o] = p.idx[t];
+    p.o_scale[o] = sc;
+    p.o_av[o] = (double)c.av;
+    p.o_rv[o] = (double)c.rv;
+    double* cc = p.o_cov + o * 9;
+    cc[0] = cv.c[0] * sc * sc; cc[1] = cc[3] = cv.c[1] * sc; cc[2] = cc[6] = cv.c[2] * sc;
+    cc[4] = cv.c[3]; cc[5] = cc[7] = cv.c[4]; cc[8] = cv.c[5];
+    const T lnp = p.lnp2[u];
+    p.o_lnprob[o] = lnp <= Num<T>::kNegBig ? -1e300 : (double)lnp;
+    // pick one of the model's Nmc draws with probability ~ exp(lnp_mc) (:2050-2053)
+    Lse<T> acc;
+    for (int j = 0; j < p.nmc; j++) {
+        T s, av, rv, lp; bool inb;
+        mc_draw<T>(p, c, j, s, av, rv, lp, inb);
+        acc.add(lp);
+    }
+    const T m = acc.m;
+    const double W = (double)acc.s;
+    double run = 0.;
+    int pick = -1;
+    T ps = c.scale, pa = c.av, pr = c.rv, pl = Num<T>::neg_inf();
+    for (int j = 0; j < p.nmc && pick < 0; j++) {
+        T s, av, rv, lp; bool inb;
+        mc_draw<T>(p, c, j, s, av, rv, lp, inb);
+        // all draws at -inf: exp(-inf - -inf) is NaN in the reference too; fall through to the last draw
+        if (lp > Num<T>::neg_inf()) run += (double)pexp(lp - m);
+        if ((W > 0. && run / W > u2) || j == p.nmc - 1) { pick = j; ps = s; pa = av; pr = rv; pl = lp; }
+    }
+    p.o_dist[o] = 1. / sqrt((double)ps);
+    p.o_red[o] = (double)pa;
+    p.o_dred[o] = (double)pr;
+    p.o_logwt[o] = pl <= Num<T>::kNegBig ? -1e300 : (double)pl;
+    }
+}
+
+}  // namespace bf

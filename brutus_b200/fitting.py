@@ -255,11 +255,18 @@ class BruteForce(object):
     """Same constructor, ``fit`` and ``_fit`` as the reference's ``BruteForce``
     (brutus/fitting.py:1110-2065), with the per-star full-grid sweep on the GPU.
 
-    Differences, all outside the hot path: the default Galactic and 3-D dust priors are not bundled
-    (pass ``lngalprior`` / ``lndustprior``; with ``dustfile=None`` and no ``lndustprior`` the A(V)
-    prior is flat, as in the reference :1396-1398); ``parallax=None`` is accepted (the reference
-    raises TypeError); results go to ``<save_file>.h5`` when h5py is importable and to
-    ``<save_file>.npz`` with the same dataset names otherwise."""
+    Two posterior paths.  With ``lngalprior=None`` (the reference's default, ``gal_lnprior``) the whole
+    per-object body of ``_fit`` runs on the device (``bf_fit_batch``): sweep, ``lnpost`` with the built-in
+    Galactic prior (brutus/pdf.py:476-749), evidence and resampling; only ``Ndraws`` samples per object
+    cross PCIe and the random numbers come from a counter-based generator seeded from ``rstate``.  With
+    a user ``lngalprior`` callable the selected models are shipped to the host and ``lnpost`` runs in NumPy
+    with the caller's ``rstate`` exactly as in the reference.
+
+    Differences, all outside the hot path: the 3-D dust prior is not bundled (no Bayestar map offline;
+    pass ``lndustprior`` on the host path; with ``dustfile=None`` and no ``lndustprior`` the A(V) prior is
+    flat, as in the reference :1396-1398); ``parallax=None`` is accepted (the reference raises TypeError);
+    ``mem_lim`` is ignored on the device path; results go to ``<save_file>.h5`` when h5py is importable and
+    to ``<save_file>.npz`` with the same dataset names otherwise."""
 
     def __init__(self, models, models_labels, labels_mask, precision="f32", device=0):
         self.NMODEL, self.NDIM, self.NCOEF = models.shape
@@ -278,6 +285,18 @@ class BruteForce(object):
             h.set_grid(self.models)
             self._handle = h
         return self._handle
+
+    # test hook: host-supplied normals / uniforms for the device posterior (tests/test_posterior_gpu.py)
+    _z_override = None
+    _u_override = None
+
+    def _post_test_hooks(self, b0, b1):
+        kw = {}
+        if self._z_override is not None:
+            kw["z_override"] = self._z_override
+        if self._u_override is not None:
+            kw["u_override"] = self._u_override[b0:b1]
+        return kw
 
     def close(self):
         if self._handle is not None:
@@ -325,8 +344,8 @@ class BruteForce(object):
                     ul = np.unique(self.models_labels[l])
                     if len(ul) > 1:
                         lnprior = lnprior + np.interp(self.models_labels[l], ul, np.log(np.gradient(ul)))
-        if lngalprior is None:
-            raise NotImplementedError("pass `lngalprior`: the default Galactic prior is not bundled")
+        if lngalprior is None and data_coords is None:   # brutus/fitting.py:1362-1365
+            raise ValueError("`data_coords` must be provided if using the default Galactic model prior.")
         if lndustprior is None and dustfile is not None:
             raise NotImplementedError("pass `lndustprior`: the Bayestar dust prior is not bundled")
         if lndustprior is None and av_gauss is None:
@@ -374,6 +393,11 @@ class BruteForce(object):
         parallax_err = np.asarray(parallax_err, dtype=np.float64)
         dlabels = self.models_labels if apply_dlabels else None
         h = self._get_handle()
+        device_posterior = lngalprior is None
+        if device_posterior and lndustprior is not None:
+            raise NotImplementedError("a user `lndustprior` needs a user `lngalprior` too (host posterior path)")
+        if device_posterior and Nmc_prior < 1:
+            raise NotImplementedError("Nmc_prior = 0 is only supported on the host posterior path")
         ext_keys = []
         if lnprior_ext is not None:
             ext_keys = list(lnprior_ext.keys())
@@ -387,12 +411,32 @@ class BruteForce(object):
         opts = _lib.make_options(avlim=avlim, av_gauss=av_gauss, rvlim=rvlim, rv_gauss=rv_gauss,
                                  dim_prior=logl_dim_prior, ltol=ltol, ltol_subthresh=ltol_subthresh,
                                  init_thresh=logl_initthresh, wt_thresh=wt_thresh)
+        if device_posterior:
+            names = (dlabels.dtype.names or ()) if dlabels is not None else ()
+            h.set_model_priors(lnprior=lnprior if np.ndim(lnprior) else np.full(self.NMODEL, float(lnprior)),
+                               feh=dlabels["feh"] if "feh" in names else None,
+                               loga=dlabels["loga"] if "loga" in names else None)
+            seed = int(rstate.randint(0, 2 ** 31 - 1)) if hasattr(rstate, "randint") else 0
         for b0 in range(0, ndata, batch):
             b1 = min(ndata, b0 + batch)
             em = es = None
             if ext_keys:
                 ext = np.array([[lnprior_ext[k][i] for k in ext_keys] for i in range(b0, b1)], dtype=np.float64)
                 em, es = ext[:, :, 0], ext[:, :, 1]
+            if device_posterior:
+                # star_base keeps the generator keyed by the catalogue index of every star
+                r = h.fit_batch(data[b0:b1], data_err[b0:b1], data_mask[b0:b1], parallax[b0:b1],
+                                parallax_err[b0:b1], coords=data_coords[b0:b1], ext_mean=em, ext_std=es,
+                                opts=opts, nmc_prior=Nmc_prior, ndraws=Ndraws,
+                                seed=seed, star_base=b0, **(self._post_test_hooks(b0, b1)))
+                for k in range(b1 - b0):
+                    out = (r["sidxs"][k].astype(np.int64), r["scales"][k], r["avs"][k], r["rvs"][k],
+                           r["cov_sar"][k], int(r["ndim"][k]), r["lnprob"][k], float(r["levid"][k]),
+                           float(r["chi2min"][k]))
+                    if return_distreds:
+                        out = out + (r["dists"][k], r["reds"][k], r["dreds"][k], r["logwts"][k])
+                    yield out
+                continue
             res = h.sweep_batch(data[b0:b1], data_err[b0:b1], data_mask[b0:b1], parallax[b0:b1],
                                 parallax_err[b0:b1], ext_mean=em, ext_std=es, opts=opts,
                                 rows=_lib.REC_FULL, copy=True)

@@ -78,6 +78,8 @@ typedef struct bf_stats {
     int64_t survivors;      /* total models that survived the cull (brutus/fitting.py:758-759)  */
     int64_t selected;       /* total models that passed wt_thresh                     */
     int64_t h2d_bytes, d2h_bytes;
+    double ms_post;         /* bf_fit_batch: prior integration, evidence, resampling kernels */
+    int64_t selected2;      /* bf_fit_batch: models that passed lnpost's second threshold     */
 } bf_stats;
 
 void bf_default_options(bf_options* opt);
@@ -145,7 +147,68 @@ int bf_sweep_batch(bf_handle* h, int64_t nstar, const double* flux, const double
                    int32_t record_rows, int32_t* ndim, int32_t* n_iter, int64_t* n_surv,
                    double* max_lnprob, int64_t* offsets, bf_records* out);
 
-/* Statistics of the most recent bf_loglike_full / bf_sweep_batch call on this handle. */
+/* ---- device-side posterior: lnpost after its first selection, evidence, resampling --------------------
+ * (brutus/fitting.py:999-1107 and :2012-2061) */
+
+/* Parameters of the default Galactic prior, gal_lnprior (brutus/pdf.py:476-486), plus the two frame
+ * constants astropy's Galactocentric frame supplies at brutus/pdf.py:630-635. */
+typedef struct bf_gal_params {
+    double R_solar, Z_solar, R_thin, Z_thin, Rs_thin, R_thick, Z_thick, f_thick, Rs_thick;
+    double Rs_halo, q_halo_ctr, q_halo_inf, r_q_halo, eta_halo, f_halo;
+    double feh_thin, feh_thin_sigma, feh_thick, feh_thick_sigma, feh_halo, feh_halo_sigma;
+    double max_age, min_age, feh_age_ctr, feh_age_scale, nsigma_from_max_age, max_sigma, min_sigma;
+    double galcen_distance, z_sun;   /* 8.122 kpc, 0.0208 kpc */
+} bf_gal_params;
+void bf_default_gal_params(bf_gal_params* g);
+
+/* Keyword arguments of lnpost / _fit that reach the posterior kernels. */
+typedef struct bf_post_options {
+    int32_t nmc_prior;      /* Nmc_prior (fit() default 50); must be >= 1                          */
+    int32_t ndraws;         /* Ndraws, default 250                                                 */
+    uint64_t seed;          /* keys the counter-based generator (stands in for `rstate`)            */
+    int32_t use_gal_prior;  /* 1: built-in gal_lnprior with `gal`; 0: flat distance prior           */
+    int32_t reserved;
+    int64_t star_base;      /* catalogue index of the first star of this call: the generator is keyed by
+                               (seed, star_base + s, model, draw), so a batched or star-sharded caller gets
+                               the same numbers as one call over the whole catalogue */
+    bf_gal_params gal;
+    /* test hooks (NULL in production): host-supplied random numbers so that the device result can be
+     * compared draw for draw with a NumPy restatement.
+     *   z_override [nmodel][3][nmc_prior] standard normals, used for every star (the reference draws
+     *              z.reshape(Nsel, 3, Nmc), brutus/utils.py:897)
+     *   u_override [nstar][2][ndraws] uniforms: [0] the model draw (:2040), [1] the MC pick (:2052) */
+    const double* z_override;
+    const double* u_override;
+} bf_post_options;
+void bf_default_post_options(bf_post_options* o);
+
+/* Static per-model inputs of lnpost, staged once: lnprior (the `lnprior` grid of fit(),
+ * brutus/fitting.py:1004), and the label columns 'feh' / 'loga' the Galactic prior uses
+ * (brutus/pdf.py:669, :694).  Each is float64 [nmodel] or NULL (0 / label absent). */
+int bf_set_model_priors(bf_handle* h, const double* lnprior, const double* feh, const double* loga);
+
+/* Posterior draws of every star, caller-allocated, [nstar*ndraws] each (cov: [nstar*ndraws*9]):
+ * the 13-tuple BruteForce._fit yields per object (brutus/fitting.py:2059-2061). */
+typedef struct bf_draws {
+    int32_t* model_idx;   /* sidxs  (-99 where a star has no selected model) */
+    double *scale, *av, *rv, *cov_sar, *lnprob, *dist, *red, *dred, *logwt;
+} bf_draws;
+
+/* The per-star body of BruteForce._fit end to end on the device (brutus/fitting.py:1980-2061):
+ * bf_sweep_batch's work, then lnpost (priors at the MLE, second threshold, covariances, Monte Carlo
+ * integration over the Galactic and parallax priors), the evidence, chi2min and the resampling.
+ * Only ndraws samples per star cross PCIe.  Not applied: the 3-D dust prior (no map bundled: flat
+ * A(V) prior, as fit(dustfile=None) :1396-1398) and the mem_lim clip (:1029-1036).
+ *   coords [nstar*2] float64 Galactic (l, b) in degrees, or NULL with use_gal_prior = 0
+ * outputs: ndim [nstar] (incl. +1 for a finite parallax, :2030), n_iter [nstar*2], nsel [nstar] (size of
+ * the second selection), levid, chi2min [nstar]; any of ndim / n_iter / nsel may be NULL. */
+int bf_fit_batch(bf_handle* h, int64_t nstar, const double* flux, const double* err, const uint8_t* mask,
+                 const double* parallax, const double* parallax_err, const double* coords,
+                 const double* ext_mean, const double* ext_std, const bf_options* opt,
+                 const bf_post_options* post, int32_t* ndim, int32_t* n_iter, int64_t* nsel,
+                 double* levid, double* chi2min, bf_draws* out);
+
+/* Statistics of the most recent bf_loglike_full / bf_sweep_batch / bf_fit_batch call on this handle. */
 int bf_get_stats(const bf_handle* h, bf_stats* out);
 
 /* Benchmark hygiene: overwrite a 512 MB scratch buffer so that nothing of the previous step stays
