@@ -11,8 +11,12 @@ builds it, one NCCL broadcast, no collective in the hot loop): weak scaling.
 
   value            stars/s from CUDA-event device time (first kernel -> last kernel of each call,
                    grid and scratch resident in HBM), max over ranks
-  e2e              stars/s through the C ABI with host buffers: wall clock of the calls, including
-                   host preparation of the star rows, H2D of the star rows and D2H of the records
+  e2e              stars/s through the call a user makes, BruteForce.fit's per-object body
+                   (bf_fit_batch: the same sweep, then lnpost with the default Galactic prior, evidence
+                   and resampling on the device; host float64 photometry in, Ndraws posterior samples
+                   per star out): wall clock of the calls, host preparation, H2D and D2H included
+  e2e_records      the same for bf_sweep_batch, which ships every selected model's record to the host
+                   for a host-side lnpost (user-supplied prior callables): PCIe-bound
   roofline         dominant kernel k_magfit: algorithmic bytes (Nmodel x Nfilt x 12 B per star per
                    pass) / its CUDA-event time, against the measured HBM copy peak
   cpu_baseline     the C oracle (port of the reference's loglike) on this box's host cores
@@ -122,6 +126,16 @@ def make_inputs(cfg_id, cfg, rank, need_grid=True):
     return grid, labels
 
 
+def model_priors(labels):
+    """Static inputs of lnpost for the mock grid: IMF prior over 'mini' (fit()'s default `lnprior`,
+    brutus/fitting.py:1296-1300) and the 'feh' / 'loga' labels of the Galactic prior."""
+    from brutus_b200 import fitting
+    names = labels.dtype.names
+    lnprior = fitting.imf_lnprior(labels["mini"]) if "mini" in names else None
+    return dict(lnprior=lnprior, feh=labels["feh"] if "feh" in names else None,
+                loga=labels["loga"] if "loga" in names else None)
+
+
 def make_stars(cfg_id, cfg, grid, rank):
     from brutus_b200 import mock
     return mock.make_stars(grid, cfg["nstar"], seed=2000 + cfg_id + 100 * rank, av_max=cfg["av_max"],
@@ -208,7 +222,7 @@ def run_b200(args):
         import torch
         from brutus_b200 import shard
         shape = (cfg["nmodel"], cfg["nfilt"], 3)
-        grid = make_inputs(args.config, cfg, 0)[0] if rank == 0 else None
+        grid, labels = make_inputs(args.config, cfg, 0) if rank == 0 else (None, None)
         # one NCCL broadcast GPU -> GPU, re-tiled on each device (bf_set_grid_device)
         dgrid = shard.broadcast_grid(grid, shape, dist=dist, src=0, handle=h,
                                      device=torch.device("cuda", local_rank))
@@ -216,9 +230,16 @@ def run_b200(args):
             grid = dgrid.cpu().numpy()  # only to draw this rank's synthetic stars from
         del dgrid
         torch.cuda.empty_cache()
+        # the per-model priors / labels of lnpost (3 x Nmodel float64), also one broadcast
+        pri = model_priors(labels) if rank == 0 else None
+        obj = [pri]
+        dist.broadcast_object_list(obj, src=0)
+        pri = obj[0]
     else:
-        grid, _ = make_inputs(args.config, cfg, 0)
+        grid, labels = make_inputs(args.config, cfg, 0)
         h.set_grid(grid)
+        pri = model_priors(labels)
+    h.set_model_priors(**pri)
     t_stage = time.perf_counter() - t0
     stars = make_stars(args.config, cfg, grid, rank)
     opts = _lib.make_options(avlim=cfg["avlim"])
@@ -242,9 +263,21 @@ def run_b200(args):
         wall = time.perf_counter() - t
         return res, wall, h.stats()
 
+    def step_fit():
+        """One pass of BruteForce.fit's per-object body (bf_fit_batch): host photometry in, posterior
+        samples out; the generator is keyed by (seed, catalogue index)."""
+        h.flush_l2()
+        t = time.perf_counter()
+        res = h.fit_batch(stars["flux"], stars["err"], stars["mask"], stars["parallax"],
+                          stars["parallax_err"], coords=stars["coords"], opts=opts,
+                          nmc_prior=args.nmc_prior, ndraws=args.ndraws, seed=12345, star_base=rank * nstar)
+        wall = time.perf_counter() - t
+        return res, wall, h.stats()
+
     for _ in range(args.warmup):
         step(True)
         step(False)
+        step_fit()
     sampler = ClockSampler(local_rank)
     sampler.start()
     # ---- timed region 1: K steps, device time from CUDA events (value, roofline) ----
@@ -267,13 +300,22 @@ def run_b200(args):
         for k, v in st.items():
             agg_e[k] = agg_e.get(k, 0) + v
     barrier()
+    # ---- timed region 3: K steps of the fit-level call (device posterior), end to end ----
+    wall_f = 0.0
+    agg_f = {}
+    for _ in range(args.steps):
+        resf, wall, st = step_fit()
+        wall_f += wall
+        for k, v in st.items():
+            agg_f[k] = agg_f.get(k, 0) + v
+    barrier()
     t_region = time.perf_counter() - t_region
     clocks = sampler.summary()
     if world > 1:
         import torch
-        t = torch.tensor([dev_ms, wall_s], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dev_ms, wall_s, wall_f], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, wall_s = float(t[0]), float(t[1])
+        dev_ms, wall_s, wall_f = float(t[0]), float(t[1]), float(t[2])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -282,6 +324,7 @@ def run_b200(args):
     total_stars = nstar * args.steps * world
     value = total_stars / (dev_ms * 1e-3)
     e2e = total_stars / wall_s
+    e2e_fit = total_stars / wall_f
     peak, peak_src = read_peaks()
     bytes_per_star = cfg["nmodel"] * cfg["nfilt"] * 12
     launches = max(1, agg["magfit_launches"])
@@ -295,12 +338,28 @@ def run_b200(args):
                    "grid": "mock %s (brutus_b200/mock.py)" % GRID_KIND, "stars_per_step_per_gpu": nstar, "parallelism": "stars sharded x%d, grid replicated" % world,
                    "l2": "512 MB L2 flush before every step",
                    "grid_stage_s": round(t_stage, 3)},
-        "e2e": {"value": e2e, "unit": "stars/s", "ms_per_step": 1e3 * wall_s / args.steps,
-                "h2d_bytes_per_step": int(agg_e["h2d_bytes"] / args.steps),
-                "d2h_bytes_per_step": int(agg_e["d2h_bytes"] / args.steps),
-                "record_rows": args.rows, "gpu_launches": int(agg_e["kernel_launches"]),
-                "note": "bf_sweep_batch with host float64 photometry in, pinned host records out; the D2H of "
-                        "one star batch overlaps the kernels of the next (PCIe-bound when many models are selected)"},
+        "e2e": {"value": e2e_fit, "unit": "stars/s", "ms_per_step": 1e3 * wall_f / args.steps,
+                "h2d_bytes_per_step": int(agg_f["h2d_bytes"] / args.steps),
+                "d2h_bytes_per_step": int(agg_f["d2h_bytes"] / args.steps),
+                "call": "bf_fit_batch (the per-object body of BruteForce.fit)",
+                "nmc_prior": args.nmc_prior, "ndraws": args.ndraws,
+                "gpu_launches": int(agg_f["kernel_launches"]),
+                "device_ms_per_step": agg_f["ms_device"] / args.steps,
+                "posterior_ms_per_step": agg_f["ms_post"] / args.steps,
+                "selected2_per_step": agg_f["selected2"] / args.steps,
+                "finite_evidence_frac": float(np.mean(resf["levid"] > -1e299)),
+                "note": "host float64 photometry in, Ndraws posterior samples per star out: the full-grid "
+                        "sweep of `value`, then lnpost (default Galactic prior, Nmc_prior Monte Carlo draws per "
+                        "selected model), evidence and resampling on the device -- a superset of the work the "
+                        "reference arm (loglike only) is timed on"},
+        "e2e_records": {"value": e2e, "unit": "stars/s", "ms_per_step": 1e3 * wall_s / args.steps,
+                        "h2d_bytes_per_step": int(agg_e["h2d_bytes"] / args.steps),
+                        "d2h_bytes_per_step": int(agg_e["d2h_bytes"] / args.steps),
+                        "call": "bf_sweep_batch", "record_rows": args.rows,
+                        "gpu_launches": int(agg_e["kernel_launches"]),
+                        "note": "host float64 photometry in, every selected model's record (48 B) out to pinned "
+                                "host memory for a host-side lnpost (user prior callables); the D2H of one star "
+                                "batch overlaps the kernels of the next; PCIe-bound (~52 GB/s)"},
         "gpu_launches": int(agg["kernel_launches"]),
         "roofline": {"bound": "hbm", "kernel": "k_magfit", "achieved": ach, "peak": peak, "unit": "GB/s",
                      "frac": ach / peak, "peak_source": peak_src,
@@ -348,6 +407,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--rows", type=int, default=11, choices=[3, 5, 11],
                     help="record rows shipped to the host per selected model (11 = everything)")
+    ap.add_argument("--nmc-prior", type=int, default=50, help="Nmc_prior of fit() (brutus/fitting.py:1429)")
+    ap.add_argument("--ndraws", type=int, default=250, help="Ndraws of fit() (brutus/fitting.py:1431)")
     ap.add_argument("--grid", default="locus", choices=["locus", "tilt"],
                     help="mock grid family (brutus_b200/mock.py): a stellar locus (default) or the degenerate "
                          "colour-tilt grid the golden vectors use")

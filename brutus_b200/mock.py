@@ -31,7 +31,8 @@ def make_grid_locus(nmodel, nfilt, seed=1000):
     evaluated at the mock filters' effective wavelengths.  Unlike :func:`make_grid` (whose single
     colour tilt is collinear with the reddening vector, so that a sixth of the grid fits any star),
     only the models near the star's Teff-A(V) degeneracy track survive, as with real grids.
-    Labels: 'mini', 'eep', 'feh', 'Mr' (``load_models``-like, brutus/utils.py:608-609)."""
+    Labels: 'mini', 'eep', 'feh', 'Mr', 'loga' (``load_models``-like, brutus/utils.py:608-609; 'loga' is a
+    main-sequence-lifetime-like log10 age in years, a deterministic function of mass and phase)."""
     rs = np.random.RandomState(seed)
     lam = _WAVE[:nfilt]
     u1, u2 = rs.uniform(size=nmodel), rs.uniform(size=nmodel)
@@ -59,9 +60,10 @@ def make_grid_locus(nmodel, nfilt, seed=1000):
         grid[lo:hi, :, 0] = mv + (bb - bbv) + blanket
         grid[lo:hi, :, 1] = (r0 - 3.3 * dr)[None, :]
         grid[lo:hi, :, 2] = dr[None, :]
-    labels = np.zeros(nmodel, dtype=[("mini", "f8"), ("eep", "f8"), ("feh", "f8"), ("Mr", "f8")])
+    labels = np.zeros(nmodel, dtype=[("mini", "f8"), ("eep", "f8"), ("feh", "f8"), ("Mr", "f8"), ("loga", "f8")])
     labels["mini"], labels["eep"], labels["feh"] = mini, 200. + 600. * u2, feh
     labels["Mr"] = grid[:, min(1, nfilt - 1), 0]
+    labels["loga"] = np.clip(10.0 - 2.5 * np.log10(mini) + 0.3 * (u2 - 0.5), 6.5, 10.13)   # <= 13.5 Gyr
     return grid, labels
 
 
@@ -95,7 +97,7 @@ def make_grid(nmodel, nfilt, seed=1000, kind="tilt"):
 def make_stars(grid, nstar, seed=2000, av_max=2.0, dropout=0.0, par_nan_frac=0.3,
                snr_range=(10., 100.)):
     """Mock catalogue drawn from the grid: returns dict(flux, err, mask, parallax, parallax_err,
-    truth=(idx, av, rv, dist))."""
+    coords, truth=(idx, av, rv, dist))."""
     rs = np.random.RandomState(seed)
     nmodel, nfilt, _ = grid.shape
     idx = rs.randint(0, nmodel, nstar)
@@ -120,5 +122,8 @@ def make_stars(grid, nstar, seed=2000, av_max=2.0, dropout=0.0, par_nan_frac=0.3
         for i in np.where((~drop).sum(axis=1) < 4)[0]:
             drop[i] = False
         mask &= ~drop
-    return dict(flux=flux, err=err, mask=mask, parallax=par, parallax_err=perr,
+    # Galactic (l, b) in degrees, from an independent stream so that the photometry above is unchanged
+    rc = np.random.RandomState(seed + 77_000)
+    coords = np.stack([rc.uniform(0., 360., nstar), np.rad2deg(np.arcsin(rc.uniform(-1., 1., nstar)))], axis=1)
+    return dict(flux=flux, err=err, mask=mask, parallax=par, parallax_err=perr, coords=coords,
                 truth=dict(idx=idx, av=av, rv=rv, dist=dist))
