@@ -1157,6 +1157,7 @@ template <typename T> struct Engine : EngineBase {
         G.use = po->use_gal_prior ? 1 : 0;
         G.has_feh = have_prior[1] ? 1 : 0;
         G.has_age = have_prior[2] ? 1 : 0;
+        G.same_rs = g.Rs_thin == g.Rs_thick ? 1 : 0;
         G.Rs_thin2 = (T)(g.Rs_thin * g.Rs_thin); G.Rs_thick2 = (T)(g.Rs_thick * g.Rs_thick); G.Rs_halo2 = (T)(g.Rs_halo * g.Rs_halo);
         G.R_solar = (T)g.R_solar; G.aZ_solar = (T)std::fabs(g.Z_solar);
         G.iR_thin = (T)(1. / g.R_thin); G.iZ_thin = (T)(1. / g.Z_thin);
@@ -1284,11 +1285,13 @@ template <typename T> struct Engine : EngineBase {
             if (n2 > 0) {
                 const unsigned nb1 = (unsigned)((n1 + kTile - 1) / kTile);
                 k_post_write<T><<<nb1, kTile, 0, stream>>>(pp);
-                k_post_mc<T><<<(unsigned)((n2 + kTile - 1) / kTile), kTile, 0, stream>>>(pp);
+                if (pp.zov) k_post_mc<T, true><<<(unsigned)((n2 + kTile - 1) / kTile), kTile, 0, stream>>>(pp);
+                else k_post_mc<T, false><<<(unsigned)((n2 + kTile - 1) / kTile), kTile, 0, stream>>>(pp);
                 stats.kernel_launches += 2;
             }
             k_post_cdf<T><<<ng, 1024, 0, stream>>>(pp);
-            k_post_draw<T><<<ng, std::min(1024, (nd + 31) / 32 * 32), 0, stream>>>(pp);
+            if (pp.zov) k_post_draw<T, true><<<ng, std::min(1024, (nd + 31) / 32 * 32), 0, stream>>>(pp);
+            else k_post_draw<T, false><<<ng, std::min(1024, (nd + 31) / 32 * 32), 0, stream>>>(pp);
             stats.kernel_launches += 2;
             CK(cudaGetLastError());
             CK(cudaEventRecord(evP1, stream));

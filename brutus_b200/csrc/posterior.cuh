@@ -19,11 +19,14 @@
 
 namespace bf {
 
-// ---- Philox4x32-10 (Salmon et al. 2011) --------------------------------------------------------------
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+// ---- Philox4x32 (Salmon et al. 2011) ------------------------------------------------------------------
+// R = 10 rounds is the standard generator (resampling uniforms); R = 7, the fewest rounds that pass
+// BigCrush in the paper, feeds the Monte Carlo normals, whose loop is bound by instruction issue.
+template <int R>
+__device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                           uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
 #pragma unroll
-    for (int r = 0; r < 10; r++) {
+    for (int r = 0; r < R; r++) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
         c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
@@ -44,8 +47,13 @@ __device__ __forceinline__ float pexp(float x) { return __expf(x); }
 __device__ __forceinline__ double pexp(double x) { return exp(x); }
 __device__ __forceinline__ float plog(float x) { return __logf(x); }
 __device__ __forceinline__ double plog(double x) { return log(x); }
-__device__ __forceinline__ float psqrt(float x) { return sqrtf(x); }
+// float: the approximate MUFU forms (2 ulp), no IEEE slow paths; the Monte Carlo noise is ~1e-1 relative
+__device__ __forceinline__ float psqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ double psqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ float prsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ double prsqrt(double x) { return 1.0 / sqrt(x); }
+__device__ __forceinline__ float prcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ double prcp(double x) { return 1.0 / x; }
 __device__ __forceinline__ float pexp10(float x) { return exp2f(x * 3.3219281f); }
 __device__ __forceinline__ double pexp10(double x) { return exp10(x); }
 
@@ -53,9 +61,9 @@ __device__ __forceinline__ double pexp10(double x) { return exp10(x); }
 template <typename T>
 __device__ __forceinline__ void normals3(uint64_t seed, uint64_t star, uint32_t model, uint32_t j, T (&z)[3]) {
     uint32_t r[4];
-    philox4x32_10(model, j, (uint32_t)star, (uint32_t)(star >> 32) ^ 0x4D435A31u, (uint32_t)seed,
+    philox4x32<7>(model, j, (uint32_t)star, (uint32_t)(star >> 32) ^ 0x4D435A31u, (uint32_t)seed,
                   (uint32_t)(seed >> 32), r);
-    const float r0 = sqrtf(-2.f * __logf(u01(r[0]))), r1 = sqrtf(-2.f * __logf(u01(r[2])));
+    const float r0 = psqrt(-2.f * __logf(u01(r[0]))), r1 = psqrt(-2.f * __logf(u01(r[2])));
     float s0, c0, s1, c1;
     __sincosf(6.2831853f * u01(r[1]), &s0, &c0);
     __sincosf(6.2831853f * u01(r[3]), &s1, &c1);
@@ -68,6 +76,7 @@ __device__ __forceinline__ void normals3(uint64_t seed, uint64_t star, uint32_t 
 template <typename T> struct GalDev {
     int use;                                  // 0: no distance prior
     int has_feh, has_age;
+    int same_rs;                              // Rs_thin == Rs_thick (the defaults): one square root serves both disks
     T Rs_thin2, Rs_thick2, Rs_halo2;          // smoothing radii squared          (:301, :363)
     T R_solar, aZ_solar;
     T iR_thin, iZ_thin, iR_thick, iZ_thick;   // inverse scale lengths            (:303-304)
@@ -107,27 +116,30 @@ __device__ __forceinline__ void model_weights(const GalDev<T>& G, const T* __res
     }
 }
 
-// ln prior(d) = 2 ln d + ln sum_X n_X + ln(sum f_X n_X / sum n_X) + ln(sum g_X n_X / sum n_X)
-// with n_X the thin / thick / halo number densities (:622-745; the three logsumexp of the reference
-// share the same exponentials)
+// ln prior = 2 ln d + ln sum_X n_X + ln(sum f_X n_X / sum n_X) + ln(sum g_X n_X / sum n_X)
+// with n_X the thin / thick / halo number densities (:622-745).  The three logsumexp of the reference share
+// the same exponentials; they are taken relative to the halo term, which dominates wherever the disks
+// underflow and is never more than ~e^10 below them, so no running maximum is needed:
+//   ln prior = ln n_halo + ln( s1 s2 / (s0 s) ),   s = 1/d^2 (the scale),  s_k = sums of n_X / n_halo.
+// `s` is the scale factor (parallax^2), `rs` = 1/sqrt(s) = the distance in kpc.
 template <typename T>
-__device__ __forceinline__ T gal_lnprior(const GalDev<T>& G, const GalStar<T>& gs, const ModelW<T>& w, T d) {
+__device__ __forceinline__ T gal_lnprior(const GalDev<T>& G, const GalStar<T>& gs, const ModelW<T>& w, T s, T d) {
     if (!G.use) return T(0);
-    const T vol = T(2) * plog(d);
     const T x = fma(d, gs.ax, gs.x0), y = d * gs.ay, z = fma(d, gs.az, gs.z0);
     const T R2 = x * x + y * y, aZ = tabs(z);
-    const T lt = -((psqrt(R2 + G.Rs_thin2) - G.R_solar) * G.iR_thin + (aZ - G.aZ_solar) * G.iZ_thin);
-    const T lk = -((psqrt(R2 + G.Rs_thick2) - G.R_solar) * G.iR_thick + (aZ - G.aZ_solar) * G.iZ_thick) + G.ln_f_thick;
+    const T Rthin = psqrt(R2 + G.Rs_thin2);
+    const T Rthick = G.same_rs ? Rthin : psqrt(R2 + G.Rs_thick2);
+    const T lt = -((Rthin - G.R_solar) * G.iR_thin + (aZ - G.aZ_solar) * G.iZ_thin);
+    const T lk = -((Rthick - G.R_solar) * G.iR_thick + (aZ - G.aZ_solar) * G.iZ_thick) + G.ln_f_thick;
     const T rp = psqrt(R2 + z * z + G.rq2);
     const T q = G.q_inf - G.dq * pexp(T(1) - rp * G.irq);
-    const T zq = z / q;
+    const T zq = z * prcp(q);
     const T lh = -G.eta * (T(0.5) * plog(R2 + zq * zq + G.Rs_halo2) - G.ln_Reff_solar) + G.ln_f_halo;
-    const T m = tmax(lt, tmax(lk, lh));
-    const T nt = pexp(lt - m), nk = pexp(lk - m), nh = pexp(lh - m);
-    const T s0 = nt + nk + nh;
-    const T s1 = w.f[0] * nt + w.f[1] * nk + w.f[2] * nh;
-    const T s2 = w.g[0] * nt + w.g[1] * nk + w.g[2] * nh;
-    return vol + m + plog(s1 * s2 / s0);
+    const T nt = pexp(lt - lh), nk = pexp(lk - lh);
+    const T s0 = nt + nk + T(1);
+    const T s1 = w.f[0] * nt + w.f[1] * nk + w.f[2];
+    const T s2 = w.g[0] * nt + w.g[1] * nk + w.g[2];
+    return lh + plog(s1 * s2 * prcp(s0 * s));
 }
 
 // ---- parameters shared by the posterior kernels ------------------------------------------------------------
@@ -183,7 +195,7 @@ template <typename T> __global__ void __launch_bounds__(kTile) k_post_mle(const 
         ModelW<T> w;
         model_weights<T>(p.G, p.feh, p.loga, i, w);
         const T scale = p.rows[p.ld + t];
-        lp = p.rows[t] + (p.lnprior ? p.lnprior[i] : T(0)) + gal_lnprior<T>(p.G, p.gstar[slot], w, T(1) / psqrt(scale));
+        lp = p.rows[t] + (p.lnprior ? p.lnprior[i] : T(0)) + gal_lnprior<T>(p.G, p.gstar[slot], w, scale, prsqrt(scale));
         p.lnp1[t] = lp;
     }
     cta_star_max<T>(p.red, RED_P1, slot, in, lp);
@@ -288,10 +300,10 @@ template <typename T> struct McCtx {
     uint64_t star;
 };
 
-template <typename T>
+template <typename T, bool ZOV>
 __device__ __forceinline__ void mc_draw(const PostParams<T>& p, const McCtx<T>& c, int j, T& s, T& a, T& r, T& lp, bool& inb) {
     T z[3];
-    if (p.zov) {
+    if (ZOV) {
         const double* zz = p.zov + (size_t)c.model * 3 * p.nmc + j;
         z[0] = (T)zz[0]; z[1] = (T)zz[p.nmc]; z[2] = (T)zz[2 * p.nmc];
     } else {
@@ -303,8 +315,8 @@ __device__ __forceinline__ void mc_draw(const PostParams<T>& p, const McCtx<T>& 
     inb = s >= T(1e-20) && a >= p.avmin && a <= p.avmax && r >= p.rvmin && r <= p.rvmax;   // (:1090-1092)
     lp = Num<T>::kNegBig;
     if (inb) {
-        const T par = psqrt(s);
-        lp = gal_lnprior<T>(p.G, c.gs, c.w, T(1) / par);
+        const T dist = prsqrt(s), par = s * dist;
+        lp = gal_lnprior<T>(p.G, c.gs, c.w, s, dist);
         if (c.pivar > T(0)) {
             const T d = par - c.par;
             lp += T(-0.5) * (d * d * c.pivar + c.lnorm_par);
@@ -345,8 +357,8 @@ template <typename T> struct Lse {
     __device__ T value() const { return s > T(0) ? m + plog(s) : Num<T>::neg_inf(); }
 };
 
-// (:1038-1106) one thread per model of the second selection
-template <typename T> __global__ void __launch_bounds__(kTile) k_post_mc(const PostParams<T> p) {
+// (:1038-1106) one thread per model of the second selection.  ZOV: normals supplied by the host (test mode)
+template <typename T, bool ZOV> __global__ void __launch_bounds__(kTile) k_post_mc(const PostParams<T> p) {
     const int64_t u = (int64_t)blockIdx.x * kTile + threadIdx.x;
     const bool in = u < p.n2;
     int slot = -1;
@@ -361,7 +373,7 @@ template <typename T> __global__ void __launch_bounds__(kTile) k_post_mc(const P
         int neff = 0;
         for (int j = 0; j < p.nmc; j++) {
             T s, a, r, lp; bool inb;
-            mc_draw<T>(p, c, j, s, a, r, lp, inb);
+            mc_draw<T, ZOV>(p, c, j, s, a, r, lp, inb);
             acc.add(lp);
             neff += inb ? 1 : 0;
         }
@@ -430,7 +442,7 @@ template <typename T> __global__ void __launch_bounds__(1024) k_post_cdf(const P
 }
 
 // one CTA per star, one thread per posterior draw (:2040-2061)
-template <typename T> __global__ void k_post_draw(const PostParams<T> p) {
+template <typename T, bool ZOV> __global__ void k_post_draw(const PostParams<T> p) {
     const int slot = p.g0 + blockIdx.x;
     const int64_t lo = p.off2[slot], hi = p.off2[slot + 1];
     for (int d = threadIdx.x; d < p.ndraws; d += blockDim.x) {
@@ -443,8 +455,8 @@ template <typename T> __global__ void k_post_draw(const PostParams<T> p) {
     } else {
         uint32_t r[4];
         const uint64_t star = (uint64_t)(p.star_base + slot);
-        philox4x32_10((uint32_t)d, 0x44524157u, (uint32_t)star, (uint32_t)(star >> 32) ^ 0x52455331u, (uint32_t)p.seed,
-                      (uint32_t)(p.seed >> 32), r);
+        philox4x32<10>((uint32_t)d, 0x44524157u, (uint32_t)star, (uint32_t)(star >> 32) ^ 0x52455331u, (uint32_t)p.seed,
+                       (uint32_t)(p.seed >> 32), r);
         u1 = u01d(r[0], r[1]);
         u2 = u01d(r[2], r[3]);
     }
@@ -474,7 +486,7 @@ template <typename T> __global__ void k_post_draw(const PostParams<T> p) {
     Lse<T> acc;
     for (int j = 0; j < p.nmc; j++) {
         T s, av, rv, lp; bool inb;
-        mc_draw<T>(p, c, j, s, av, rv, lp, inb);
+        mc_draw<T, ZOV>(p, c, j, s, av, rv, lp, inb);
         acc.add(lp);
     }
     const T m = acc.m;
@@ -484,7 +496,7 @@ template <typename T> __global__ void k_post_draw(const PostParams<T> p) {
     T ps = c.scale, pa = c.av, pr = c.rv, pl = Num<T>::neg_inf();
     for (int j = 0; j < p.nmc && pick < 0; j++) {
         T s, av, rv, lp; bool inb;
-        mc_draw<T>(p, c, j, s, av, rv, lp, inb);
+        mc_draw<T, ZOV>(p, c, j, s, av, rv, lp, inb);
         // all draws at -inf: exp(-inf - -inf) is NaN in the reference too; fall through to the last draw
         if (lp > Num<T>::neg_inf()) run += (double)pexp(lp - m);
         if ((W > 0. && run / W > u2) || j == p.nmc - 1) { pick = j; ps = s; pa = av; pr = rv; pl = lp; }
