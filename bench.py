@@ -214,6 +214,8 @@ def run_b200(args):
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     h = _lib.Handle(local_rank, args.precision)
     # ---- stage the grid: rank 0 builds it; one NCCL broadcast; device-side re-tiling ----
