@@ -221,9 +221,11 @@ __device__ __forceinline__ void lnl_lnprob(T chi2, T sden, T scale, bool surv, c
     lnl += ext;
     lp = lnl;
     if (srow[SR_SC + SC_SPAPPLY] != T(0)) {
-        T svar = srow[SR_SC + SC_SVAR] + Num<T>::div(T(1), tabs(sden));
+        // approximate reciprocals (float: MUFU.RCP, 1-2 ulp): this term only enters lnprob, i.e. the selection
+        // threshold and max_lnprob, never the reported lnl / chi2
+        T svar = srow[SR_SC + SC_SVAR] + Num<T>::div_fast(T(1), tabs(sden));
         T d = scale - srow[SR_SC + SC_SMEAN];
-        lp = lnl + T(-0.5) * (Num<T>::div(d * d, svar) + Num<T>::log(T(6.283185307179586) * svar));
+        lp = lnl + T(-0.5) * (Num<T>::div_fast(d * d, svar) + Num<T>::log(T(6.283185307179586) * svar));
     }
     if (!Num<T>::finite(lp)) lp = Num<T>::kNegBig;
 }
