@@ -20,7 +20,8 @@ MAX_FILT = 16
 SYMBOLS = ("bf_default_options", "bf_create", "bf_destroy", "bf_last_error", "bf_set_grid",
            "bf_set_grid_device", "bf_set_labels", "bf_loglike_full", "bf_sweep_batch",
            "bf_get_stats", "bf_flush_l2", "bf_device_count", "bf_version",
-           "bf_default_gal_params", "bf_default_post_options", "bf_set_model_priors", "bf_fit_batch")
+           "bf_default_gal_params", "bf_default_post_options", "bf_set_model_priors", "bf_fit_batch",
+           "bf_get_seds")
 
 
 class BrutusCudaError(RuntimeError):
@@ -117,6 +118,7 @@ def load():
     lib.bf_set_model_priors.argtypes = [vp, dp, dp, dp]
     lib.bf_fit_batch.argtypes = [vp, C.c_int64, dp, dp, u8p, dp, dp, dp, dp, dp, op,
                                  C.POINTER(PostOptions), i32p, i32p, i64p, dp, dp, C.POINTER(Draws)]
+    lib.bf_get_seds.argtypes = [vp, C.c_int64, i32p, dp, dp, C.c_int32, dp, dp, dp]
     lib.bf_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.bf_flush_l2.argtypes = [vp]
     lib.bf_device_count.restype = C.c_int
@@ -287,6 +289,23 @@ class Handle:
             out[name] = mat[k]
         out["icov6"] = mat[5:11] if rec.nrows >= 11 else None
         return out
+
+    def get_seds(self, av, rv, idx=None, return_flux=False, want_rvec=True, want_drvec=True):
+        """``_get_seds`` (brutus/utils.py:286-347) on the staged grid for the models ``idx`` (default: every
+        model, in order).  Returns ``(seds, rvecs, drvecs)``, float64 ``(n, Nfilt)`` (None where not wanted)."""
+        a = np.ascontiguousarray(av, dtype=np.float64)
+        r = np.ascontiguousarray(rv, dtype=np.float64)
+        ix = None if idx is None else np.ascontiguousarray(idx, dtype=np.int32)
+        n = a.shape[0]
+        if a.ndim != 1 or r.shape != a.shape or (ix is not None and ix.shape != a.shape):
+            raise ValueError("av, rv (and idx) must be 1-D arrays of the same length")
+        seds = np.empty((n, self.nfilt))
+        rvecs = np.empty((n, self.nfilt)) if want_rvec else None
+        drvecs = np.empty((n, self.nfilt)) if want_drvec else None
+        self._check(self._lib.bf_get_seds(self._h, n, _ptr(ix, C.c_int32), _ptr(a, C.c_double), _ptr(r, C.c_double),
+                                          int(bool(return_flux)), _ptr(seds, C.c_double),
+                                          _ptr(rvecs, C.c_double), _ptr(drvecs, C.c_double)))
+        return seds, rvecs, drvecs
 
     def set_model_priors(self, lnprior=None, feh=None, loga=None):
         """Stage the static inputs of lnpost: the `lnprior` grid (brutus/fitting.py:1004) and the label

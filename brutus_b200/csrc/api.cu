@@ -63,6 +63,30 @@ template <typename T> __global__ void k_convert_labels(const double* src, T* dst
     for (int l = 0; l < nlabel; l++) dst[(int64_t)l * npad + i] = i < nmodel ? (T)src[(int64_t)l * nmodel + i] : T(0);
 }
 
+// get_seds / _get_seds (brutus/utils.py:286-347) for n (model, Av, Rv) samples; one thread per (sample, band)
+template <typename T>
+__global__ void k_get_seds(const float* __restrict__ rows, int rs, int nfilt, int64_t n, const int* __restrict__ idx,
+                           const double* __restrict__ av, const double* __restrict__ rv, int flux,
+                           double* __restrict__ seds, double* __restrict__ rvecs, double* __restrict__ drvecs) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * nfilt) return;
+    const int64_t i = t / nfilt;
+    const int j = (int)(t - i * nfilt);
+    const float* __restrict__ row = rows + (int64_t)(idx ? idx[i] : i) * rs;
+    const T mag0 = (T)row[j], r0 = (T)row[nfilt + j], dr = (T)row[2 * nfilt + j];
+    T dv = dr;                                   // :336
+    T rvec = r0 + (T)rv[i] * dr;                 // :337
+    T sed = mag0 + (T)av[i] * rvec;              // :338
+    if (flux) {                                  // :341-345
+        sed = Num<T>::exp2(T(-kC2) * sed);
+        rvec *= T(kFac) * sed;
+        dv *= T(kFac) * sed;
+    }
+    seds[t] = (double)sed;
+    if (rvecs) rvecs[t] = (double)rvec;
+    if (drvecs) drvecs[t] = (double)dv;
+}
+
 template <typename T>
 __global__ void k_reset_red(typename Enc<T>::U* red, const int* list, int nlist, unsigned mask) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -299,6 +323,8 @@ struct EngineBase {
                             int32_t* n_iter, int64_t* n_surv, double* max_lnprob, int64_t* offsets,
                             bf_records* out) = 0;
     virtual int set_model_priors(const double* lnprior, const double* feh, const double* loga) = 0;
+    virtual int get_seds(int64_t n, const int32_t* idx, const double* av, const double* rv, int flux, double* seds,
+                         double* rvecs, double* drvecs) = 0;
     virtual int fit_batch(int64_t nstar, const double* flux, const double* errv, const uint8_t* mask,
                           const double* par, const double* perr, const double* coords, const double* ext_mean,
                           const double* ext_std, const bf_options* opt, const bf_post_options* po, int32_t* ndim,
@@ -1128,6 +1154,44 @@ template <typename T> struct Engine : EngineBase {
         return BF_OK;
     }
 
+    // ---- get_seds on the staged grid (bf_get_seds) ----
+    int get_seds(int64_t n, const int32_t* idx, const double* av, const double* rv, int flux, double* seds,
+                 double* rvecs, double* drvecs) override {
+        CK(cudaSetDevice(device));
+        if (!kt) { err = "bf_get_seds: no grid (call bf_set_grid)"; return BF_E_NOGRID; }
+        if (n < 0 || (n > 0 && (!av || !rv || !seds))) { err = "bf_get_seds: null argument"; return BF_E_INVALID; }
+        if (!idx && n != nmodel) { err = "bf_get_seds: without idx, n must equal nmodel"; return BF_E_INVALID; }
+        if (n == 0) return BF_OK;
+        if (idx)
+            for (int64_t i = 0; i < n; i++)
+                if (idx[i] < 0 || idx[i] >= nmodel) { err = "bf_get_seds: model index out of range"; return BF_E_INVALID; }
+        const int nout = 1 + (rvecs ? 1 : 0) + (drvecs ? 1 : 0);
+        DevBuf<double> d_in, d_o;
+        DevBuf<int> d_ix;
+        CK(d_in.ensure((size_t)2 * n));
+        CK(d_o.ensure((size_t)nout * n * nfilt));
+        CK(cudaMemcpyAsync(d_in.p, av, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_in.p + n, rv, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        if (idx) {
+            CK(d_ix.ensure((size_t)n));
+            CK(cudaMemcpyAsync(d_ix.p, idx, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, stream));
+        }
+        double* o_s = d_o.p;
+        double* o_r = rvecs ? d_o.p + (size_t)n * nfilt : nullptr;
+        double* o_d = drvecs ? d_o.p + (size_t)(nout - 1) * n * nfilt : nullptr;
+        const int64_t tot = n * nfilt;
+        k_get_seds<T><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(d_rows.p, rs, nfilt, n, idx ? d_ix.p : nullptr, d_in.p,
+                                                                       d_in.p + n, flux, o_s, o_r, o_d);
+        CK(cudaGetLastError());
+        stats.kernel_launches++;
+        CK(cudaMemcpyAsync(seds, o_s, (size_t)tot * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        if (rvecs) CK(cudaMemcpyAsync(rvecs, o_r, (size_t)tot * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        if (drvecs) CK(cudaMemcpyAsync(drvecs, o_d, (size_t)tot * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        d_in.release(); d_o.release(); d_ix.release();
+        return BF_OK;
+    }
+
     // ---- static per-model priors / labels of lnpost (bf_set_model_priors) ----
     int set_model_priors(const double* lnprior, const double* feh, const double* loga) override {
         CK(cudaSetDevice(device));
@@ -1448,6 +1512,12 @@ int bf_fit_batch(bf_handle* h, int64_t nstar, const double* flux, const double* 
     if (!h) return BF_E_INVALID;
     return h->eng->fit_batch(nstar, flux, err, mask, parallax, parallax_err, coords, ext_mean, ext_std, opt, post,
                              ndim, n_iter, nsel, levid, chi2min, out);
+}
+
+int bf_get_seds(bf_handle* h, int64_t n, const int32_t* idx, const double* av, const double* rv, int32_t return_flux,
+                double* seds, double* rvecs, double* drvecs) {
+    if (!h) return BF_E_INVALID;
+    return h->eng->get_seds(n, idx, av, rv, return_flux, seds, rvecs, drvecs);
 }
 
 int bf_flush_l2(bf_handle* h) {

@@ -208,6 +208,16 @@ int bf_fit_batch(bf_handle* h, int64_t nstar, const double* flux, const double* 
                  const bf_post_options* post, int32_t* ndim, int32_t* n_iter, int64_t* nsel,
                  double* levid, double* chi2min, bf_draws* out);
 
+/* Reddened SEDs of (model, Av, Rv) samples from the staged grid -- get_seds / _get_seds
+ * (brutus/utils.py:1089-1159, :286-347), the grid-touching part of photometric_offsets (:1268-1271).
+ *   n       number of samples
+ *   idx     [n] model index of each sample, or NULL for the identity (n == nmodel: the whole grid)
+ *   av, rv  [n] float64
+ *   return_flux  0: magnitudes; 1: flux densities 10^(-0.4 m), reddening vectors scaled by -0.4 ln10 F
+ * outputs (caller-allocated float64, [n*nfilt], C order; rvecs / drvecs may be NULL). */
+int bf_get_seds(bf_handle* h, int64_t n, const int32_t* idx, const double* av, const double* rv,
+                int32_t return_flux, double* seds, double* rvecs, double* drvecs);
+
 /* Statistics of the most recent bf_loglike_full / bf_sweep_batch / bf_fit_batch call on this handle. */
 int bf_get_stats(const bf_handle* h, bf_stats* out);
 

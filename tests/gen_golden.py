@@ -137,12 +137,69 @@ def gen_galprior(fit):
     print("wrote galprior")
 
 
+OFFSETS_CASE = dict(grid=dict(nmodel=3_000, nfilt=8, seed=1040), nobj=40, nsamps=25, Nmc=30, seed=4040, rseed=123)
+
+
+def build_offsets_case():
+    """Inputs of the photometric_offsets / get_seds golden case (regenerated from seeds by the tests)."""
+    c = OFFSETS_CASE
+    grid, labels = mock.make_grid(**c["grid"])
+    rs = np.random.RandomState(c["seed"])
+    nobj, nsamps, nfilt = c["nobj"], c["nsamps"], grid.shape[1]
+    idxs = rs.randint(0, grid.shape[0], (nobj, nsamps))
+    reds = rs.uniform(0., 2., (nobj, nsamps))
+    dreds = rs.normal(3.3, 0.2, (nobj, nsamps))
+    dists = 10. ** rs.uniform(-0.5, 0.5, (nobj, nsamps))
+    # photometry: the first sample's SED, offset per band, plus noise
+    co = grid[idxs[:, 0]].astype(np.float64)
+    mag = co[:, :, 0] + reds[:, :1] * (co[:, :, 1] + dreds[:, :1] * co[:, :, 2])
+    true_off = 1. + 0.05 * np.linspace(-1., 1., nfilt)
+    phot = 10. ** (-0.4 * mag) / dists[:, :1] ** 2 / true_off[None, :]
+    err = 0.03 * phot
+    phot = phot + rs.normal(size=phot.shape) * err
+    mask = rs.uniform(size=phot.shape) > 0.15
+    mask[:, 0] |= mask.sum(axis=1) < 5
+    weights = rs.uniform(0.2, 1., (nobj, nsamps))
+    weights[3] = 0.
+    sel = rs.uniform(size=nobj) > 0.1
+    mask_fit = np.ones(nfilt, dtype=bool)
+    mask_fit[-1] = False
+    old = 1. + 0.01 * rs.normal(size=nfilt)
+    return dict(grid=grid, phot=phot, err=err, mask=mask, idxs=idxs, reds=reds, dreds=dreds, dists=dists,
+                sel=sel, weights=weights, mask_fit=mask_fit, old_offsets=old)
+
+
+def gen_offsets(fit):
+    """Golden outputs of the reference's get_seds and photometric_offsets (brutus/utils.py:1089-1400)."""
+    from brutus import utils as rutils  # the reference module
+    c = build_offsets_case()
+    out = {}
+    n = 200
+    rs = np.random.RandomState(5)
+    av, rv = rs.uniform(0., 3., n), rs.normal(3.3, 0.3, n)
+    for flux in (False, True):
+        s, r, d = rutils.get_seds(c["grid"][:n], av=av, rv=rv, return_flux=flux, return_rvec=True, return_drvec=True)
+        out["seds_%d" % flux], out["rvecs_%d" % flux], out["drvecs_%d" % flux] = s, r, d
+    out["seds_default"] = rutils.get_seds(c["grid"][:n])
+    out["av"], out["rv"] = av, rv
+    for name, kw in (("plain", {}), ("prior", dict(prior_mean=np.ones(8), prior_std=np.full(8, 0.02), dim_prior=False))):
+        r = rutils.photometric_offsets(c["phot"], c["err"], c["mask"], c["grid"], c["idxs"], c["reds"], c["dreds"],
+                                       c["dists"], sel=c["sel"], weights=c["weights"], mask_fit=c["mask_fit"],
+                                       Nmc=OFFSETS_CASE["Nmc"], old_offsets=c["old_offsets"], verbose=False,
+                                       rstate=np.random.RandomState(OFFSETS_CASE["rseed"]), **kw)
+        out["ratios_" + name], out["ratios_err_" + name], out["nratio_" + name] = r
+    np.savez_compressed(os.path.join(GOLD, "offsets.npz"), **out)
+    print("wrote offsets")
+
+
 if __name__ == "__main__":
     fit = ref_import.import_reference()
     os.makedirs(GOLD, exist_ok=True)
-    only = [a for a in sys.argv[1:] if a in LOGLIKE_CASES or a == "galprior"]
+    only = [a for a in sys.argv[1:] if a in LOGLIKE_CASES or a in ("galprior", "offsets")]
     gen_loglike(fit, only=only)
     if not only:
         gen_fit(fit)
     if not only or "galprior" in sys.argv[1:]:
         gen_galprior(fit)
+    if not only or "offsets" in sys.argv[1:]:
+        gen_offsets(fit)
