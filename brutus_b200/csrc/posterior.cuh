@@ -35,8 +35,9 @@ __device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// uniform in (0, 1) from 32 random bits (24 bits used: exact in float)
-__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 5.9604645e-8f + 2.9802322e-8f; }
+// uniform in (0, 1) from 32 random bits: the top 23 bits become the mantissa of a float in [1, 2) (no
+// int->float conversion, which would occupy the transcendental pipe the Monte Carlo loop is short of)
+__device__ __forceinline__ float u01(uint32_t x) { return __uint_as_float(0x3f800000u | (x >> 9)) - 0.99999994f; }
 // uniform in [0, 1) with 53 bits
 __device__ __forceinline__ double u01d(uint32_t a, uint32_t b) {
     return (double)((((uint64_t)a << 32) | b) >> 11) * (1.0 / 9007199254740992.0);
