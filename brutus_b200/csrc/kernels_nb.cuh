@@ -477,7 +477,8 @@ __global__ void __launch_bounds__(kTile) k_magfit(const SweepParams<T> p) {
 // (stepsize 1, lnl_old = -1e300, :778-779).
 // =================================================================================================
 template <typename T, int NB>
-__global__ void __launch_bounds__(kTile) k_refit(const RefitParams<T> p) {
+// 64 registers -> 4 CTAs per SM: the kernel waits on gathers (ncu: long_scoreboard 6.7 per issue), occupancy helps
+__global__ void __launch_bounds__(kTile, 4) k_refit(const RefitParams<T> p) {
     constexpr int NP = (NB + 1) / 2;
     const int64_t q = (int64_t)blockIdx.x * kTile + threadIdx.x;
     const bool inr = q < p.ncand;
@@ -560,7 +561,8 @@ __device__ __forceinline__ void resid_at(const ModelRegs<T, NB>& m, const DevOpt
 // Stars whose loop has converged (SI_ACTIVE == 0, decided on the device by k_flux_ctl) are skipped.
 // =================================================================================================
 template <typename T, int NB>
-__global__ void __launch_bounds__(kTile) k_flux(const FluxParams<T> p) {
+// 80 registers -> 3 CTAs per SM (2 at the natural 90); 4 CTAs would spill and measured slower
+__global__ void __launch_bounds__(kTile, 3) k_flux(const FluxParams<T> p) {
     constexpr int NP = (NB + 1) / 2;
     const int64_t t = (int64_t)blockIdx.x * kTile + threadIdx.x;
     const bool inrange = t < p.nsv;
