@@ -192,10 +192,100 @@ def gen_offsets(fit):
     print("wrote offsets")
 
 
+NGC2682_FITS = os.path.join(ref_import.REFERENCE_ROOT, "demos", "NGC_2682.fits")
+NGC2682_GRID = dict(nmodel=4_000, nfilt=8, seed=1050, kind="locus")
+
+
+def read_fits_bintable(path):
+    """Minimal reader of a FITS binary-table extension (no astropy here): header cards -> big-endian NumPy
+    structured dtype."""
+    import re
+    raw = open(path, "rb").read()
+
+    def header(off):
+        cards = {}
+        while True:
+            blk = raw[off:off + 2880]
+            off += 2880
+            for i in range(36):
+                c = blk[i * 80:(i + 1) * 80].decode("ascii")
+                if c[:8].strip() == "END":
+                    return cards, off
+                if c[8:10] == "= ":
+                    v = c[10:].split("/")[0].strip()
+                    cards[c[:8].strip()] = v.strip("'").strip() if v.startswith("'") else v
+
+    _, off = header(0)
+    h, off = header(off)
+    code = {"L": "i1", "B": "u1", "I": ">i2", "J": ">i4", "K": ">i8", "E": ">f4", "D": ">f8"}
+    fields = []
+    for i in range(1, int(h["TFIELDS"]) + 1):
+        m = re.match(r"(\d*)([ALBIJKED])", h["TFORM%d" % i])
+        rep, c = int(m.group(1) or 1), m.group(2)
+        if c == "A":
+            fields.append((h["TTYPE%d" % i], "S%d" % rep))
+        elif rep == 1:
+            fields.append((h["TTYPE%d" % i], code[c]))
+        else:
+            fields.append((h["TTYPE%d" % i], code[c], (rep,)))
+    dt = np.dtype(fields)
+    assert dt.itemsize == int(h["NAXIS1"])
+    return np.frombuffer(raw, dtype=dt, count=int(h["NAXIS2"]), offset=off)
+
+
+def ngc2682_grid():
+    """Mock grid for the NGC 2682 catalogue: the locus mock with magnitudes placed at 1 kpc (+10 mag), so that
+    scale = parallax^2 holds for real parallaxes (the real Bayestar grid cannot be fetched offline)."""
+    grid, labels = mock.make_grid(**NGC2682_GRID)
+    grid[:, :, 0] += 10.
+    return grid, labels
+
+
+def gen_ngc2682(fit):
+    """The 8 bands of demos/NGC_2682.fits that the Bayestar grid covers (PS grizy + 2MASS JHKs), assembled as in
+    demos/Overview 5 cell 13: PS fluxes in maggies, 2MASS magnitudes -> maggies, 2 % / 3 %
+    systematic floors, parallax zero-point +0.054 mas and 0.043 mas floor.  Stored with the reference's loglike
+    outputs for three of its stars against the mock grid."""
+    t = read_fits_bintable(NGC2682_FITS)
+    n = len(t)
+    phot = np.full((n, 8), np.nan)
+    err = np.full((n, 8), np.nan)
+    phot[:, :5] = t["ucal_fluxqz.median"]
+    err[:, :5] = t["ucal_fluxqz.err"]
+    for k, b in enumerate(("J", "H", "Ks")):
+        m, me = t["2MASS_%s" % b].astype(float), t["2MASS_%s_Err" % b].astype(float)
+        f = 10. ** (-0.4 * m)
+        phot[:, 5 + k], err[:, 5 + k] = f, 0.4 * np.log(10.) * f * me
+    floor = np.array([0.02] * 5 + [0.03] * 3)
+    with np.errstate(all="ignore"):
+        err = np.sqrt(err ** 2 + (floor[None, :] * phot) ** 2)
+        mask = np.isfinite(phot) & np.isfinite(err) & (err > 0.) & (phot > 0.) & (err / phot < 0.5)
+    par = t["Parallax"].astype(float) + 0.054
+    perr = np.sqrt(t["Parallax_Err"].astype(float) ** 2 + 0.043 ** 2)
+    coords = np.stack([t["l"].astype(float), t["b"].astype(float)], axis=1)
+    out = dict(phot=phot, err=err, mask=mask, parallax=par, parallax_err=perr, coords=coords,
+               memprob=t["HDBscan_MemProb"].astype(float))
+    grid, _ = ngc2682_grid()
+    gF = np.array(grid, order="F")
+    nb = mask.sum(axis=1)
+    picks = [int(np.where(nb == 8)[0][0]), int(np.where((nb >= 4) & (nb < 8))[0][0]),
+             int(np.where((nb >= 5) & ~np.isfinite(par))[0][0]) if np.any((nb >= 5) & ~np.isfinite(par))
+             else int(np.where(nb == 8)[0][7])]
+    out["picks"] = np.array(picks)
+    for i in picks:
+        m = mask[i].copy()
+        r = fit.loglike(phot[i], err[i], m, gF, return_vals=True, parallax=par[i], parallax_err=perr[i])
+        for key, val in zip(("lnl", "ndim", "chi2", "scale", "av", "rv", "icov"), r):
+            out["%s_%d" % (key, i)] = np.asarray(val)
+        out["mask_%d" % i] = m
+    np.savez_compressed(os.path.join(GOLD, "ngc2682.npz"), **out)
+    print("wrote ngc2682: %d objects, bands-per-object %s, picks %s" % (n, np.bincount(nb).tolist(), picks))
+
+
 if __name__ == "__main__":
     fit = ref_import.import_reference()
     os.makedirs(GOLD, exist_ok=True)
-    only = [a for a in sys.argv[1:] if a in LOGLIKE_CASES or a in ("galprior", "offsets")]
+    only = [a for a in sys.argv[1:] if a in LOGLIKE_CASES or a in ("galprior", "offsets", "ngc2682")]
     gen_loglike(fit, only=only)
     if not only:
         gen_fit(fit)
@@ -203,3 +293,5 @@ if __name__ == "__main__":
         gen_galprior(fit)
     if not only or "offsets" in sys.argv[1:]:
         gen_offsets(fit)
+    if (not only or "ngc2682" in sys.argv[1:]) and os.path.exists(NGC2682_FITS):
+        gen_ngc2682(fit)

@@ -1,0 +1,128 @@
+"""Real photometry through the path: the NGC 2682 (M67) demo catalogue of the reference (BASELINE.json configs[3];
+demos/NGC_2682.fits, 1 585 objects, here the 8 bands the Bayestar grid covers), with ragged band coverage, NaNs,
+missing parallaxes and real Galactic coordinates.  The fixture tests/golden/ngc2682.npz holds the assembled
+catalogue and the unmodified reference's `loglike` outputs for three of its stars against a mock grid
+(tests/gen_golden.py::gen_ngc2682; the real Bayestar grid cannot be fetched offline).
+
+CPU part: the oracle against those golden outputs.  GPU part: the CUDA path against golden + oracle, the whole
+catalogue through bf_sweep_batch / bf_fit_batch, and the reference's ValueError for objects with < 4 bands."""
+import os
+
+import numpy as np
+import pytest
+
+import gen_golden
+import golden_cases as gc
+
+
+@pytest.fixture(scope="module")
+def cat():
+    d = np.load(os.path.join(gc.GOLD, "ngc2682.npz"))
+    grid, labels = gen_golden.ngc2682_grid()
+    return d, grid, labels
+
+
+def _ref(d, i):
+    return tuple(d["%s_%d" % (k, i)] if k != "ndim" else int(d["ndim_%d" % i]) for k in gc.KEYS)
+
+
+def test_oracle_matches_reference_on_real_photometry(cat, oracle_mod):
+    d, grid, _ = cat
+    for i in d["picks"]:
+        m = d["mask"][i].copy()
+        out = oracle_mod.loglike(d["phot"][i], d["err"][i], m, grid, return_vals=True,
+                                 parallax=d["parallax"][i], parallax_err=d["parallax_err"][i])
+        assert np.array_equal(m, d["mask_%d" % i])
+        for key, a, b in zip(gc.KEYS, out, _ref(d, i)):
+            if key == "ndim":
+                assert a == b
+            else:
+                assert gc.rel_err(a, b) < 1e-9, (int(i), key)
+
+
+@pytest.mark.gpu
+def test_loglike_f64_matches_reference(cat):
+    from brutus_b200 import fitting
+    d, grid, _ = cat
+    try:
+        for i in d["picks"]:
+            m = d["mask"][i].copy()
+            out = fitting.loglike(d["phot"][i], d["err"][i], m, grid, return_vals=True, precision="f64",
+                                  parallax=d["parallax"][i], parallax_err=d["parallax_err"][i])
+            assert np.array_equal(m, d["mask_%d" % i])
+            for key, a, b in zip(gc.KEYS, out, _ref(d, i)):
+                if key == "ndim":
+                    assert a == b
+                else:
+                    assert gc.rel_err(a, b) < 1e-8, (int(i), key)
+    finally:
+        fitting.release_handles()
+
+
+@pytest.mark.gpu
+def test_whole_catalogue_sweep_and_fit(cat, oracle_mod):
+    from brutus_b200 import _lib, fitting
+    d, grid, labels = cat
+    ok = d["mask"].sum(axis=1) >= 4                      # brutus/fitting.py:1413-1420
+    assert (~ok).sum() == 68
+    idx = np.where(ok)[0]
+    phot, err, mask = d["phot"][idx], d["err"][idx], d["mask"][idx]
+    par, perr, coords = d["parallax"][idx], d["parallax_err"][idx], d["coords"][idx]
+    h = _lib.Handle(0, "f32")
+    try:
+        h.set_grid(grid)
+        res = h.sweep_batch(phot, err, mask, par, perr, copy=True)
+        assert np.all(np.diff(res["offsets"]) > 0)
+        assert np.array_equal(res["ndim"], mask.sum(axis=1))
+        rs = np.random.RandomState(4)
+        for j in rs.choice(len(idx), 12, replace=False):
+            pk = dict(parallax=par[j], parallax_err=perr[j])
+            ref = oracle_mod.loglike(phot[j], err[j], mask[j].copy(), grid, return_vals=True, return_diag=True, **pk)
+            _, lnprob, sel = oracle_mod.select(ref[0], ref[3], ref[6], **pk)
+            lo, hi = res["offsets"][j], res["offsets"][j + 1]
+            got = res["model_idx"][lo:hi]
+            common, ia, ib = np.intersect1d(got, sel, return_indices=True)
+            assert len(common) >= 0.98 * len(sel) - 1 and len(got) <= 1.02 * len(sel) + 2, (int(j), len(got), len(sel))
+            assert tuple(res["n_iter"][j]) == (ref[7]["n_iter_mag"], ref[7]["n_iter_flux"]), int(j)
+            assert np.max(np.abs(res["chi2"][lo:hi][ia] - ref[2][common])) < 5e-3 + 5e-5 * np.max(ref[2][common])
+            assert np.max(np.abs(res["av"][lo:hi][ia] - ref[4][common])) < 5e-4
+            assert abs(res["max_lnprob"][j] - lnprob[sel].max()) < 5e-3
+        # the device posterior on real coordinates / parallaxes
+        h.set_model_priors(lnprior=fitting.imf_lnprior(labels["mini"]), feh=labels["feh"], loga=labels["loga"])
+        fit = h.fit_batch(phot, err, mask, par, perr, coords=coords, nmc_prior=20, ndraws=50, seed=1)
+        assert np.all(fit["levid"] > -1e299) and np.all(fit["sidxs"] >= 0)
+        assert np.all(np.isfinite(fit["dists"])) and np.all(fit["dists"] > 0)
+        assert np.array_equal(fit["ndim"], mask.sum(axis=1) + (np.isfinite(par) & np.isfinite(perr)))
+        # ... and against the host posterior (NumPy lnpost with the restated Galactic prior and NumPy's generator)
+        # on a few stars: the evidence agrees within the Monte Carlo error, the distance posteriors overlap
+        from oracle import galprior as gp
+        lmask = np.ones(1, dtype=[(n, bool) for n in labels.dtype.names])
+        bf = fitting.BruteForce(grid, labels, lmask)
+        pick = rs.choice(len(idx), 5, replace=False)
+        try:
+            kw = dict(parallax=par[pick], parallax_err=perr[pick], Nmc_prior=200, Ndraws=300, dustfile=None,
+                      lnprior=fitting.imf_lnprior(labels["mini"]), data_coords=coords[pick])
+            dev = list(bf._fit(phot[pick], err[pick], mask[pick], rstate=np.random.RandomState(2), **kw))
+            host = list(bf._fit(phot[pick], err[pick], mask[pick], rstate=np.random.RandomState(3),
+                                lngalprior=lambda dd, c, labels=None: gp.gal_lnprior(dd, c, labels=labels), **kw))
+        finally:
+            bf.close()
+        for a, b in zip(dev, host):
+            assert abs(a[7] - b[7]) < 0.1, ("levid", a[7], b[7])
+            assert a[5] == b[5] and abs(a[8] - b[8]) < 5e-3 + 5e-5 * abs(b[8])
+            sd = np.std(np.log(b[9])) / np.sqrt(300.) * 5. + 0.02
+            assert abs(np.mean(np.log(a[9])) - np.mean(np.log(b[9]))) < sd, "dist"
+    finally:
+        h.close()
+
+
+@pytest.mark.gpu
+def test_fit_rejects_objects_with_fewer_than_4_bands(cat, tmp_path):
+    from brutus_b200 import fitting
+    d, grid, labels = cat
+    lmask = np.ones(1, dtype=[(n, bool) for n in labels.dtype.names])
+    bf = fitting.BruteForce(grid, labels, lmask)
+    with pytest.raises(ValueError):
+        bf.fit(d["phot"], d["err"], d["mask"], np.arange(len(d["phot"])), str(tmp_path / "x"),
+               parallax=d["parallax"], parallax_err=d["parallax_err"], data_coords=d["coords"], dustfile=None,
+               verbose=False)
