@@ -372,7 +372,7 @@ class BruteForce(object):
              lnprior_ext=None, wt_thresh=1e-3, cdf_thresh=2e-3, Ndraws=250, lngalprior=None,
              lndustprior=None, dustfile=None, apply_dlabels=True, data_coords=None,
              return_distreds=True, logl_dim_prior=True, ltol=3e-2, ltol_subthresh=1e-2,
-             logl_initthresh=5e-3, mem_lim=8000., rstate=None, batch=256):
+             logl_initthresh=5e-3, mem_lim=8000., rstate=None, batch=1024):
         """Generator with the reference's contract (brutus/fitting.py:1803-2061): yields, per object,
         ``(sidxs, scales, avs, rvs, cov_sar, Ndim, lnprob, levid, chi2min[, dists, reds, dreds,
         logwts])``.  Stars go to the GPU ``batch`` at a time; the prior integration and resampling
