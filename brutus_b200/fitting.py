@@ -372,7 +372,7 @@ class BruteForce(object):
              lnprior_ext=None, wt_thresh=1e-3, cdf_thresh=2e-3, Ndraws=250, lngalprior=None,
              lndustprior=None, dustfile=None, apply_dlabels=True, data_coords=None,
              return_distreds=True, logl_dim_prior=True, ltol=3e-2, ltol_subthresh=1e-2,
-             logl_initthresh=5e-3, mem_lim=8000., rstate=None, batch=1024):
+             logl_initthresh=5e-3, mem_lim=8000., rstate=None, batch=1024, _device_arrays=False):
         """Generator with the reference's contract (brutus/fitting.py:1803-2061): yields, per object,
         ``(sidxs, scales, avs, rvs, cov_sar, Ndim, lnprob, levid, chi2min[, dists, reds, dreds,
         logwts])``.  Stars go to the GPU ``batch`` at a time; the prior integration and resampling
@@ -429,6 +429,9 @@ class BruteForce(object):
                                 parallax_err[b0:b1], coords=data_coords[b0:b1], ext_mean=em, ext_std=es,
                                 opts=opts, nmc_prior=Nmc_prior, ndraws=Ndraws,
                                 seed=seed, star_base=b0, **(self._post_test_hooks(b0, b1)))
+                if _device_arrays:   # fit(): whole-batch arrays, no per-object Python loop
+                    yield b0, b1, r
+                    continue
                 for k in range(b1 - b0):
                     out = (r["sidxs"][k].astype(np.int64), r["scales"][k], r["avs"][k], r["rvs"][k],
                            r["cov_sar"][k], int(r["ndim"][k]), r["lnprob"][k], float(r["levid"][k]),
@@ -511,6 +514,7 @@ class BruteForce(object):
             for k in ("samps_dist", "samps_red", "samps_dred", "samps_logp"):
                 out[k] = np.ones((ndata, Ndraws), dtype="float32")
         t0 = time.time()
+        device_posterior = lngalprior is None
         gen = self._fit(data, data_err, data_mask, parallax=parallax, parallax_err=parallax_err,
                         avlim=avlim, rvlim=rvlim, av_gauss=av_gauss,
                         rv_gauss=rv_gauss, Nmc_prior=Nmc_prior, lnprior=lnprior, lnprior_ext=lnprior_ext,
@@ -519,7 +523,21 @@ class BruteForce(object):
                         apply_dlabels=apply_dlabels, data_coords=data_coords,
                         return_distreds=save_dar_draws, ltol_subthresh=ltol_subthresh,
                         logl_dim_prior=logl_dim_prior, logl_initthresh=logl_initthresh, ltol=ltol,
-                        mem_lim=mem_lim)
+                        mem_lim=mem_lim, _device_arrays=device_posterior)
+        if device_posterior:   # the device returns (Nbatch, Ndraws) arrays: assign them wholesale
+            for b0, b1, r in gen:
+                out["model_idx"][b0:b1], out["ml_scale"][b0:b1] = r["sidxs"], r["scales"]
+                out["ml_av"][b0:b1], out["ml_rv"][b0:b1], out["ml_cov_sar"][b0:b1] = r["avs"], r["rvs"], r["cov_sar"]
+                out["obj_Nbands"][b0:b1], out["obj_log_post"][b0:b1] = r["ndim"], r["lnprob"]
+                out["obj_log_evid"][b0:b1], out["obj_chi2min"][b0:b1] = r["levid"], r["chi2min"]
+                if save_dar_draws:
+                    out["samps_dist"][b0:b1], out["samps_red"][b0:b1] = r["dists"], r["reds"]
+                    out["samps_dred"][b0:b1], out["samps_logp"][b0:b1] = r["dreds"], r["logwts"]
+                if verbose:
+                    sys.stderr.write("\rFitted objects {:d}/{:d} (mean time: {:2.6f} s/obj)    ".format(
+                        b1, ndata, (time.time() - t0) / b1))
+                    sys.stderr.flush()
+            gen = ()
         for i, r in enumerate(gen):
             out["model_idx"][i], out["ml_scale"][i], out["ml_av"][i], out["ml_rv"][i] = r[0], r[1], r[2], r[3]
             out["ml_cov_sar"][i], out["obj_Nbands"][i], out["obj_log_post"][i] = r[4], r[5], r[6]
