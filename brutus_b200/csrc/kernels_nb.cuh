@@ -59,6 +59,8 @@ __device__ __forceinline__ P2<float> ld2(const float* p) { P2<float> r; r.v = *r
 __device__ __forceinline__ P2<double> ld2(const double* p) { return mk2(p[0], p[1]); }
 
 // Star-independent per-model quantities, hoisted out of the star loop.
+constexpr int kRefitTile = kTile;  // threads per CTA of k_refit (128 measured neutral: finer survivor appends scatter the flux gathers)
+constexpr int kFluxTile = 64;    // threads per CTA of k_flux (see the kernel)
 template <typename T, int NB> struct ModelRegs {
     static constexpr int NP = (NB + 1) / 2;
     P2<T> ncb[NP];  // -(b_j - bbar), b_j = mu_j + Abar r0_j  (model magnitudes at the prior-mean reddening)
@@ -478,9 +480,9 @@ __global__ void __launch_bounds__(kTile) k_magfit(const SweepParams<T> p) {
 // =================================================================================================
 template <typename T, int NB>
 // 64 registers -> 4 CTAs per SM: the kernel waits on gathers (ncu: long_scoreboard 6.7 per issue), occupancy helps
-__global__ void __launch_bounds__(kTile, 4) k_refit(const RefitParams<T> p) {
+__global__ void __launch_bounds__(kRefitTile, 4 * kTile / kRefitTile) k_refit(const RefitParams<T> p) {
     constexpr int NP = (NB + 1) / 2;
-    const int64_t q = (int64_t)blockIdx.x * kTile + threadIdx.x;
+    const int64_t q = (int64_t)blockIdx.x * kRefitTile + threadIdx.x;
     const bool inr = q < p.ncand;
     bool surv = false;
     int slot = -1, model = 0;
@@ -509,7 +511,7 @@ __global__ void __launch_bounds__(kTile, 4) k_refit(const RefitParams<T> p) {
         Av = A; Rv = rho; model = (int)i;
     }
     // append the survivors to the compact flux working set: one global atomic per CTA
-    __shared__ int s_w[kTile / 32];
+    __shared__ int s_w[kRefitTile / 32];
     __shared__ int s_base;
     const unsigned bal = __ballot_sync(0xffffffffu, surv);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -517,7 +519,7 @@ __global__ void __launch_bounds__(kTile, 4) k_refit(const RefitParams<T> p) {
     __syncthreads();
     if (threadIdx.x == 0) {
         int n = 0;
-        for (int k = 0; k < kTile / 32; k++) n += s_w[k];
+        for (int k = 0; k < kRefitTile / 32; k++) n += s_w[k];
         s_base = n ? atomicAdd(p.nsv, n) : 0;
     }
     __syncthreads();
@@ -561,10 +563,14 @@ __device__ __forceinline__ void resid_at(const ModelRegs<T, NB>& m, const DevOpt
 // Stars whose loop has converged (SI_ACTIVE == 0, decided on the device by k_flux_ctl) are skipped.
 // =================================================================================================
 template <typename T, int NB>
-// 80 registers -> 3 CTAs per SM (2 at the natural 90); 4 CTAs would spill and measured slower
-__global__ void __launch_bounds__(kTile, 3) k_flux(const FluxParams<T> p) {
+// 80 registers -> 24 warps per SM (16 at the natural 90 registers; 64 registers spill and measured slower).
+// CTAs of kFluxTile = 64 threads: every thread waits on a two-level gather and then runs ~650 dependent
+// instructions, and the per-star reductions at the end need CTA-wide barriers, so with 256-thread CTAs the
+// warps that finish early idle at the barrier while their registers stay allocated (ncu: issue 26 %, DRAM
+// 22 %).  Measured per 1 000 stars: 256 threads 8.6 ms, 128: 7.7, 64: 7.4, 32: 8.5 (global atomics per CTA).
+__global__ void __launch_bounds__(kFluxTile, 3 * kTile / kFluxTile) k_flux(const FluxParams<T> p) {
     constexpr int NP = (NB + 1) / 2;
-    const int64_t t = (int64_t)blockIdx.x * kTile + threadIdx.x;
+    const int64_t t = (int64_t)blockIdx.x * kFluxTile + threadIdx.x;
     const bool inrange = t < p.nsv;
     int slot = inrange ? p.sv.star[t] : -1;
     const bool act = inrange && p.star_int[slot * SI_COUNT + SI_ACTIVE] != 0;
@@ -717,11 +723,11 @@ template <typename T, int NB> void launch_magfit(const SweepParams<T>& p, cudaSt
 }
 template <typename T, int NB> void launch_refit(const RefitParams<T>& p, cudaStream_t st) {
     if (p.ncand <= 0) return;
-    k_refit<T, NB><<<(unsigned)((p.ncand + kTile - 1) / kTile), kTile, 0, st>>>(p);
+    k_refit<T, NB><<<(unsigned)((p.ncand + kRefitTile - 1) / kRefitTile), kRefitTile, 0, st>>>(p);
 }
 template <typename T, int NB> void launch_flux(const FluxParams<T>& p, cudaStream_t st) {
     if (p.nsv <= 0) return;
-    k_flux<T, NB><<<(unsigned)((p.nsv + kTile - 1) / kTile), kTile, 0, st>>>(p);
+    k_flux<T, NB><<<(unsigned)((p.nsv + kFluxTile - 1) / kFluxTile), kFluxTile, 0, st>>>(p);
 }
 template <typename T, int NB, typename O> void launch_records(const RecordParams<T, O>& p, cudaStream_t st) {
     if (p.nrec <= 0) return;
