@@ -21,43 +21,6 @@
 
 namespace bf {
 
-// ---- two-lane values --------------------------------------------------------------------------------
-template <typename T> struct P2;
-template <> struct __align__(8) P2<float> { unsigned long long v; };
-template <> struct __align__(16) P2<double> { double x, y; };
-
-__device__ __forceinline__ P2<float> mk2(float a, float b) {
-    P2<float> r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b));
-    return r;
-}
-__device__ __forceinline__ P2<double> mk2(double a, double b) { P2<double> r; r.x = a; r.y = b; return r; }
-__device__ __forceinline__ float lo2(P2<float> p) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p.v)); return a; }
-__device__ __forceinline__ float hi2(P2<float> p) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p.v)); return b; }
-__device__ __forceinline__ double lo2(P2<double> p) { return p.x; }
-__device__ __forceinline__ double hi2(P2<double> p) { return p.y; }
-template <typename T> __device__ __forceinline__ P2<T> bc2(T a) { return mk2(a, a); }   // folds into a .F32 broadcast operand
-__device__ __forceinline__ P2<float> fma2(P2<float> a, P2<float> b, P2<float> c) {
-    P2<float> r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r;
-}
-__device__ __forceinline__ P2<float> mul2(P2<float> a, P2<float> b) {
-    P2<float> r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r;
-}
-__device__ __forceinline__ P2<float> add2(P2<float> a, P2<float> b) {
-    P2<float> r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r;
-}
-__device__ __forceinline__ P2<float> sub2(P2<float> a, P2<float> b) {
-    P2<float> r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r;
-}
-__device__ __forceinline__ P2<double> fma2(P2<double> a, P2<double> b, P2<double> c) { return mk2(fma(a.x, b.x, c.x), fma(a.y, b.y, c.y)); }
-__device__ __forceinline__ P2<double> mul2(P2<double> a, P2<double> b) { return mk2(a.x * b.x, a.y * b.y); }
-__device__ __forceinline__ P2<double> add2(P2<double> a, P2<double> b) { return mk2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ P2<double> sub2(P2<double> a, P2<double> b) { return mk2(a.x - b.x, a.y - b.y); }
-template <typename T> __device__ __forceinline__ T hsum2(P2<T> p) { return lo2(p) + hi2(p); }
-// pair (2p, 2p+1) of a star-row array (shared or global memory, 8/16-byte aligned)
-__device__ __forceinline__ P2<float> ld2(const float* p) { P2<float> r; r.v = *reinterpret_cast<const unsigned long long*>(p); return r; }
-__device__ __forceinline__ P2<double> ld2(const double* p) { return mk2(p[0], p[1]); }
-
 // Star-independent per-model quantities, hoisted out of the star loop.
 constexpr int kRefitTile = kTile;  // threads per CTA of k_refit (128 measured neutral: finer survivor appends scatter the flux gathers)
 constexpr int kFluxTile = 64;    // threads per CTA of k_flux (see the kernel)

@@ -58,6 +58,22 @@ __device__ __forceinline__ double prcp(double x) { return 1.0 / x; }
 __device__ __forceinline__ float pexp10(float x) { return exp2f(x * 3.3219281f); }
 __device__ __forceinline__ double pexp10(double x) { return exp10(x); }
 
+__device__ __forceinline__ float pex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ double pex2(double x) { return exp2(x); }
+__device__ __forceinline__ float plg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ double plg2(double x) { return log2(x); }
+// lane-wise transcendental of a pair (MUFU is scalar: the two halves of the register pair are fed one by one)
+#define BF_PAIR_FN(name, fn) \
+    template <typename T> __device__ __forceinline__ P2<T> name(P2<T> v) { return mk2(fn(lo2(v)), fn(hi2(v))); }
+BF_PAIR_FN(sqrt2, psqrt)
+BF_PAIR_FN(rsqrt2, prsqrt)
+BF_PAIR_FN(rcp2, prcp)
+BF_PAIR_FN(ex22, pex2)
+BF_PAIR_FN(lg22, plg2)
+BF_PAIR_FN(abs2, tabs)
+#undef BF_PAIR_FN
+constexpr double kLog2e = 1.4426950408889634, kLn2 = 0.6931471805599453;
+
 // three standard normals for (star, model, draw j): Box-Muller on one Philox block
 template <typename T>
 __device__ __forceinline__ void normals3(uint64_t seed, uint64_t star, uint32_t model, uint32_t j, T (&z)[3]) {
@@ -326,6 +342,77 @@ __device__ __forceinline__ void mc_draw(const PostParams<T>& p, const McCtx<T>& 
     }
 }
 
+// ---- two Monte Carlo draws at a time ---------------------------------------------------------------------
+// k_post_mc is bound by instruction issue (ncu: 184 instructions and 17 MUFU per draw, issue 78 %, XU 71 %), so
+// the floating-point work of draws (j, j+1) is done with packed FP32 (FFMA2 / FMUL2 / FADD2: one issue slot
+// for both draws); the transcendentals stay scalar.  Same formula as gal_lnprior above, evaluated in base 2.
+// T = double runs the same code on plain pairs.
+template <typename T>
+__device__ __forceinline__ P2<T> gal_lnprior2(const GalDev<T>& G, const GalStar<T>& gs, const ModelW<T>& w, P2<T> s, P2<T> d) {
+    const P2<T> x = fma2(d, bc2(gs.ax), bc2(gs.x0)), y = mul2(d, bc2(gs.ay)), z = fma2(d, bc2(gs.az), bc2(gs.z0));
+    const P2<T> R2 = fma2(x, x, mul2(y, y));
+    const P2<T> dz = sub2(abs2(z), bc2(G.aZ_solar));
+    const P2<T> Rthin = sqrt2(add2(R2, bc2(G.Rs_thin2)));
+    const P2<T> Rthick = G.same_rs ? Rthin : sqrt2(add2(R2, bc2(G.Rs_thick2)));
+    // log2 of the disk densities relative to the solar neighbourhood
+    const P2<T> lt = fma2(sub2(Rthin, bc2(G.R_solar)), bc2(T(-kLog2e) * G.iR_thin), mul2(dz, bc2(T(-kLog2e) * G.iZ_thin)));
+    const P2<T> lk = fma2(sub2(Rthick, bc2(G.R_solar)), bc2(T(-kLog2e) * G.iR_thick),
+                          fma2(dz, bc2(T(-kLog2e) * G.iZ_thick), bc2(T(kLog2e) * G.ln_f_thick)));
+    const P2<T> rp = sqrt2(add2(fma2(z, z, R2), bc2(G.rq2)));
+    const P2<T> q = fma2(ex22(fma2(rp, bc2(T(-kLog2e) * G.irq), bc2(T(kLog2e)))), bc2(-G.dq), bc2(G.q_inf));
+    const P2<T> zq = mul2(z, rcp2(q));
+    // log2 of the halo density: -eta/2 log2(Reff^2) + eta log2(Reff_solar) + log2 f_halo
+    const P2<T> lh = fma2(lg22(add2(fma2(zq, zq, R2), bc2(G.Rs_halo2))), bc2(T(-0.5) * G.eta),
+                          bc2(T(kLog2e) * (G.eta * G.ln_Reff_solar + G.ln_f_halo)));
+    const P2<T> nt = ex22(sub2(lt, lh)), nk = ex22(sub2(lk, lh));
+    const P2<T> s0 = add2(add2(nt, nk), bc2(T(1)));
+    const P2<T> s1 = fma2(nt, bc2(w.f[0]), fma2(nk, bc2(w.f[1]), bc2(w.f[2])));
+    const P2<T> s2 = fma2(nt, bc2(w.g[0]), fma2(nk, bc2(w.g[1]), bc2(w.g[2])));
+    const P2<T> arg = mul2(mul2(s1, s2), rcp2(mul2(s0, s)));
+    return mul2(add2(lh, lg22(arg)), bc2(T(kLn2)));
+}
+
+// draws j and j + 1 of a selected model: (s, Av, Rv), in-bounds flags and log-priors (:1070-1095).  The second
+// lane is computed even when j + 1 == nmc (the caller ignores it).
+template <typename T> struct McPair {
+    P2<T> s, a, r, lp;
+    bool inb[2];
+};
+
+template <typename T, bool ZOV>
+__device__ __forceinline__ void mc_pair(const PostParams<T>& p, const McCtx<T>& c, int j, McPair<T>& o) {
+    T za[3], zb[3];
+    if (ZOV) {
+        const int jb = j + 1 < p.nmc ? j + 1 : j;
+        const double* zz = p.zov + (size_t)c.model * 3 * p.nmc;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { za[k] = (T)zz[k * p.nmc + j]; zb[k] = (T)zz[k * p.nmc + jb]; }
+    } else {
+        normals3<T>(p.seed, c.star, c.model, (uint32_t)j, za);
+        normals3<T>(p.seed, c.star, c.model, (uint32_t)(j + 1), zb);
+    }
+    const P2<T> z0 = mk2(za[0], zb[0]), z1 = mk2(za[1], zb[1]), z2 = mk2(za[2], zb[2]);
+    o.s = mul2(bc2(c.scale), fma2(bc2(c.L[0]), z0, bc2(T(1))));
+    o.a = fma2(bc2(c.L[2]), z1, fma2(bc2(c.L[1]), z0, bc2(c.av)));
+    o.r = fma2(bc2(c.L[5]), z2, fma2(bc2(c.L[4]), z1, fma2(bc2(c.L[3]), z0, bc2(c.rv))));
+    const T sv[2] = {lo2(o.s), hi2(o.s)}, av[2] = {lo2(o.a), hi2(o.a)}, rv[2] = {lo2(o.r), hi2(o.r)};
+#pragma unroll
+    for (int k = 0; k < 2; k++)   // (:1090-1092)
+        o.inb[k] = sv[k] >= T(1e-20) && av[k] >= p.avmin && av[k] <= p.avmax && rv[k] >= p.rvmin && rv[k] <= p.rvmax;
+    // out-of-bounds lanes may carry a negative scale: give them a harmless one, their result is discarded
+    const P2<T> sc = mk2(o.inb[0] ? sv[0] : c.scale, o.inb[1] ? sv[1] : c.scale);
+    const P2<T> dist = rsqrt2(sc), par = mul2(sc, dist);
+    P2<T> lp = p.G.use ? gal_lnprior2<T>(p.G, c.gs, c.w, sc, dist) : bc2(T(0));
+    if (c.pivar > T(0)) {
+        const P2<T> d = sub2(par, bc2(c.par));
+        lp = fma2(mul2(d, d), bc2(T(-0.5) * c.pivar), add2(lp, bc2(T(-0.5) * c.lnorm_par)));
+    }
+    T l0 = lo2(lp), l1 = hi2(lp);
+    l0 = !o.inb[0] ? Num<T>::kNegBig : (l0 != l0 ? Num<T>::neg_inf() : l0);
+    l1 = !o.inb[1] ? Num<T>::kNegBig : (l1 != l1 ? Num<T>::neg_inf() : l1);
+    o.lp = mk2(l0, l1);
+}
+
 template <typename T>
 __device__ __forceinline__ void mc_setup(const PostParams<T>& p, int64_t t, int slot, McCtx<T>& c, Cov3& cv) {
     const int64_t i = p.idx[t];
@@ -359,7 +446,7 @@ template <typename T> struct Lse {
 };
 
 // (:1038-1106) one thread per model of the second selection.  ZOV: normals supplied by the host (test mode)
-template <typename T, bool ZOV> __global__ void __launch_bounds__(kTile) k_post_mc(const PostParams<T> p) {
+template <typename T, bool ZOV> __global__ void __launch_bounds__(kTile, 4) k_post_mc(const PostParams<T> p) {
     const int64_t u = (int64_t)blockIdx.x * kTile + threadIdx.x;
     const bool in = u < p.n2;
     int slot = -1;
@@ -372,11 +459,15 @@ template <typename T, bool ZOV> __global__ void __launch_bounds__(kTile) k_post_
         mc_setup<T>(p, t, slot, c, cv);
         Lse<T> acc;
         int neff = 0;
-        for (int j = 0; j < p.nmc; j++) {
-            T s, a, r, lp; bool inb;
-            mc_draw<T, ZOV>(p, c, j, s, a, r, lp, inb);
-            acc.add(lp);
-            neff += inb ? 1 : 0;
+        for (int j = 0; j < p.nmc; j += 2) {
+            McPair<T> m;
+            mc_pair<T, ZOV>(p, c, j, m);
+            acc.add(lo2(m.lp));
+            neff += m.inb[0] ? 1 : 0;
+            if (j + 1 < p.nmc) {
+                acc.add(hi2(m.lp));
+                neff += m.inb[1] ? 1 : 0;
+            }
         }
         const int64_t i = p.idx[t];
         lnp = p.rows[t] + (p.lnprior ? p.lnprior[i] : T(0));                 // lnlike + lnprior (:1024)
@@ -485,22 +576,30 @@ template <typename T, bool ZOV> __global__ void k_post_draw(const PostParams<T> 
     p.o_lnprob[o] = lnp <= Num<T>::kNegBig ? -1e300 : (double)lnp;
     // pick one of the model's Nmc draws with probability ~ exp(lnp_mc) (:2050-2053)
     Lse<T> acc;
-    for (int j = 0; j < p.nmc; j++) {
-        T s, av, rv, lp; bool inb;
-        mc_draw<T, ZOV>(p, c, j, s, av, rv, lp, inb);
-        acc.add(lp);
+    for (int j = 0; j < p.nmc; j += 2) {   // the same paired evaluation as k_post_mc: identical log-priors
+        McPair<T> m;
+        mc_pair<T, ZOV>(p, c, j, m);
+        acc.add(lo2(m.lp));
+        if (j + 1 < p.nmc) acc.add(hi2(m.lp));
     }
     const T m = acc.m;
     const double W = (double)acc.s;
     double run = 0.;
     int pick = -1;
     T ps = c.scale, pa = c.av, pr = c.rv, pl = Num<T>::neg_inf();
-    for (int j = 0; j < p.nmc && pick < 0; j++) {
-        T s, av, rv, lp; bool inb;
-        mc_draw<T, ZOV>(p, c, j, s, av, rv, lp, inb);
-        // all draws at -inf: exp(-inf - -inf) is NaN in the reference too; fall through to the last draw
-        if (lp > Num<T>::neg_inf()) run += (double)pexp(lp - m);
-        if ((W > 0. && run / W > u2) || j == p.nmc - 1) { pick = j; ps = s; pa = av; pr = rv; pl = lp; }
+    for (int j0 = 0; j0 < p.nmc && pick < 0; j0 += 2) {
+        McPair<T> mp;
+        mc_pair<T, ZOV>(p, c, j0, mp);
+        const T sv[2] = {lo2(mp.s), hi2(mp.s)}, av[2] = {lo2(mp.a), hi2(mp.a)}, rv[2] = {lo2(mp.r), hi2(mp.r)};
+        const T lv[2] = {lo2(mp.lp), hi2(mp.lp)};
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int j = j0 + k;
+            if (j >= p.nmc || pick >= 0) continue;
+            // all draws at -inf: exp(-inf - -inf) is NaN in the reference too; fall through to the last draw
+            if (lv[k] > Num<T>::neg_inf()) run += (double)pexp(lv[k] - m);
+            if ((W > 0. && run / W > u2) || j == p.nmc - 1) { pick = j; ps = sv[k]; pa = av[k]; pr = rv[k]; pl = lv[k]; }
+        }
     }
     p.o_dist[o] = 1. / sqrt((double)ps);
     p.o_red[o] = (double)pa;
