@@ -1362,8 +1362,9 @@ template <typename T> struct Engine : EngineBase {
                 stats.kernel_launches += 2;
             }
             k_post_cdf<T><<<ng, 1024, 0, stream>>>(pp);
-            if (pp.zov) k_post_draw<T, true><<<ng, std::min(1024, (nd + 31) / 32 * 32), 0, stream>>>(pp);
-            else k_post_draw<T, false><<<ng, std::min(1024, (nd + 31) / 32 * 32), 0, stream>>>(pp);
+            const int dthreads = std::min(kTile, (nd + 31) / 32 * 32);   // the kernel strides over the draws
+            if (pp.zov) k_post_draw<T, true><<<ng, dthreads, 0, stream>>>(pp);
+            else k_post_draw<T, false><<<ng, dthreads, 0, stream>>>(pp);
             stats.kernel_launches += 2;
             CK(cudaGetLastError());
             CK(cudaEventRecord(evP1, stream));

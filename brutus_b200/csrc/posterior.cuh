@@ -534,7 +534,7 @@ template <typename T> __global__ void __launch_bounds__(1024) k_post_cdf(const P
 }
 
 // one CTA per star, one thread per posterior draw (:2040-2061)
-template <typename T, bool ZOV> __global__ void k_post_draw(const PostParams<T> p) {
+template <typename T, bool ZOV> __global__ void __launch_bounds__(kTile) k_post_draw(const PostParams<T> p) {
     const int slot = p.g0 + blockIdx.x;
     const int64_t lo = p.off2[slot], hi = p.off2[slot + 1];
     for (int d = threadIdx.x; d < p.ndraws; d += blockDim.x) {

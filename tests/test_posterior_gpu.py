@@ -165,3 +165,34 @@ def test_fit_batch_argument_errors():
         assert out["sidxs"].shape == (2, 7) and np.all(out["sidxs"] >= 0)
     finally:
         h.close()
+
+
+def test_fit_batch_edge_cases():
+    """Empty catalogue; more draws than a CTA has threads with an odd Nmc_prior; a prior that excludes every model
+    (the reference would fail on an empty selection: the device reports sidxs = -99 and levid = -1e300)."""
+    from brutus_b200 import _lib
+    grid, lab, st, coords, lnprior = _case(nmodel=800, nstar=3)
+    h = _lib.Handle(0, "f32")
+    try:
+        h.set_grid(grid)
+        h.set_model_priors(lnprior=lnprior, feh=lab["feh"], loga=lab["loga"])
+        out = h.fit_batch(st["flux"][:0], st["err"][:0], st["mask"][:0], coords=coords[:0], nmc_prior=4, ndraws=5)
+        assert out["sidxs"].shape == (0, 5) and out["levid"].shape == (0,)
+        out = h.fit_batch(st["flux"], st["err"], st["mask"], st["parallax"], st["parallax_err"], coords=coords,
+                          nmc_prior=3, ndraws=1500, seed=9)
+        assert out["sidxs"].shape == (3, 1500)
+        ok = out["nsel"] > 0       # (this case's labels put some models beyond 13.8 Gyr: a star may select none)
+        assert ok.sum() >= 2 and np.all(out["sidxs"][ok] >= 0) and np.all(out["sidxs"][ok] < 800)
+        assert np.all(out["sidxs"][~ok] == -99) and np.all(out["levid"][~ok] <= -1e299)
+        assert np.all(np.isfinite(out["dists"][ok])) and np.all(np.isfinite(out["levid"][ok]))
+        # every drawn (scale, av, rv) is the record of its model: same model -> same values within a star
+        for k in np.where(ok)[0]:
+            _, first = np.unique(out["sidxs"][k], return_index=True)
+            for j in first[:20]:
+                same = out["sidxs"][k] == out["sidxs"][k][j]
+                assert np.all(out["scales"][k][same] == out["scales"][k][j])
+        h.set_model_priors(lnprior=np.full(800, -np.inf))
+        out = h.fit_batch(st["flux"], st["err"], st["mask"], coords=coords, nmc_prior=4, ndraws=6)
+        assert np.all(out["nsel"] == 0) and np.all(out["sidxs"] == -99) and np.all(out["levid"] <= -1e299)
+    finally:
+        h.close()
