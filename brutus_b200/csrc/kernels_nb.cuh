@@ -442,8 +442,9 @@ __global__ void __launch_bounds__(kTile) k_magfit(const SweepParams<T> p) {
 // (stepsize 1, lnl_old = -1e300, :778-779).
 // =================================================================================================
 template <typename T, int NB>
-// 64 registers -> 4 CTAs per SM: the kernel waits on gathers (ncu: long_scoreboard 6.7 per issue), occupancy helps
-__global__ void __launch_bounds__(kRefitTile, 4 * kTile / kRefitTile) k_refit(const RefitParams<T> p) {
+// up to 8 bands: 64 registers -> 4 CTAs per SM: the kernel waits on gathers (ncu: long_scoreboard 6.7 per issue),
+// occupancy helps; more bands need more registers (3 CTAs up to 12 bands, 2 beyond, to stay clear of spills)
+__global__ void __launch_bounds__(kRefitTile, (NB <= 8 ? 4 : (NB <= 12 ? 3 : 2)) * kTile / kRefitTile) k_refit(const RefitParams<T> p) {
     constexpr int NP = (NB + 1) / 2;
     const int64_t q = (int64_t)blockIdx.x * kRefitTile + threadIdx.x;
     const bool inr = q < p.ncand;
@@ -531,7 +532,7 @@ template <typename T, int NB>
 // instructions, and the per-star reductions at the end need CTA-wide barriers, so with 256-thread CTAs the
 // warps that finish early idle at the barrier while their registers stay allocated (ncu: issue 26 %, DRAM
 // 22 %).  Measured per 1 000 stars: 256 threads 8.6 ms, 128: 7.7, 64: 7.4, 32: 8.5 (global atomics per CTA).
-__global__ void __launch_bounds__(kFluxTile, 3 * kTile / kFluxTile) k_flux(const FluxParams<T> p) {
+__global__ void __launch_bounds__(kFluxTile, (NB <= 8 ? 3 : 2) * kTile / kFluxTile) k_flux(const FluxParams<T> p) {
     constexpr int NP = (NB + 1) / 2;
     const int64_t t = (int64_t)blockIdx.x * kFluxTile + threadIdx.x;
     const bool inrange = t < p.nsv;
