@@ -214,8 +214,14 @@ def run_b200(args):
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            # keep stdout to the one JSON line (an image-level nccl.conf may ask for the version banner;
+            # the environment takes precedence over it)
+            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL prints its version banner on stdout at the first communicator: keep fd 1 for the JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     h = _lib.Handle(local_rank, args.precision)
     # ---- stage the grid: rank 0 builds it; one NCCL broadcast; device-side re-tiling ----
@@ -237,6 +243,11 @@ def run_b200(args):
         obj = [pri]
         dist.broadcast_object_list(obj, src=0)
         pri = obj[0]
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     else:
         grid, labels = make_inputs(args.config, cfg, 0)
         h.set_grid(grid)
