@@ -283,7 +283,8 @@ def run_b200(args):
         t = time.perf_counter()
         res = h.fit_batch(stars["flux"], stars["err"], stars["mask"], stars["parallax"],
                           stars["parallax_err"], coords=stars["coords"], opts=opts,
-                          nmc_prior=args.nmc_prior, ndraws=args.ndraws, seed=12345, star_base=rank * nstar)
+                          nmc_prior=args.nmc_prior, ndraws=args.ndraws, seed=12345, star_base=rank * nstar,
+                          mem_lim=8000.)   # fit()'s default mem_lim (brutus/fitting.py:1436)
         wall = time.perf_counter() - t
         return res, wall, h.stats()
 
@@ -360,6 +361,7 @@ def run_b200(args):
                 "device_ms_per_step": agg_f["ms_device"] / args.steps,
                 "posterior_ms_per_step": agg_f["ms_post"] / args.steps,
                 "selected2_per_step": agg_f["selected2"] / args.steps,
+                "clipped_stars_per_step": agg_f["clipped"] / args.steps,
                 "finite_evidence_frac": float(np.mean(resf["levid"] > -1e299)),
                 "note": "host float64 photometry in, Ndraws posterior samples per star out: the full-grid "
                         "sweep of `value`, then lnpost (default Galactic prior, Nmc_prior Monte Carlo draws per "

@@ -52,7 +52,7 @@ class Stats(C.Structure):
                 ("resweeps", C.c_int64), ("candidates", C.c_int64), ("fallbacks", C.c_int64),
                 ("survivors", C.c_int64),
                 ("selected", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-                ("ms_post", C.c_double), ("selected2", C.c_int64)]
+                ("ms_post", C.c_double), ("selected2", C.c_int64), ("clipped", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -73,7 +73,7 @@ class GalParams(C.Structure):
 class PostOptions(C.Structure):
     _fields_ = [("nmc_prior", C.c_int32), ("ndraws", C.c_int32), ("seed", C.c_uint64),
                 ("use_gal_prior", C.c_int32), ("reserved", C.c_int32), ("star_base", C.c_int64),
-                ("gal", GalParams),
+                ("nsel_max", C.c_int64), ("gal", GalParams),
                 ("z_override", C.c_void_p), ("u_override", C.c_void_p)]
 
 
@@ -321,7 +321,7 @@ class Handle:
 
     def fit_batch(self, flux, err, mask, parallax=None, parallax_err=None, coords=None, ext_mean=None,
                   ext_std=None, opts=None, nmc_prior=50, ndraws=250, seed=0, use_gal_prior=True,
-                  gal=None, star_base=0, z_override=None, u_override=None):
+                  gal=None, star_base=0, mem_lim=None, z_override=None, u_override=None):
         """The per-object body of ``BruteForce._fit`` on the device (``bf_fit_batch``): returns a dict
         with the reference's 13-tuple members as (Ndata, Ndraws) arrays (``sidxs, scales, avs, rvs,
         cov_sar, lnprob, dists, reds, dreds, logwts``) and per-object ``ndim, levid, chi2min, nsel,
@@ -350,6 +350,8 @@ class Handle:
         po.nmc_prior, po.ndraws, po.seed = int(nmc_prior), int(ndraws), int(seed) & (2 ** 64 - 1)
         po.use_gal_prior = int(bool(use_gal_prior))
         po.star_base = int(star_base)
+        # lnpost's memory clip: Nsel_max = int(mem_lim / Nmc_prior / 4e-4) (brutus/fitting.py:969-970); None = off
+        po.nsel_max = 0 if mem_lim is None else max(1, int(float(mem_lim) / po.nmc_prior / 4.0e-4))
         for k, v in (gal or {}).items():
             if k not in GAL_FIELDS:
                 raise ValueError("unknown Galactic prior parameter %r" % k)

@@ -16,6 +16,8 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_segmented_radix_sort.cuh>
+
 #include "../../include/brutus_b200.h"
 #include "common.cuh"
 #include "posterior.cuh"
@@ -478,7 +480,9 @@ template <typename T> struct Engine : EngineBase {
     // device posterior (bf_fit_batch)
     cudaEvent_t evP0 = nullptr, evP1 = nullptr;
     bool have_prior[3] = {false, false, false};   // lnprior, feh, loga staged?
-    DevBuf<T> d_lnprior, d_feh, d_loga, d_lnp1, d_lnp2;
+    DevBuf<T> d_lnprior, d_feh, d_loga, d_lnp1, d_lnp2, d_lnb1, d_keys, d_keys_sorted, d_clip;
+    DevBuf<int> d_seg;
+    DevBuf<char> d_cubtmp;
     DevBuf<GalStar<T>> d_gstar;
     DevBuf<int> d_rstar, d_nsel2, d_sel2, d_oidx;
     DevBuf<int64_t> d_off2;
@@ -510,6 +514,7 @@ template <typename T> struct Engine : EngineBase {
         d_nsurv.release(); d_nsel.release(); d_ctr.release(); d_blk.release(); d_cand.release();
         d_probe.release(); d_ncand.release(); d_base.release(); d_tot.release(); d_red.release(); d_out.release(); d_flush.release();
         d_lnprior.release(); d_feh.release(); d_loga.release(); d_lnp1.release(); d_lnp2.release(); d_gstar.release();
+        d_lnb1.release(); d_keys.release(); d_keys_sorted.release(); d_clip.release(); d_seg.release(); d_cubtmp.release();
         d_rstar.release(); d_nsel2.release(); d_sel2.release(); d_oidx.release(); d_off2.release(); d_cdf.release();
         d_ptot.release(); d_odbl.release(); h_nsel2.release();
         if (evP0) cudaEventDestroy(evP0);
@@ -1335,7 +1340,8 @@ template <typename T> struct Engine : EngineBase {
             int64_t n2 = 0;
             if (n1 > 0) {
                 CK(d_lnp1.ensure((size_t)n1)); CK(d_lnp2.ensure((size_t)n1)); CK(d_sel2.ensure((size_t)n1)); CK(d_cdf.ensure((size_t)n1));
-                pp.lnp1 = d_lnp1.p; pp.lnp2 = d_lnp2.p; pp.sel2 = d_sel2.p; pp.cdf = d_cdf.p;
+                CK(d_lnb1.ensure((size_t)n1));
+                pp.lnp1 = d_lnp1.p; pp.lnp2 = d_lnp2.p; pp.sel2 = d_sel2.p; pp.cdf = d_cdf.p; pp.lnb1 = d_lnb1.p;
                 const unsigned nb1 = (unsigned)((n1 + kTile - 1) / kTile);
                 k_post_mle<T><<<nb1, kTile, 0, stream>>>(pp);
                 k_post_count<T><<<nb1, kTile, 0, stream>>>(pp);
@@ -1351,6 +1357,49 @@ template <typename T> struct Engine : EngineBase {
                 if (nsel) nsel[g.s0 + s] = h_nsel2[s];
             }
             n2 = h_off2[g.g1];
+            // ---- lnpost's memory clip (:1029-1036): stars whose second selection exceeds nsel_max keep their
+            // nsel_max best models by lnlike + lnprior (one segmented radix sort over the over-full stars) ----
+            if (po->nsel_max > 0 && n2 > 0) {
+                std::vector<int> seg;   // begin, end, slot per over-full star
+                for (int s = g.g0; s < g.g1; s++)
+                    if (h_nsel2[s] > po->nsel_max) { seg.push_back((int)h_off2[s]); seg.push_back((int)h_off2[s + 1]); seg.push_back(s); }
+                const int nseg = (int)seg.size() / 3;
+                if (nseg > 0) {
+                    if (n2 >= ((int64_t)1 << 31)) { err = "bf_fit_batch: second selection too large for the memory clip"; return BF_E_NOMEM; }
+                    std::vector<int> hs(3 * (size_t)nseg);
+                    for (int k = 0; k < nseg; k++) { hs[k] = seg[3 * k]; hs[nseg + k] = seg[3 * k + 1]; hs[2 * nseg + k] = seg[3 * k + 2]; }
+                    CK(d_seg.ensure(hs.size()));
+                    CK(cudaMemcpyAsync(d_seg.p, hs.data(), hs.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+                    CK(d_keys.ensure((size_t)n2)); CK(d_keys_sorted.ensure((size_t)n2)); CK(d_clip.ensure((size_t)batch_cap));
+                    pp.n2 = n2; pp.keys = d_keys.p;
+                    CK(cudaMemcpyAsync(d_off2.p + g.g0, h_off2.data() + g.g0, (size_t)(ng + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+                    const unsigned nb1 = (unsigned)((n1 + kTile - 1) / kTile);
+                    k_post_write<T><<<nb1, kTile, 0, stream>>>(pp);
+                    k_post_keys<T><<<(unsigned)((n2 + 255) / 256), 256, 0, stream>>>(pp);
+                    size_t tmp_bytes = 0;
+                    CK(cub::DeviceSegmentedRadixSort::SortKeysDescending(nullptr, tmp_bytes, d_keys.p, d_keys_sorted.p, (int)n2, nseg,
+                                                                         d_seg.p, d_seg.p + nseg, 0, (int)sizeof(T) * 8, stream));
+                    CK(d_cubtmp.ensure(tmp_bytes + 16));
+                    CK(cub::DeviceSegmentedRadixSort::SortKeysDescending(d_cubtmp.p, tmp_bytes, d_keys.p, d_keys_sorted.p, (int)n2, nseg,
+                                                                         d_seg.p, d_seg.p + nseg, 0, (int)sizeof(T) * 8, stream));
+                    k_fill<T><<<(batch_cap + 255) / 256, 256, 0, stream>>>(d_clip.p, batch_cap, -std::numeric_limits<T>::infinity());
+                    k_post_thr<T><<<(nseg + 255) / 256, 256, 0, stream>>>(d_keys_sorted.p, d_seg.p, d_seg.p + 2 * nseg, nseg, po->nsel_max, d_clip.p);
+                    pp.clip_thr = d_clip.p;
+                    CK(cudaMemsetAsync(d_nsel2.p + g.g0, 0, (size_t)ng * sizeof(int), stream));
+                    k_post_count<T><<<nb1, kTile, 0, stream>>>(pp);
+                    k_scan_blocks<<<1, 1024, 0, stream>>>(d_blk.p, nb1, d_tot.p);
+                    stats.kernel_launches += 7;
+                    CK(cudaGetLastError());
+                    publish(h_nsel2.data() + g.g0, d_nsel2.p + g.g0, (size_t)ng * sizeof(int));
+                    CK(cudaStreamSynchronize(stream));
+                    for (int s = g.g0; s < g.g1; s++) {
+                        h_off2[s + 1] = h_off2[s] + h_nsel2[s];
+                        if (nsel) nsel[g.s0 + s] = h_nsel2[s];
+                    }
+                    n2 = h_off2[g.g1];
+                    stats.clipped += nseg;
+                }
+            }
             stats.selected2 += n2;
             pp.n2 = n2;
             CK(cudaMemcpyAsync(d_off2.p + g.g0, h_off2.data() + g.g0, (size_t)(ng + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
@@ -1504,6 +1553,7 @@ void bf_default_gal_params(bf_gal_params* g) {   /* defaults of gal_lnprior, bru
 void bf_default_post_options(bf_post_options* o) {
     if (!o) return;
     o->nmc_prior = 50; o->ndraws = 250; o->seed = 0; o->use_gal_prior = 1; o->reserved = 0; o->star_base = 0;
+    o->nsel_max = 0;
     bf_default_gal_params(&o->gal);
     o->z_override = nullptr; o->u_override = nullptr;
 }

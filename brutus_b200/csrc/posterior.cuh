@@ -179,6 +179,9 @@ template <typename T> struct PostParams {
     T avmin, avmax, rvmin, rvmax;
     // second selection
     T* lnp1;                 // [n1]
+    T* lnb1;                 // [n1] lnlike + lnprior: the ranking key of the memory clip (:1024, :1029-1036)
+    const T* clip_thr;       // [batch] smallest key kept by the clip (-inf: star not clipped), or null
+    T* keys;                 // [n2] keys of the second selection, gathered for the segmented sort
     int* blk;                // per 256-record block counts -> offsets
     int* nsel2;              // [batch]
     int* sel2;               // [n2] -> record index t
@@ -212,8 +215,10 @@ template <typename T> __global__ void __launch_bounds__(kTile) k_post_mle(const 
         ModelW<T> w;
         model_weights<T>(p.G, p.feh, p.loga, i, w);
         const T scale = p.rows[p.ld + t];
-        lp = p.rows[t] + (p.lnprior ? p.lnprior[i] : T(0)) + gal_lnprior<T>(p.G, p.gstar[slot], w, scale, prsqrt(scale));
+        const T base = p.rows[t] + (p.lnprior ? p.lnprior[i] : T(0));
+        lp = base + gal_lnprior<T>(p.G, p.gstar[slot], w, scale, prsqrt(scale));
         p.lnp1[t] = lp;
+        p.lnb1[t] = base;
     }
     cta_star_max<T>(p.red, RED_P1, slot, in, lp);
 }
@@ -222,6 +227,7 @@ template <typename T> __device__ __forceinline__ bool post_flag(const PostParams
     slot = -1;
     if (t >= p.n1) return false;
     slot = p.rstar[t];
+    if (p.clip_thr && !(p.lnb1[t] >= p.clip_thr[slot])) return false;                       // (:1029-1036)
     return p.lnp1[t] > Enc<T>::dec(p.red[(int64_t)slot * kNumRed + RED_P1]) + p.ln_wt;   // (:1013-1016)
 }
 
@@ -248,6 +254,23 @@ template <typename T> __global__ void __launch_bounds__(kTile) k_post_write(cons
         for (int k = 0; k < w; k++) pre += s_w[k];
         p.sel2[p.blk[blockIdx.x] + pre] = (int)t;
     }
+}
+
+// memory clip (:1029-1036): keys of the second selection, and the threshold of every over-full star from its
+// keys sorted in descending order (segment k of the sort = star seg_slot[k], starting at seg_begin[k])
+template <typename T> __global__ void k_post_keys(const PostParams<T> p) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < p.n2) p.keys[u] = p.lnb1[p.sel2[u]];
+}
+template <typename T>
+__global__ void k_post_thr(const T* __restrict__ sorted, const int* __restrict__ seg_begin, const int* __restrict__ seg_slot,
+                           int nseg, int64_t nsel_max, T* __restrict__ thr) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nseg) thr[seg_slot[k]] = sorted[(int64_t)seg_begin[k] + nsel_max - 1];
+}
+template <typename T> __global__ void k_fill(T* p, int n, T v) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) p[k] = v;
 }
 
 // Covariance of (s, Av, Rv) in RELATIVE scale units (s' = s / scale, so that the matrix is O(1) whatever

@@ -265,7 +265,7 @@ class BruteForce(object):
     Differences, all outside the hot path: the 3-D dust prior is not bundled (no Bayestar map offline;
     pass ``lndustprior`` on the host path; with ``dustfile=None`` and no ``lndustprior`` the A(V) prior is
     flat, as in the reference :1396-1398); ``parallax=None`` is accepted (the reference raises TypeError);
-    ``mem_lim`` is ignored on the device path; results go to ``<save_file>.h5`` when h5py is importable and
+    results go to ``<save_file>.h5`` when h5py is importable and
     to ``<save_file>.npz`` with the same dataset names otherwise."""
 
     def __init__(self, models, models_labels, labels_mask, precision="f32", device=0):
@@ -428,7 +428,7 @@ class BruteForce(object):
                 r = h.fit_batch(data[b0:b1], data_err[b0:b1], data_mask[b0:b1], parallax[b0:b1],
                                 parallax_err[b0:b1], coords=data_coords[b0:b1], ext_mean=em, ext_std=es,
                                 opts=opts, nmc_prior=Nmc_prior, ndraws=Ndraws,
-                                seed=seed, star_base=b0, **(self._post_test_hooks(b0, b1)))
+                                seed=seed, star_base=b0, mem_lim=mem_lim, **(self._post_test_hooks(b0, b1)))
                 if _device_arrays:   # fit(): whole-batch arrays, no per-object Python loop
                     yield b0, b1, r
                     continue

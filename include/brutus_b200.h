@@ -80,6 +80,7 @@ typedef struct bf_stats {
     int64_t h2d_bytes, d2h_bytes;
     double ms_post;         /* bf_fit_batch: prior integration, evidence, resampling kernels */
     int64_t selected2;      /* bf_fit_batch: models that passed lnpost's second threshold     */
+    int64_t clipped;        /* bf_fit_batch: stars whose second selection was cut to nsel_max */
 } bf_stats;
 
 void bf_default_options(bf_options* opt);
@@ -171,6 +172,9 @@ typedef struct bf_post_options {
     int64_t star_base;      /* catalogue index of the first star of this call: the generator is keyed by
                                (seed, star_base + s, model, draw), so a batched or star-sharded caller gets
                                the same numbers as one call over the whole catalogue */
+    int64_t nsel_max;       /* lnpost's memory clip (brutus/fitting.py:969-970, :1029-1036): when a star's second
+                               selection holds more than nsel_max = int(mem_lim / Nmc_prior / 4e-4) models, only
+                               the nsel_max with the largest lnlike + lnprior are kept; 0 = no clip */
     bf_gal_params gal;
     /* test hooks (NULL in production): host-supplied random numbers so that the device result can be
      * compared draw for draw with a NumPy restatement.
@@ -198,7 +202,7 @@ typedef struct bf_draws {
  * bf_sweep_batch's work, then lnpost (priors at the MLE, second threshold, covariances, Monte Carlo
  * integration over the Galactic and parallax priors), the evidence, chi2min and the resampling.
  * Only ndraws samples per star cross PCIe.  Not applied: the 3-D dust prior (no map bundled: flat
- * A(V) prior, as fit(dustfile=None) :1396-1398) and the mem_lim clip (:1029-1036).
+ * A(V) prior, as fit(dustfile=None) :1396-1398).
  *   coords [nstar*2] float64 Galactic (l, b) in degrees, or NULL with use_gal_prior = 0
  * outputs: ndim [nstar] (incl. +1 for a finite parallax, :2030), n_iter [nstar*2], nsel [nstar] (size of
  * the second selection), levid, chi2min [nstar]; any of ndim / n_iter / nsel may be NULL. */

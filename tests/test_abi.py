@@ -34,7 +34,7 @@ def test_struct_layout_matches_header(lib):
     assert (o.ltol, o.ltol_subthresh, o.init_thresh, o.wt_thresh, o.select_slack) == (3e-2, 1e-2, 5e-3, 1e-3, 1.0)
     assert (o.dim_prior, o.max_iter, o.apply_parallax_clip) == (1, 0, 1)
     assert C.sizeof(_lib.Options) == 8 * 8 + 5 * 8 + 4 * 4
-    assert C.sizeof(_lib.Stats) == 4 * 8 + 10 * 8 + 2 * 8
+    assert C.sizeof(_lib.Stats) == 4 * 8 + 10 * 8 + 3 * 8
     assert C.sizeof(_lib.Records) == 8 + 8 + 4 + 4 + 8 + 8
     po = _lib.PostOptions()
     lib.bf_default_post_options(C.byref(po))
@@ -43,7 +43,8 @@ def test_struct_layout_matches_header(lib):
     assert (po.gal.R_solar, po.gal.Z_thick, po.gal.f_halo, po.gal.min_sigma) == (8.2, 0.9, 0.005, 1.0)
     assert (po.gal.galcen_distance, po.gal.z_sun) == (8.122, 0.0208)
     assert not po.z_override and not po.u_override
-    assert C.sizeof(_lib.PostOptions) == 4 + 4 + 8 + 4 + 4 + 8 + 30 * 8 + 2 * 8
+    assert C.sizeof(_lib.PostOptions) == 4 + 4 + 8 + 4 + 4 + 8 + 8 + 30 * 8 + 2 * 8
+    assert po.nsel_max == 0
     assert C.sizeof(_lib.Draws) == 10 * 8
 
 

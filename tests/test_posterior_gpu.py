@@ -196,3 +196,49 @@ def test_fit_batch_edge_cases():
         assert np.all(out["nsel"] == 0) and np.all(out["sidxs"] == -99) and np.all(out["levid"] <= -1e299)
     finally:
         h.close()
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_memory_clip_matches_host(precision):
+    """lnpost's mem_lim clip (brutus/fitting.py:1029-1036): a star whose second selection exceeds
+    Nsel_max = int(mem_lim / Nmc_prior / 4e-4) keeps its Nsel_max best models by lnlike + lnprior.  The host path
+    re-orders the kept models by rank, so draws are not comparable one to one; the kept set, the evidence (same
+    normals on both sides) and chi2min are."""
+    from brutus_b200 import fitting
+    grid, lab, st, coords, lnprior = _case()
+    nstar, nmc, ndraws = len(st["flux"]), 20, 30
+    nsel_max = 150
+    mem_lim = (nsel_max + 0.5) * nmc * 4.0e-4
+    lmask = np.ones(1, dtype=[(n, bool) for n in lab.dtype.names])
+    bf = fitting.BruteForce(grid, lab, lmask, precision=precision)
+    rs = np.random.RandomState(7)
+    z = rs.normal(size=(grid.shape[0], 3, nmc))
+    u = rs.uniform(size=(nstar, 2, ndraws))
+    kw = dict(parallax=st["parallax"], parallax_err=st["parallax_err"], Nmc_prior=nmc, lnprior=lnprior, Ndraws=ndraws,
+              dustfile=None, data_coords=coords, mem_lim=mem_lim)
+    try:
+        bf._z_override, bf._u_override = z, u
+        dev = list(bf._fit(st["flux"], st["err"], st["mask"].copy(), **kw))
+        stats = bf._get_handle().stats()
+        bf._z_override = bf._u_override = None
+        h = bf._get_handle()
+        res = h.sweep_batch(st["flux"], st["err"], st["mask"], st["parallax"], st["parallax_err"], copy=True)
+        sels = []
+        for i in range(nstar):
+            lo, hi = res["offsets"][i], res["offsets"][i + 1]
+            sels.append(fitting.lnpost_selected(
+                res["model_idx"][lo:hi], res["lnl"][lo:hi], res["scale"][lo:hi], res["av"][lo:hi], res["rv"][lo:hi],
+                fitting._unpack_icov(res["icov6"][:, lo:hi]), parallax=st["parallax"][i], parallax_err=st["parallax_err"][i],
+                coord=coords[i], Nmc_prior=nmc, lnprior=lnprior, lngalprior=_galprior, dlabels=lab, mem_lim=mem_lim,
+                rstate=np.random.RandomState(1), apply_av_prior=False)[0])
+        host = list(bf._fit(st["flux"], st["err"], st["mask"].copy(), lngalprior=_galprior,
+                            rstate=gp.ReplayRState(z, sels, u[:, 0], u[:, 1]), **kw))
+    finally:
+        bf.close()
+    assert max(len(s) for s in sels) == nsel_max and stats["clipped"] >= 2
+    assert abs(stats["selected2"] - sum(len(s) for s in sels)) <= (0 if precision == "f64" else 3)
+    for i, (d, hh) in enumerate(zip(dev, host)):
+        tol = 1e-7 if precision == "f64" else 5e-3
+        assert abs(d[7] - hh[7]) < tol * max(1., abs(hh[7])), (i, "levid", d[7], hh[7])
+        assert abs(d[8] - hh[8]) < (1e-7 if precision == "f64" else 2e-3) * max(1., abs(hh[8])), (i, "chi2min")
+        assert set(d[0]) <= set(sels[i]) or precision == "f32"      # every drawn model belongs to the kept set
