@@ -82,6 +82,7 @@ NAMES = ("sidxs", "scales", "avs", "rvs", "cov_sar", "Ndim", "lnprob", "levid", 
          "dreds", "logwts")
 
 
+
 def test_device_posterior_replay_f64():
     dev, host, sels, nsel_dev = _run_both("f64", _case())
     assert nsel_dev == sum(len(s) for s in sels)
@@ -242,3 +243,48 @@ def test_memory_clip_matches_host(precision):
         assert abs(d[7] - hh[7]) < tol * max(1., abs(hh[7])), (i, "levid", d[7], hh[7])
         assert abs(d[8] - hh[8]) < (1e-7 if precision == "f64" else 2e-3) * max(1., abs(hh[8])), (i, "chi2min")
         assert set(d[0]) <= set(sels[i]) or precision == "f32"      # every drawn model belongs to the kept set
+
+
+def test_device_posterior_replay_ext_prior_f64():
+    """lnprior_ext (Gaussian priors on label columns, brutus/fitting.py:1995-2009) enters lnlike inside the sweep
+    and therefore both selections, the evidence and the draws: device and host paths agree draw for draw."""
+    from brutus_b200 import fitting
+    grid, lab, st, coords, lnprior = _case(nstar=4)
+    nstar, nmc, ndraws = len(st["flux"]), 10, 20
+    lmask = np.ones(1, dtype=[(n, bool) for n in lab.dtype.names])
+    bf = fitting.BruteForce(grid, lab, lmask, precision="f64")
+    rs = np.random.RandomState(17)
+    z = rs.normal(size=(grid.shape[0], 3, nmc))
+    u = rs.uniform(size=(nstar, 2, ndraws))
+    ext = {"feh": np.array([[-0.3, 0.4], [np.nan, 0.2], [-1.0, 0.3], [0.1, 0.5]]),
+           "mini": np.array([[1.0, 0.8], [0.7, 0.5], [np.nan, np.nan], [1.5, 1.0]])}
+    kw = dict(parallax=st["parallax"], parallax_err=st["parallax_err"], Nmc_prior=nmc, lnprior=lnprior, Ndraws=ndraws,
+              dustfile=None, data_coords=coords, lnprior_ext=ext)
+    try:
+        bf._z_override, bf._u_override = z, u
+        dev = list(bf._fit(st["flux"], st["err"], st["mask"].copy(), **kw))
+        bf._z_override = bf._u_override = None
+        # selections of the host path (pass 1), then the replay (pass 2)
+        sels, orig = [], fitting.lnpost_selected
+
+        def recording(*a, **k):
+            out = orig(*a, **k)
+            sels.append(out[0])
+            return out
+        fitting.lnpost_selected = recording
+        try:
+            first = list(bf._fit(st["flux"], st["err"], st["mask"].copy(), lngalprior=_galprior,
+                                 rstate=np.random.RandomState(1), **kw))
+        finally:
+            fitting.lnpost_selected = orig
+        sels = list(sels)
+        host = list(bf._fit(st["flux"], st["err"], st["mask"].copy(), lngalprior=_galprior,
+                            rstate=gp.ReplayRState(z, sels, u[:, 0], u[:, 1]), **kw))
+    finally:
+        bf.close()
+    assert len(first) == nstar
+    for i, (d, h) in enumerate(zip(dev, host)):
+        assert np.array_equal(d[0], h[0]), (i, "sidxs")
+        for k in (1, 2, 3, 6, 7, 8, 9, 10, 11, 12):
+            a, b = np.asarray(d[k], dtype=np.float64), np.asarray(h[k], dtype=np.float64)
+            assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-12)) < 1e-7, (i, NAMES[k])
