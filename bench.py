@@ -385,6 +385,17 @@ def run_b200(args):
                              "launch = that x the stars of the launch; 32 stars reuse a grid tile held in "
                              "registers, so the DRAM traffic (`traffic`, ncu, same per-launch basis) is far "
                              "lower and the kernel is FP32-issue bound (DESIGN.md section 5)",
+                     "issue": None if (traffic is None or cfg["nfilt"] != 8 or not clocks.get("sm_mhz")) else {
+                         "note": "what actually bounds the kernel: FP32 instruction issue. warp instructions per 32 "
+                                 "(model, star) pairs from the committed ncu capture x pairs swept / kernel time, "
+                                 "against 4 warp-instructions per clock per SM at the SM clock sampled during the run",
+                         "warp_inst_per_32_pairs": traffic.get("warp_instructions_per_32_model_star_pairs"),
+                         "achieved_ginst_s": traffic.get("warp_instructions_per_32_model_star_pairs", 0)
+                         * (cfg["nmodel"] / 32.0) * agg["magfit_star_passes"] / (agg["ms_magfit"] * 1e-3) / 1e9,
+                         "peak_ginst_s": 148 * 4 * clocks["sm_mhz"] * 1e6 / 1e9,
+                         "frac": traffic.get("warp_instructions_per_32_model_star_pairs", 0)
+                         * (cfg["nmodel"] / 32.0) * agg["magfit_star_passes"] / (agg["ms_magfit"] * 1e-3)
+                         / (148 * 4 * clocks["sm_mhz"] * 1e6)},
                      "kernel_share_of_step": agg["ms_magfit"] / dev_ms,
                      "launches": int(agg["magfit_launches"]),
                      "ms_per_launch": agg["ms_magfit"] / launches},

@@ -50,10 +50,12 @@ __global__ void k_retile(const float* __restrict__ src, float* __restrict__ dst,
     for (int k = 3 * nfilt; k < rs; k++) rows[i * rs + k] = 0.f;
     for (int j = 0; j < nfilt; j++)
         for (int c = 0; c < 3; c++) {
-            float v = 0.f;
-            if (i < nmodel)
-                v = layout == BF_LAYOUT_C ? src[(i * nfilt + j) * 3 + c]
-                                          : src[((int64_t)c * nfilt + j) * nmodel + i];
+            // the padding models (i >= nmodel) replicate the last real model: they can then take part in the
+            // sweep's per-star max-reductions unmasked (a duplicate never changes a maximum); only their
+            // candidate bits are suppressed
+            const int64_t ii = i < nmodel ? i : nmodel - 1;
+            const float v = layout == BF_LAYOUT_C ? src[(ii * nfilt + j) * 3 + c]
+                                                  : src[((int64_t)c * nfilt + j) * nmodel + ii];
             dst[((int64_t)c * nfilt + j) * npad + i] = v;
             rows[i * rs + c * nfilt + j] = v;
         }
@@ -62,7 +64,8 @@ __global__ void k_retile(const float* __restrict__ src, float* __restrict__ dst,
 template <typename T> __global__ void k_convert_labels(const double* src, T* dst, int64_t nmodel, int64_t npad, int nlabel) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npad) return;
-    for (int l = 0; l < nlabel; l++) dst[(int64_t)l * npad + i] = i < nmodel ? (T)src[(int64_t)l * nmodel + i] : T(0);
+    // padding entries replicate the last real model, like the grid's (k_retile)
+    for (int l = 0; l < nlabel; l++) dst[(int64_t)l * npad + i] = (T)src[(int64_t)l * nmodel + (i < nmodel ? i : nmodel - 1)];
 }
 
 // get_seds / _get_seds (brutus/utils.py:286-347) for n (model, Av, Rv) samples; one thread per (sample, band)

@@ -285,11 +285,10 @@ __global__ void __launch_bounds__(kTile) k_kprobe(const ProbeParams<T> p) {
     for (int t = threadIdx.x; t < kStarChunk * 2 * kProbeIter; t += kTile)
         s_red[t / (2 * kProbeIter)][t % (2 * kProbeIter)] = Enc<T>::enc(Num<T>::neg_inf());
     __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * p.tile_stride * kTile + threadIdx.x;
-    const bool valid = i < p.nmodel;
+    const int64_t i = (int64_t)blockIdx.x * p.tile_stride * kTile + threadIdx.x;   // < npad; padding replicates a real model
     const DevOpts<T> o = p.o;
     ModelRegs<T, NB> m;
-    load_model<T, NB>(p.grid, p.npad, valid ? i : 0, o, m);
+    load_model<T, NB>(p.grid, p.npad, i, o, m);
     const int lane = threadIdx.x & 31;
     const T ninf = Num<T>::neg_inf();
     T acc[2 * kProbeIter];
@@ -307,7 +306,7 @@ __global__ void __launch_bounds__(kTile) k_kprobe(const ProbeParams<T> p) {
         for (int k = 0; k < kProbeIter; k++) {
             T ell, delta;
             mag_iter<T, NB>(m, o, u, S, c, Q, Tm, e, r, A, rho, gs, ell, delta);
-            T l = valid ? ell : ninf;
+            T l = ell;
             T b = (delta >= o.mtol) ? l : ninf;
             l = warp_max_fast(l);
             b = warp_max_fast(b);
@@ -346,7 +345,9 @@ __global__ void __launch_bounds__(kTile) k_kprobe(const ProbeParams<T> p) {
 // (kStarChunk == 32), so the star loop contains no shared-memory atomics.
 // =================================================================================================
 template <typename T, int NB>
-__global__ void __launch_bounds__(kTile) k_magfit(const SweepParams<T> p) {
+// up to 8 bands: capped at 80 registers (3 CTAs = 24 warps per SM); left to itself ptxas takes 94 and the
+// kernel loses a third of its warps (measured 15.8 -> 16.4 ms per 1 000 stars)
+__global__ void __launch_bounds__(kTile, (NB <= 8 ? 3 : 2)) k_magfit(const SweepParams<T> p) {
     using U = typename Enc<T>::U;
     constexpr int NP = (NB + 1) / 2;
     static_assert(kStarChunk == 32, "lane <-> star mapping of the reductions");
@@ -399,17 +400,14 @@ __global__ void __launch_bounds__(kTile) k_magfit(const SweepParams<T> p) {
         // --- provisional lnlike / lnprob from the mag-fit values (final for every non-survivor) ---
         const int slot = s_slot[s];
         T ext = T(0);
-        if (p.nlabel > 0 && valid) ext = ext_prior<T>(p.labels, p.ext + (int64_t)slot * p.nlabel * 3, p.nlabel, p.npad, i);
+        if (p.nlabel > 0) ext = ext_prior<T>(p.labels, p.ext + (int64_t)slot * p.nlabel * 3, p.nlabel, p.npad, i);
         T lnl0, lq;
         lnl_lnprob<T>(r4.chi2, r4.den * r4.E * r4.E, r4.s, false, srow, o.dim_prior, ext, lnl0, lq);
-        l0 = valid ? l0 : ninf; b0 = valid ? b0 : ninf;
-        l1 = valid ? l1 : ninf; b1 = valid ? b1 : ninf;
-        const T lpv = valid ? lp : ninf;
-        const T lqv = valid ? lq : ninf;
+        // no `valid` masks on the reductions: padding models replicate the last real model (k_retile)
         l0 = warp_max_fast(l0); b0 = warp_max_fast(b0);
         l1 = warp_max_fast(l1); b1 = warp_max_fast(b1);
-        const T lpm = warp_max_fast(lpv);
-        const T lqm = warp_max_fast(lqv);
+        const T lpm = warp_max_fast(lp);
+        const T lqm = warp_max_fast(lq);
         if (lane == s) { acc0 = l0; acc1 = b0; acc2 = l1; acc3 = b1; acc4 = lpm; acc5 = lqm; }
         // --- candidate bit ---
         const T thr1 = Num<T>::max(s_snap[s][0], lpm) + ln_init_c;
