@@ -284,7 +284,8 @@ def run_b200(args):
         res = h.fit_batch(stars["flux"], stars["err"], stars["mask"], stars["parallax"],
                           stars["parallax_err"], coords=stars["coords"], opts=opts,
                           nmc_prior=args.nmc_prior, ndraws=args.ndraws, seed=12345, star_base=rank * nstar,
-                          mem_lim=8000.)   # fit()'s default mem_lim (brutus/fitting.py:1436)
+                          mem_lim=8000.,   # fit()'s default mem_lim (brutus/fitting.py:1436)
+                          copy=False)      # the draws stay in the library's pinned arena (like the records)
         wall = time.perf_counter() - t
         return res, wall, h.stats()
 

@@ -321,11 +321,12 @@ class Handle:
 
     def fit_batch(self, flux, err, mask, parallax=None, parallax_err=None, coords=None, ext_mean=None,
                   ext_std=None, opts=None, nmc_prior=50, ndraws=250, seed=0, use_gal_prior=True,
-                  gal=None, star_base=0, mem_lim=None, z_override=None, u_override=None):
+                  gal=None, star_base=0, mem_lim=None, z_override=None, u_override=None, copy=True):
         """The per-object body of ``BruteForce._fit`` on the device (``bf_fit_batch``): returns a dict
         with the reference's 13-tuple members as (Ndata, Ndraws) arrays (``sidxs, scales, avs, rvs,
         cov_sar, lnprob, dists, reds, dreds, logwts``) and per-object ``ndim, levid, chi2min, nsel,
-        n_iter``."""
+        n_iter``.  With ``copy=False`` the draw arrays are zero-copy views of the library's pinned result
+        arena, valid until the next ``fit_batch`` call on this handle."""
         f = np.ascontiguousarray(flux, dtype=np.float64)
         e = np.ascontiguousarray(err, dtype=np.float64)
         m = np.ascontiguousarray(mask).astype(np.uint8)
@@ -370,16 +371,7 @@ class Handle:
             po.u_override = u.ctypes.data
             keep.append(u)
         nd = po.ndraws
-        out = dict(sidxs=np.full((ns, nd), -99, dtype=np.int32), scales=np.zeros((ns, nd)),
-                   avs=np.zeros((ns, nd)), rvs=np.zeros((ns, nd)), cov_sar=np.zeros((ns, nd, 3, 3)),
-                   lnprob=np.zeros((ns, nd)), dists=np.zeros((ns, nd)), reds=np.zeros((ns, nd)),
-                   dreds=np.zeros((ns, nd)), logwts=np.zeros((ns, nd)))
         dr = Draws()
-        dr.model_idx = out["sidxs"].ctypes.data
-        for cname, key in (("scale", "scales"), ("av", "avs"), ("rv", "rvs"), ("cov_sar", "cov_sar"),
-                           ("lnprob", "lnprob"), ("dist", "dists"), ("red", "reds"), ("dred", "dreds"),
-                           ("logwt", "logwts")):
-            setattr(dr, cname, out[key].ctypes.data)
         ndim = np.zeros(ns, dtype=np.int32)
         nit = np.zeros((ns, 2), dtype=np.int32)
         nsel = np.zeros(ns, dtype=np.int64)
@@ -392,5 +384,18 @@ class Handle:
             _ptr(nit, C.c_int32), _ptr(nsel, C.c_int64), _ptr(levid, C.c_double),
             _ptr(chi2min, C.c_double), C.byref(dr)))
         del keep
+        out = {}
+        if ns > 0:
+            out["sidxs"] = np.ctypeslib.as_array(C.cast(dr.model_idx, C.POINTER(C.c_int32)), shape=(ns, nd))
+            for cname, key in (("scale", "scales"), ("av", "avs"), ("rv", "rvs"), ("lnprob", "lnprob"),
+                               ("dist", "dists"), ("red", "reds"), ("dred", "dreds"), ("logwt", "logwts")):
+                out[key] = np.ctypeslib.as_array(C.cast(getattr(dr, cname), C.POINTER(C.c_double)), shape=(ns, nd))
+            out["cov_sar"] = np.ctypeslib.as_array(C.cast(dr.cov_sar, C.POINTER(C.c_double)), shape=(ns, nd, 3, 3))
+            if copy:
+                out = {k: v.copy() for k, v in out.items()}
+        else:
+            out = dict(sidxs=np.zeros((0, nd), dtype=np.int32), cov_sar=np.zeros((0, nd, 3, 3)))
+            for key in ("scales", "avs", "rvs", "lnprob", "dists", "reds", "dreds", "logwts"):
+                out[key] = np.zeros((0, nd))
         out.update(ndim=ndim, n_iter=nit, nsel=nsel, levid=levid, chi2min=chi2min)
         return out

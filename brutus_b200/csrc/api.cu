@@ -463,6 +463,8 @@ template <typename T> struct Engine : EngineBase {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
     cudaEvent_t ev_rec[2] = {nullptr, nullptr}, ev_cp[2] = {nullptr, nullptr};
+    char* draw_arena = nullptr; // pinned host memory holding the posterior draws of the last bf_fit_batch
+    size_t draw_cap = 0;        // in draws (nstar * ndraws)
     char* arena = nullptr;      // pinned host memory holding the records of the last bf_sweep_batch
     int64_t arena_cap = 0;
     int64_t nmodel = 0, npad = 0, nwords = 0;
@@ -532,6 +534,7 @@ template <typename T> struct Engine : EngineBase {
             if (ev_cp[k]) cudaEventDestroy(ev_cp[k]);
         }
         if (arena) cudaFreeHost(arena);
+        if (draw_arena) cudaFreeHost(draw_arena);
         if (h_pin) cudaFreeHost(h_pin);
         h_int.release(); h_nsurv.release(); h_nsel.release(); h_red.release(); h_probe.release(); h_ncand.release();
         if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -1275,8 +1278,16 @@ template <typename T> struct Engine : EngineBase {
         CK(cudaSetDevice(device));
         if (!kt) { err = "bf_fit_batch: no grid (call bf_set_grid)"; return BF_E_NOGRID; }
         if (nstar < 0 || (nstar > 0 && (!flux || !errv || !mask)) || !opt || !po || !out || !levid || !chi2min) { err = "bf_fit_batch: null argument"; return BF_E_INVALID; }
-        if (!out->model_idx || !out->scale || !out->av || !out->rv || !out->cov_sar || !out->lnprob || !out->dist ||
-            !out->red || !out->dred || !out->logwt) { err = "bf_fit_batch: null output array"; return BF_E_INVALID; }
+        // library-owned pinned arena for the draws: [idx int32 | 8 double arrays | cov 9 doubles] x nstar*ndraws
+        const size_t ntot = (size_t)std::max<int64_t>(nstar, 1) * po->ndraws;
+        if (ntot > draw_cap) {
+            if (draw_arena) cudaFreeHost(draw_arena);
+            draw_arena = nullptr; draw_cap = 0;
+            CK(cudaHostAlloc((void**)&draw_arena, ntot * (17 * sizeof(double) + sizeof(int32_t)) + 64, cudaHostAllocPortable));
+            draw_cap = ntot;
+        }
+        double* const hd = (double*)draw_arena;                     // 8 arrays, then cov
+        int32_t* const hidx = (int32_t*)(draw_arena + ntot * 17 * sizeof(double));
         if (po->nmc_prior < 1 || po->ndraws < 1) { err = "bf_fit_batch: nmc_prior and ndraws must be >= 1"; return BF_E_INVALID; }
         if (po->use_gal_prior && !coords) { err = "`coord` must be provided if using the default Galactic model prior."; return BF_E_INVALID; }
         stats = bf_stats{};
@@ -1422,11 +1433,12 @@ template <typename T> struct Engine : EngineBase {
             CK(cudaEventRecord(evP1, stream));
             // ---- ndraws samples per star back to the caller's arrays ----
             const size_t off = (size_t)g.g0 * nd, cnt = (size_t)ng * nd, dst = (size_t)(g.s0 + g.g0) * nd;
-            CK(cudaMemcpyAsync(out->model_idx + dst, pp.o_idx + off, cnt * sizeof(int), cudaMemcpyDeviceToHost, stream));
-            double* hdst[8] = {out->scale, out->av, out->rv, out->lnprob, out->dist, out->red, out->dred, out->logwt};
+            CK(cudaMemcpyAsync(hidx + dst, pp.o_idx + off, cnt * sizeof(int), cudaMemcpyDeviceToHost, stream));
+            double* hdst[8];
+            for (int k = 0; k < 8; k++) hdst[k] = hd + (size_t)k * ntot;   // scale, av, rv, lnprob, dist, red, dred, logwt
             for (int k = 0; k < 8; k++)
                 CK(cudaMemcpyAsync(hdst[k] + dst, ob + k * per + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, stream));
-            CK(cudaMemcpyAsync(out->cov_sar + dst * 9, pp.o_cov + off * 9, cnt * 9 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(hd + 8 * ntot + dst * 9, pp.o_cov + off * 9, cnt * 9 * sizeof(double), cudaMemcpyDeviceToHost, stream));
             CK(cudaMemcpyAsync(levid + g.s0 + g.g0, pp.o_levid + g.g0, (size_t)ng * sizeof(double), cudaMemcpyDeviceToHost, stream));
             CK(cudaMemcpyAsync(chi2min + g.s0 + g.g0, pp.o_chi2min + g.g0, (size_t)ng * sizeof(double), cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));
@@ -1440,6 +1452,9 @@ template <typename T> struct Engine : EngineBase {
                                nullptr, nullptr, offsets.data(), batch_cap, post);
         d_zov.release(); d_uov.release();
         if (rc) return rc;
+        out->model_idx = hidx;
+        out->scale = hd; out->av = hd + ntot; out->rv = hd + 2 * ntot; out->lnprob = hd + 3 * ntot; out->dist = hd + 4 * ntot;
+        out->red = hd + 5 * ntot; out->dred = hd + 6 * ntot; out->logwt = hd + 7 * ntot; out->cov_sar = hd + 8 * ntot;
         if (ndim && par && perr)   // the parallax counts as one more datum (brutus/fitting.py:2028-2030)
             for (int64_t s = 0; s < nstar; s++)
                 if (std::isfinite(par[s]) && std::isfinite(perr[s])) ndim[s] += 1;

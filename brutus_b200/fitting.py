@@ -428,7 +428,8 @@ class BruteForce(object):
                 r = h.fit_batch(data[b0:b1], data_err[b0:b1], data_mask[b0:b1], parallax[b0:b1],
                                 parallax_err[b0:b1], coords=data_coords[b0:b1], ext_mean=em, ext_std=es,
                                 opts=opts, nmc_prior=Nmc_prior, ndraws=Ndraws,
-                                seed=seed, star_base=b0, mem_lim=mem_lim, **(self._post_test_hooks(b0, b1)))
+                                seed=seed, star_base=b0, mem_lim=mem_lim, copy=not _device_arrays,
+                                **(self._post_test_hooks(b0, b1)))
                 if _device_arrays:   # fit(): whole-batch arrays, no per-object Python loop
                     yield b0, b1, r
                     continue

@@ -191,11 +191,13 @@ void bf_default_post_options(bf_post_options* o);
  * (brutus/pdf.py:669, :694).  Each is float64 [nmodel] or NULL (0 / label absent). */
 int bf_set_model_priors(bf_handle* h, const double* lnprior, const double* feh, const double* loga);
 
-/* Posterior draws of every star, caller-allocated, [nstar*ndraws] each (cov: [nstar*ndraws*9]):
- * the 13-tuple BruteForce._fit yields per object (brutus/fitting.py:2059-2061). */
+/* Posterior draws of every star, [nstar*ndraws] each (cov_sar: [nstar*ndraws*9]): the 13-tuple
+ * BruteForce._fit yields per object (brutus/fitting.py:2059-2061).  Like bf_records, the arrays live in pinned
+ * host memory OWNED BY THE LIBRARY (the device writes them over PCIe at full link speed, no staging copy):
+ * bf_fit_batch fills in the pointers; they stay valid until the next bf_fit_batch on the handle or bf_destroy. */
 typedef struct bf_draws {
-    int32_t* model_idx;   /* sidxs  (-99 where a star has no selected model) */
-    double *scale, *av, *rv, *cov_sar, *lnprob, *dist, *red, *dred, *logwt;
+    const int32_t* model_idx;   /* sidxs  (-99 where a star has no selected model) */
+    const double *scale, *av, *rv, *cov_sar, *lnprob, *dist, *red, *dred, *logwt;
 } bf_draws;
 
 /* The per-star body of BruteForce._fit end to end on the device (brutus/fitting.py:1980-2061):
