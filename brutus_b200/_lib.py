@@ -133,7 +133,7 @@ def _ptr(a, t):
 
 def make_options(avlim=(0., 20.), av_gauss=(0., 1e6), rvlim=(1., 8.), rv_gauss=(3.32, 0.18),
                  dim_prior=True, ltol=3e-2, ltol_subthresh=1e-2, init_thresh=5e-3, wt_thresh=1e-3,
-                 max_iter=0, apply_parallax_clip=True, skip_d2h=False, select_slack=1.0):
+                 max_iter=0, apply_parallax_clip=True, skip_d2h=False, select_slack=0.5):
     if av_gauss is None:  # brutus/fitting.py:695-696
         av_gauss = (0., 1e6)
     o = Options()

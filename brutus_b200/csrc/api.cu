@@ -495,7 +495,7 @@ template <typename T> struct Engine : EngineBase {
     PinVec<int> h_nsel2;
 
     std::vector<T> h_stars, h_ext;
-    std::vector<int> h_list;
+    std::vector<int> h_list, h_kpred;
     std::vector<int64_t> h_base;
     PinVec<int> h_int, h_nsurv, h_nsel;      // control read-backs: mapped pinned memory (k_publish)
     PinVec<U> h_red, h_probe;
@@ -639,6 +639,7 @@ template <typename T> struct Engine : EngineBase {
         h_stars.resize((size_t)batch_cap * kStarStride);
         CK(h_int.resize((size_t)batch_cap * SI_COUNT));
         h_list.resize(batch_cap);
+        h_kpred.assign(batch_cap, 0);
         CK(h_red.resize((size_t)batch_cap * kNumRed));
         CK(h_probe.resize((size_t)batch_cap * 2 * kProbeIter));
         CK(h_ncand.resize(batch_cap));
@@ -704,13 +705,14 @@ template <typename T> struct Engine : EngineBase {
         return ms;
     }
 
-    // ---- phase 0: speculate the mag-iteration count of each star from a 1/16 subsample of the grid ----
+    // ---- phase 0: speculate the mag-iteration count of each star from a 1/32 subsample of the grid ----
     int probe_k(int ns, const DevOpts<T>& o, int max_iter) {
         const int64_t ntile = npad / kTile;
         if (ntile < 128 || max_iter < 2) return BF_OK;   // small grids: a re-sweep is cheaper than a probe
         ProbeParams<T> pp;
         pp.grid = d_grid.p; pp.npad = npad; pp.nmodel = nmodel; pp.stars = d_stars.p; pp.nstar = ns;
-        pp.tile_stride = 16; pp.o = o; pp.out = d_probe.p;
+        pp.tile_stride = 32; pp.o = o; pp.out = d_probe.p;   // 1/32 of the grid: measured best (16: +0.65 ms of probe; 64: more re-sweeps)
+        if (const char* e = getenv("BRUTUS_B200_PROBE_STRIDE")) pp.tile_stride = std::max(1, atoi(e));
         for (size_t k = 0; k < (size_t)ns * 2 * kProbeIter; k++) h_probe[k] = Enc<T>::enc(-std::numeric_limits<T>::infinity());
         CK(cudaMemcpyAsync(d_probe.p, h_probe.data(), (size_t)ns * 2 * kProbeIter * sizeof(U), cudaMemcpyHostToDevice, stream));
         phase_begin();
@@ -725,7 +727,13 @@ template <typename T> struct Engine : EngineBase {
                 const U* r = &h_probe[((size_t)s * kProbeIter + (k - 1)) * 2];
                 if (!(Enc<T>::dec(r[1]) > Enc<T>::dec(r[0]) + o.ln_init)) break;   // err < tol at iteration k
             }
-            h_int[s * SI_COUNT + SI_KSPEC] = std::min(k, max_iter);
+            // The probe only chooses between 1 and 2 for the first full sweep.  A sweep with K iterations tells
+            // whether the FULL grid converged at K-1 and at K, and the reference stops at the FIRST converged
+            // iteration, so K is only ever raised two at a time from iterations already known not to have
+            // converged (sweep()): starting a star at K >= 3 on the word of a subsample would leave its early
+            // iterations unverified.
+            h_int[s * SI_COUNT + SI_KSPEC] = std::min(std::min(k, 2), max_iter);
+            h_kpred[s] = k;   // the subsample's prediction steers how far a later sweep reaches (never past known + 2)
         }
         return BF_OK;
     }
@@ -771,13 +779,18 @@ template <typename T> struct Engine : EngineBase {
                 if (n_mag) n_mag[s] = ksp;
                 if (exact[s]) continue;
                 const U* r = &h_red[(size_t)s * kNumRed];
-                // brutus/fitting.py:252-263 restated on the two max-reductions
+                // brutus/fitting.py:252-263 restated on the two max-reductions.  Invariant: every iteration below
+                // ksp - 1 is already known NOT to have converged on the full grid (first sweep at ksp <= 2, then
+                // +2 only after a sweep that saw ksp - 1 and ksp unconverged), so the first converged iteration
+                // among {ksp - 1, ksp} is the reference's stopping iteration.
                 const bool conv_prev = ksp >= 2 && !(Enc<T>::dec(r[RED_B0]) > Enc<T>::dec(r[RED_L0]) + o.ln_init);
                 const bool conv_last = !(Enc<T>::dec(r[RED_B1]) > Enc<T>::dec(r[RED_L1]) + o.ln_init);
                 if (conv_prev) {           // the reference would have stopped one iteration earlier
                     ksp -= 1; exact[s] = 1; next.push_back(s);
                 } else if (!conv_last && ksp < max_iter) {
-                    ksp = std::min(ksp + 2, max_iter); next.push_back(s);
+                    // next sweep: iterations (ksp, ksp + 1) if the probe expects convergence at ksp + 1, else
+                    // (ksp + 1, ksp + 2); either way contiguous with what is known
+                    ksp = std::min(h_kpred[s] == ksp + 1 ? ksp + 1 : ksp + 2, max_iter); next.push_back(s);
                 } else {
                     exact[s] = 1;
                 }
@@ -885,6 +898,7 @@ template <typename T> struct Engine : EngineBase {
             h_int[s * SI_COUNT + SI_NDIM] = sp.ndim;
             // initial speculation: 2 mag iterations (what the reference needs in the common case)
             h_int[s * SI_COUNT + SI_KSPEC] = std::min(2, max_iter);
+            h_kpred[s] = 0;
             h_int[s * SI_COUNT + SI_ACTIVE] = 0;
             h_int[s * SI_COUNT + SI_NFLUX] = 0;
             if (ndim_out) ndim_out[s] = sp.ndim;
@@ -1480,7 +1494,7 @@ void bf_default_options(bf_options* o) {
     o->rvlim[0] = 1.; o->rvlim[1] = 8.;
     o->rv_gauss[0] = 3.32; o->rv_gauss[1] = 0.18;
     o->ltol = 3e-2; o->ltol_subthresh = 1e-2; o->init_thresh = 5e-3; o->wt_thresh = 1e-3;
-    o->select_slack = 1.0;
+    o->select_slack = 0.5;
     o->dim_prior = 1; o->max_iter = 0; o->apply_parallax_clip = 1; o->skip_d2h = 0;
 }
 

@@ -51,7 +51,7 @@ typedef struct bf_options {
     double ltol_subthresh;  /* default 1e-2         */
     double init_thresh;     /* default 5e-3         */
     double wt_thresh;       /* default 1e-3 (bf_sweep_batch only) */
-    double select_slack;    /* default 1.0 (bf_sweep_batch only): the sweep keeps as selection candidates the
+    double select_slack;    /* default 0.5 (bf_sweep_batch only): the sweep keeps as selection candidates the
                                models whose provisional lnprob is within ln(wt_thresh) - select_slack of the
                                running maximum.  Results do not depend on it: if the final max(lnprob) falls
                                more than select_slack below the provisional one the star is redone with every
