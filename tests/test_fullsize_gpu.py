@@ -147,3 +147,23 @@ def test_permutation_and_batch_independence(case):
     one = _sweep(c, st, slice(1, 2))
     ra, rb = _star(one, 0), _star(full, 1)
     assert np.array_equal(ra["model_idx"], rb["model_idx"]) and np.array_equal(ra["chi2"], rb["chi2"])
+
+
+def test_result_independent_of_probe_subsample(case):
+    """The iteration-count probe (k_kprobe on a subsample of the grid) only speeds the sweep up: iteration
+    counts, survivor counts and records must not depend on which subsample it looks at."""
+    import os
+    c, st = case, case["st"]
+    outs = []
+    try:
+        for stride in ("4", "64", "1000000"):          # the last one: the probe sees a single tile
+            os.environ["BRUTUS_B200_PROBE_STRIDE"] = stride
+            outs.append(_sweep(c, st))
+    finally:
+        os.environ.pop("BRUTUS_B200_PROBE_STRIDE", None)
+    assert outs[0]["n_iter"][:, 0].max() >= 2
+    for o in outs[1:]:
+        assert np.array_equal(o["n_iter"], outs[0]["n_iter"])
+        assert np.array_equal(o["n_surv"], outs[0]["n_surv"])
+        assert np.array_equal(o["offsets"], outs[0]["offsets"])
+        assert np.array_equal(o["model_idx"], outs[0]["model_idx"]) and np.array_equal(o["chi2"], outs[0]["chi2"])
