@@ -360,6 +360,10 @@ __global__ void k_publish(const uint32_t* __restrict__ src, uint32_t* __restrict
 template <typename P> struct PinVec {
     P* p = nullptr;
     size_t n = 0;
+    PinVec() = default;
+    PinVec(const PinVec&) = delete;
+    PinVec& operator=(const PinVec&) = delete;
+    ~PinVec() { release(); }
     cudaError_t resize(size_t want) {
         if (want <= n) return cudaSuccess;
         if (p) cudaFreeHost(p);
@@ -378,6 +382,10 @@ template <typename P> struct PinVec {
 template <typename P> struct DevBuf {
     P* p = nullptr;
     size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }   // temporaries on error paths (CK returns early) do not leak
     cudaError_t ensure(size_t want) {
         if (want <= n) return cudaSuccess;
         if (p) cudaFree(p);
