@@ -192,6 +192,34 @@ def gen_offsets(fit):
     print("wrote offsets")
 
 
+LNPOST_CASE = dict(name="mixed_9band", Nmc_prior=15, rseed=5, mem_lims=(8000., 0.75))
+
+
+def gen_lnpost(fit):
+    """Golden outputs of the reference's `lnpost` (brutus/fitting.py:823-1107) on the `loglike` results of the
+    mixed_9band case: pins brutus_b200.fitting.lnpost_selected (the host posterior path, and the checker of the
+    device posterior) on the CPU.  The second mem_lim makes the memory clip (:1029-1036) bite."""
+    c = LNPOST_CASE
+    grid, labels, st, kw = build_case(c["name"])
+    gF = np.array(grid, order="F")
+    lnprior = -0.1 * (labels["Mr"] - 5.) ** 2
+    out = {}
+    for i in range(len(st["flux"])):
+        m = st["mask"][i].copy()
+        res = fit.loglike(st["flux"][i], st["err"][i], m, gF, return_vals=True, parallax=st["parallax"][i],
+                          parallax_err=st["parallax_err"][i], **kw)
+        for k, mem in enumerate(c["mem_lims"]):
+            r = fit.lnpost(tuple(np.array(x) if np.ndim(x) else x for x in res), parallax=st["parallax"][i],
+                           parallax_err=st["parallax_err"][i], coord=np.zeros(2), Nmc_prior=c["Nmc_prior"],
+                           lnprior=lnprior, wt_thresh=1e-3, lngalprior=toy_galprior, apply_av_prior=False,
+                           dlabels=labels, avlim=(0., 20.), rvlim=(1., 8.), mem_lim=mem,
+                           rstate=np.random.RandomState(c["rseed"]))
+            for key, val in zip(("sel", "cov_sar", "lnp", "dists", "reds", "dreds", "logwts"), r):
+                out["%s_%d_%d" % (key, i, k)] = np.asarray(val)
+    np.savez_compressed(os.path.join(GOLD, "lnpost.npz"), **out)
+    print("wrote lnpost")
+
+
 NGC2682_FITS = os.path.join(ref_import.REFERENCE_ROOT, "demos", "NGC_2682.fits")
 NGC2682_GRID = dict(nmodel=4_000, nfilt=8, seed=1050, kind="locus")
 
@@ -285,7 +313,7 @@ def gen_ngc2682(fit):
 if __name__ == "__main__":
     fit = ref_import.import_reference()
     os.makedirs(GOLD, exist_ok=True)
-    only = [a for a in sys.argv[1:] if a in LOGLIKE_CASES or a in ("galprior", "offsets", "ngc2682")]
+    only = [a for a in sys.argv[1:] if a in LOGLIKE_CASES or a in ("galprior", "offsets", "ngc2682", "lnpost")]
     gen_loglike(fit, only=only)
     if not only:
         gen_fit(fit)
@@ -293,5 +321,7 @@ if __name__ == "__main__":
         gen_galprior(fit)
     if not only or "offsets" in sys.argv[1:]:
         gen_offsets(fit)
+    if not only or "lnpost" in sys.argv[1:]:
+        gen_lnpost(fit)
     if (not only or "ngc2682" in sys.argv[1:]) and os.path.exists(NGC2682_FITS):
         gen_ngc2682(fit)
