@@ -11,7 +11,7 @@ tests.  Nothing here computes.
 """
 import numpy as np
 
-__all__ = ["shard_bounds", "broadcast_grid", "gather_catalogue"]
+__all__ = ["shard_bounds", "broadcast_grid", "gather_catalogue", "fit_shard", "gather_draws"]
 
 
 def shard_bounds(ndata, world, rank):
@@ -83,5 +83,35 @@ def gather_catalogue(local, ndata, dist=None, dst=0):
     merged["icov6"] = (np.concatenate([o["icov6"] for o in out], axis=1)
                        if out[0].get("icov6") is not None else None)
     if len(merged["ndim"]) != ndata:
+        raise RuntimeError("shards do not add up to the catalogue")
+    return merged
+
+
+def fit_shard(handle, data, data_err, data_mask, parallax=None, parallax_err=None, coords=None, world=1, rank=0,
+              **fit_kwargs):
+    """This rank's shard of the catalogue through ``Handle.fit_batch`` (the per-object body of ``BruteForce.fit``
+    on the device).  ``star_base`` is set to the shard's first catalogue index, so every star gets the random
+    numbers it would get in a single-process run: the gathered result does not depend on the number of GPUs.
+    Returns ``(lo, hi, result)``."""
+    lo, hi = shard_bounds(len(data), world, rank)
+    cut = lambda a: None if a is None else np.asarray(a)[lo:hi]
+    res = handle.fit_batch(cut(data), cut(data_err), cut(data_mask), cut(parallax), cut(parallax_err),
+                           coords=cut(coords), star_base=lo, **fit_kwargs)
+    return lo, hi, res
+
+
+def gather_draws(local, ndata, dist=None, dst=0):
+    """Concatenate per-shard ``fit_batch`` results (every member is a per-star array) in catalogue order on
+    rank ``dst``; None elsewhere.  Final host-side gather, outside the hot loop."""
+    if dist is None:
+        return local
+    rank, world = dist.get_rank(), dist.get_world_size()
+    payload = {k: np.array(v) for k, v in local.items()}      # copies: the draws may be views of a pinned arena
+    out = [None] * world if rank == dst else None
+    dist.gather_object(payload, out, dst=dst)
+    if rank != dst:
+        return None
+    merged = {k: np.concatenate([o[k] for o in out]) for k in out[0]}
+    if len(merged["levid"]) != ndata:
         raise RuntimeError("shards do not add up to the catalogue")
     return merged

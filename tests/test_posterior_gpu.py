@@ -288,3 +288,23 @@ def test_device_posterior_replay_ext_prior_f64():
         for k in (1, 2, 3, 6, 7, 8, 9, 10, 11, 12):
             a, b = np.asarray(d[k], dtype=np.float64), np.asarray(h[k], dtype=np.float64)
             assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-12)) < 1e-7, (i, NAMES[k])
+
+
+def test_fit_shards_equal_single_call():
+    """Star-sharded fit (brutus_b200.shard.fit_shard: star_base = first catalogue index of the shard) gives every
+    star the same posterior samples as one call over the whole catalogue -- here three shards on one GPU."""
+    from brutus_b200 import _lib, shard
+    grid, lab, st, coords, lnprior = _case(nmodel=2000, nstar=7)
+    h = _lib.Handle(0, "f32")
+    try:
+        h.set_grid(grid)
+        h.set_model_priors(lnprior=lnprior, feh=lab["feh"], loga=np.minimum(lab["loga"], 10.1))
+        kw = dict(nmc_prior=12, ndraws=20, seed=77)
+        one = h.fit_batch(st["flux"], st["err"], st["mask"], st["parallax"], st["parallax_err"], coords=coords, **kw)
+        parts = [shard.fit_shard(h, st["flux"], st["err"], st["mask"], st["parallax"], st["parallax_err"],
+                                 coords=coords, world=3, rank=r, **kw) for r in range(3)]
+    finally:
+        h.close()
+    assert [p[:2] for p in parts] == [shard.shard_bounds(7, 3, r) for r in range(3)]
+    for k in one:
+        assert np.array_equal(np.concatenate([p[2][k] for p in parts]), one[k]), k

@@ -54,6 +54,20 @@ def oracle_sweep(grid, st, lo, hi):
     return res
 
 
+class _FakeFitHandle(object):
+    """Stands in for brutus_b200._lib.Handle.fit_batch on the CPU: per-star outputs that depend only on the star's
+    data and on its catalogue index (as the real call's counter-based generator does through star_base)."""
+
+    def fit_batch(self, flux, err, mask, parallax=None, parallax_err=None, coords=None, star_base=0, ndraws=4, **kw):
+        n = len(flux)
+        idx = star_base + np.arange(n)
+        rs = [np.random.RandomState(1000 + int(i)) for i in idx]
+        draws = np.array([r.randint(0, 3000, ndraws) for r in rs]).reshape(n, ndraws)
+        return dict(sidxs=draws.astype(np.int32), levid=np.asarray(flux).sum(axis=1) + idx,
+                    dists=np.array([r.uniform(size=ndraws) for r in rs]).reshape(n, ndraws),
+                    ndim=np.asarray(mask).sum(axis=1).astype(np.int32))
+
+
 def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, HERE)
@@ -71,12 +85,21 @@ def _worker(rank, world, port, q):
         lo, hi = shard_bounds(ndata, world, rank)
         local = oracle_sweep(grid, st, lo, hi)                                 # hot loop: no communication
         merged = gather_catalogue(local, ndata, dist=dist)
+        # the fit-level call: shards carry their first catalogue index (star_base), results gather in order
+        from brutus_b200.shard import fit_shard, gather_draws
+        flo, fhi, fres = fit_shard(_FakeFitHandle(), st["flux"], st["err"], st["mask"], st["parallax"],
+                                   st["parallax_err"], coords=st["coords"], world=world, rank=rank, ndraws=4)
+        assert (flo, fhi) == (lo, hi)
+        draws = gather_draws(fres, ndata, dist=dist)
         if rank == 0:
             whole = oracle_sweep(grid, st, 0, ndata)
             ok = all(np.array_equal(merged[k], whole[k]) for k in whole)
+            one = _FakeFitHandle().fit_batch(st["flux"], st["err"], st["mask"], st["parallax"], st["parallax_err"],
+                                             coords=st["coords"], star_base=0, ndraws=4)
+            ok = ok and all(np.array_equal(draws[k], one[k]) for k in one)
             q.put(("ok", ok, int(merged["offsets"][-1])))
         else:
-            assert merged is None
+            assert merged is None and draws is None
     except Exception as e:  # pragma: no cover
         q.put(("error", repr(e), rank))
         raise
