@@ -69,3 +69,29 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "oracle" not in txt.replace("# oracle", ""), (f, "product code must not touch oracle/")
+
+
+def test_ctypes_structs_match_the_header_as_compiled(tmp_path):
+    """sizeof / offsetof of every struct of include/brutus_b200.h as a C compiler sees them == the ctypes mirror."""
+    import subprocess
+    from brutus_b200 import _lib
+    src = tmp_path / "sz.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "brutus_b200.h"
+int main(void) {
+    printf("%zu %zu %zu %zu %zu %zu\n", sizeof(bf_options), sizeof(bf_stats), sizeof(bf_records), sizeof(bf_gal_params),
+           sizeof(bf_post_options), sizeof(bf_draws));
+    printf("%zu %zu %zu %zu %zu\n", offsetof(bf_options, dim_prior), offsetof(bf_stats, ms_post),
+           offsetof(bf_post_options, star_base), offsetof(bf_post_options, gal), offsetof(bf_post_options, z_override));
+    return 0;
+}''')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True).split()
+    sizes = [C.sizeof(t) for t in (_lib.Options, _lib.Stats, _lib.Records, _lib.GalParams, _lib.PostOptions, _lib.Draws)]
+    offs = [_lib.Options.dim_prior.offset, _lib.Stats.ms_post.offset, _lib.PostOptions.star_base.offset,
+            _lib.PostOptions.gal.offset, _lib.PostOptions.z_override.offset]
+    assert [int(x) for x in out[:6]] == sizes
+    assert [int(x) for x in out[6:]] == offs
