@@ -392,19 +392,20 @@ class BruteForce(object):
         parallax = np.asarray(parallax, dtype=np.float64)
         parallax_err = np.asarray(parallax_err, dtype=np.float64)
         dlabels = self.models_labels if apply_dlabels else None
-        h = self._get_handle()
         device_posterior = lngalprior is None
         if device_posterior and lndustprior is not None:
             raise NotImplementedError("a user `lndustprior` needs a user `lngalprior` too (host posterior path)")
         if device_posterior and Nmc_prior < 1:
             raise NotImplementedError("Nmc_prior = 0 is only supported on the host posterior path")
         ext_keys = []
-        if lnprior_ext is not None:
+        if lnprior_ext is not None:   # validated before any device work, like every other argument error
             ext_keys = list(lnprior_ext.keys())
             for k in ext_keys:
                 if k not in self.models_labels.dtype.names:
                     raise ValueError("Provided `lnprior_ext` has keys which do not match the "
                                      "underlying model labels.")
+        h = self._get_handle()
+        if ext_keys:
             h.set_labels(np.stack([np.asarray(self.models_labels[k], dtype=np.float64) for k in ext_keys]))
         elif h.nlabel:
             h.set_labels(np.zeros((0, self.NMODEL)))

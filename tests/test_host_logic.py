@@ -1,0 +1,95 @@
+"""CPU: the host-side mirror of the reference's argument handling (no GPU is touched: every error below is raised
+before the first device call, like in the reference) and the small prior functions it carries."""
+import numpy as np
+import pytest
+
+import golden_cases as gc
+from brutus_b200 import fitting, mock
+from oracle import ref_import
+
+
+@pytest.fixture(scope="module")
+def bf_case():
+    grid, labels = mock.make_grid(500, 6, seed=3)
+    st = mock.make_stars(grid, 4, seed=4)
+    lmask = np.ones(1, dtype=[("Mr", bool), ("feh", bool)])
+    return fitting.BruteForce(grid, labels, lmask), st
+
+
+def _kw(st, **over):
+    kw = dict(parallax=st["parallax"], parallax_err=st["parallax_err"], lnprior=np.zeros(500),
+              lngalprior=gc.toy_galprior, data_coords=np.zeros((4, 2)), verbose=False)
+    kw.update(over)
+    return kw
+
+
+def test_threshold_order_is_checked_first(bf_case, tmp_path):      # brutus/fitting.py:1305-1308
+    bf, st = bf_case
+    with pytest.raises(ValueError, match="threshold"):
+        bf.fit(st["flux"], st["err"], st["mask"], np.arange(4), str(tmp_path / "a"),
+               **_kw(st, logl_initthresh=0.5, ltol_subthresh=1e-2))
+
+
+def test_parallax_needs_its_error(bf_case, tmp_path):              # brutus/fitting.py:1325-1327
+    bf, st = bf_case
+    with pytest.raises(ValueError, match="parallax"):
+        bf.fit(st["flux"], st["err"], st["mask"], np.arange(4), str(tmp_path / "b"), **_kw(st, parallax_err=None))
+
+
+def test_fewer_than_four_bands(bf_case, tmp_path):                 # brutus/fitting.py:1413-1420
+    bf, st = bf_case
+    bad = st["mask"].copy()
+    bad[1, :3] = False
+    with pytest.raises(ValueError, match="fewer than 4 bands"):
+        bf.fit(st["flux"], st["err"], bad, np.arange(4), str(tmp_path / "c"), **_kw(st))
+    # mag_max / merr_max cuts count too (:1404-1411): a faint-magnitude cut that removes every band
+    with pytest.raises(ValueError):
+        bf.fit(st["flux"], st["err"], st["mask"], np.arange(4), str(tmp_path / "d"), **_kw(st, mag_max=-100.))
+
+
+def test_default_prior_needs_coordinates(bf_case, tmp_path):       # brutus/fitting.py:1362-1365
+    bf, st = bf_case
+    with pytest.raises(ValueError, match="data_coords"):
+        bf.fit(st["flux"], st["err"], st["mask"], np.arange(4), str(tmp_path / "e"),
+               **_kw(st, lngalprior=None, data_coords=None, dustfile=None))
+
+
+def test_lnprior_ext_keys_are_validated(bf_case):                  # brutus/fitting.py:1972-1976
+    bf, st = bf_case
+    with pytest.raises(ValueError, match="lnprior_ext"):
+        next(bf._fit(st["flux"], st["err"], st["mask"], lnprior_ext={"nope": np.zeros((4, 2))},
+                     **{k: v for k, v in _kw(st).items() if k != "verbose"}))
+
+
+def test_loglike_argument_errors():
+    grid, _ = mock.make_grid(200, 5, seed=5)
+    st = mock.make_stars(grid, 1, seed=6)
+    with pytest.raises(ValueError, match="initial threshold"):    # brutus/fitting.py:691-693
+        fitting.loglike(st["flux"][0], st["err"][0], st["mask"][0].copy(), grid, init_thresh=0.5)
+    with pytest.raises(NotImplementedError):
+        fitting.loglike(st["flux"][0], st["err"][0], st["mask"][0].copy(), grid, av_init=np.zeros(200))
+
+
+def test_imf_prior_is_normalised_and_broken_at_half_a_solar_mass():
+    m = np.linspace(0.0801, 100., 2_000_001)
+    p = np.exp(fitting.imf_lnprior(m))
+    assert abs(np.trapezoid(p, m) - 1.) < 2e-3          # brutus/pdf.py:38-108 normalises over [0.08, inf)
+    assert np.all(np.isneginf(fitting.imf_lnprior(np.array([0.05, 0.08]))))
+    lo, hi = fitting.imf_lnprior(np.array([0.4999999, 0.5000001]))
+    assert abs(lo - hi) < 1e-5                          # continuous at the break
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
+def test_small_priors_match_the_live_reference():
+    ref_import.import_reference()
+    from brutus import pdf as rpdf
+    rs = np.random.RandomState(8)
+    m = 10. ** rs.uniform(-1.2, 1.5, 500)
+    assert np.allclose(fitting.imf_lnprior(m), rpdf.imf_lnprior(m), rtol=1e-12, atol=0, equal_nan=True)
+    p = rs.uniform(0.05, 3., 200)
+    for pm, pe in ((1.0, 0.1), (0.2, 0.1), (np.nan, 0.1), (-0.3, 0.05)):
+        assert np.allclose(fitting.parallax_lnprior(p, pm, pe), rpdf.parallax_lnprior(p, pm, pe), rtol=1e-12)
+        s, se = p ** 2, rs.uniform(0.01, 0.5, 200)
+        assert np.allclose(fitting.scale_parallax_lnprior(s, se, pm, pe), rpdf.scale_parallax_lnprior(s, se, pm, pe),
+                           rtol=1e-12)
