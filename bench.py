@@ -174,7 +174,8 @@ def run_reference(args):
     from oracle import oracle
     oracle.build()
     nt = host_cores()
-    per_step = max(nt, 8) if cfg["nmodel"] <= 1_000_000 else max(nt // 2, 4)
+    # a bounded sample per step: ~3 s of work on all cores at C2 (the whole run stays within a minute or two)
+    per_step = max(4 * nt, 8) if cfg["nmodel"] <= 1_000_000 else max(nt, 4)
     cfg_s = dict(cfg, nstar=per_step * (args.steps + args.warmup))
     stars = make_stars(args.config, cfg_s, grid, 0)
     times = []
@@ -410,7 +411,8 @@ def run_b200(args):
     }
     if world == 1 and not args.no_cpu:
         nt_probe = host_cores()
-        nsample = max(8, min(2 * nt_probe, 64)) if cfg["nmodel"] <= 1_000_000 else max(4, min(nt_probe, 32))
+        # ~10-15 s of CPU work: 16 stars per core at C2 (0.7 s per star and core), 4 per core on the 3M-model grids
+        nsample = max(8, 16 * nt_probe) if cfg["nmodel"] <= 1_000_000 else max(4, 4 * nt_probe)
         rate, nt, dt = cpu_sample(cfg, grid, stars, 0, min(nsample, nstar))
         line["cpu_baseline"] = {"value": rate, "unit": "stars/s", "cores": nt, "kind": "port",
                                 "sample": "first %d stars of the same catalogue and grid, %.1f s, OpenMP over "
