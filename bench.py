@@ -294,6 +294,9 @@ def run_b200(args):
         step(True)
         step(False)
         step_fit()
+    tracing = bool(int(os.environ.get("BRUTUS_B200_TRACE", "0") or 0))
+    if tracing:
+        h.trace()   # drop the warm-up's entries
     sampler = ClockSampler(local_rank)
     sampler.start()
     # ---- timed region 1: K steps, device time from CUDA events (value, roofline) ----
@@ -307,6 +310,9 @@ def run_b200(args):
         for k, v in st.items():
             agg[k] = agg.get(k, 0) + v
     barrier()
+    if tracing:   # per-kernel CUDA-event times of the device-timed steps (stderr; the JSON line stays alone on stdout)
+        for name, (cnt, ms) in sorted(h.trace().items(), key=lambda kv: -kv[1][1]):
+            sys.stderr.write("trace value-steps  %-22s %6d launches %10.3f ms/step\n" % (name, cnt, ms / args.steps))
     # ---- timed region 2: K steps end to end through the C ABI with host buffers ----
     wall_s = 0.0
     agg_e = {}
@@ -325,6 +331,8 @@ def run_b200(args):
         for k, v in st.items():
             agg_f[k] = agg_f.get(k, 0) + v
     barrier()
+    if tracing:
+        h.trace()
     t_region = time.perf_counter() - t_region
     clocks = sampler.summary()
     if world > 1:

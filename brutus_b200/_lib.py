@@ -21,7 +21,7 @@ SYMBOLS = ("bf_default_options", "bf_create", "bf_destroy", "bf_last_error", "bf
            "bf_set_grid_device", "bf_set_labels", "bf_loglike_full", "bf_sweep_batch",
            "bf_get_stats", "bf_flush_l2", "bf_device_count", "bf_version",
            "bf_default_gal_params", "bf_default_post_options", "bf_set_model_priors", "bf_fit_batch",
-           "bf_get_seds")
+           "bf_get_seds", "bf_get_trace")
 
 
 class BrutusCudaError(RuntimeError):
@@ -52,7 +52,8 @@ class Stats(C.Structure):
                 ("resweeps", C.c_int64), ("candidates", C.c_int64), ("fallbacks", C.c_int64),
                 ("survivors", C.c_int64),
                 ("selected", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-                ("ms_post", C.c_double), ("selected2", C.c_int64), ("clipped", C.c_int64)]
+                ("ms_post", C.c_double), ("selected2", C.c_int64), ("clipped", C.c_int64),
+                ("fixups", C.c_int64), ("flux_more_launches", C.c_int64), ("regroups", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -120,6 +121,8 @@ def load():
                                  C.POINTER(PostOptions), i32p, i32p, i64p, dp, dp, C.POINTER(Draws)]
     lib.bf_get_seds.argtypes = [vp, C.c_int64, i32p, dp, dp, C.c_int32, dp, dp, dp]
     lib.bf_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.bf_get_trace.argtypes = [vp]
+    lib.bf_get_trace.restype = C.c_char_p
     lib.bf_flush_l2.argtypes = [vp]
     lib.bf_device_count.restype = C.c_int
     lib.bf_version.restype = C.c_char_p
@@ -219,6 +222,15 @@ class Handle:
         s = Stats()
         self._lib.bf_get_stats(self._h, C.byref(s))
         return s.as_dict()
+
+    def trace(self):
+        """Per-kernel device times since the last call (needs BRUTUS_B200_TRACE=1 when the handle is created):
+        ``{kernel: (launches, ms)}``."""
+        out = {}
+        for line in self._lib.bf_get_trace(self._h).decode().splitlines():
+            name, n, _, ms, _ = line.split()
+            out[name] = (int(n), float(ms))
+        return out
 
     def loglike_full(self, flux, err, mask, parallax, parallax_err, opts, want_icov=True):
         n = self.nmodel

@@ -12,7 +12,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <limits>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -54,8 +56,13 @@ __global__ void k_retile(const float* __restrict__ src, float* __restrict__ dst,
             // sweep's per-star max-reductions unmasked (a duplicate never changes a maximum); only their
             // candidate bits are suppressed
             const int64_t ii = i < nmodel ? i : nmodel - 1;
-            const float v = layout == BF_LAYOUT_C ? src[(ii * nfilt + j) * 3 + c]
-                                                  : src[((int64_t)c * nfilt + j) * nmodel + ii];
+            float v = layout == BF_LAYOUT_C ? src[(ii * nfilt + j) * 3 + c]
+                                            : src[((int64_t)c * nfilt + j) * nmodel + ii];
+            // A band the caller masks out is neutralised by zero star weights, which only works on finite
+            // coefficients: sentinel (NaN / inf) entries are stored as 0.  The reference slices masked bands
+            // away (brutus/fitting.py:714) and never reads them; a sentinel in a band that IS used makes the
+            // reference return NaN for that model, here it is fitted with a zero coefficient.
+            if (!isfinite(v)) v = 0.f;
             dst[((int64_t)c * nfilt + j) * npad + i] = v;
             rows[i * rs + c * nfilt + j] = v;
         }
@@ -127,10 +134,13 @@ __device__ __forceinline__ int block_exscan_1024(int v, int* s_w, int& total) {
     return incl - v;
 }
 
-// one CTA per star: exclusive scan of the popcounts of the star's candidate words -> wpre; total -> ncand
+// one CTA per star: exclusive scan of the popcounts of the star's bitmap words -> wpre; total -> nbits.
+// Run on the candidate map (candidate counts, when a group has to be split) and, after k_sel cleared the
+// bits of the candidates that failed the selection, on the selection map: wpre[word] + popc(lower bits) is
+// then the position of a selected model within its star, in ascending model order.
 __global__ void __launch_bounds__(1024) k_cand_scan(const uint32_t* __restrict__ cand, int* __restrict__ wpre,
                                                     const int* __restrict__ list, int64_t nwords,
-                                                    int64_t* __restrict__ ncand) {
+                                                    int64_t* __restrict__ nbits) {
     __shared__ int s_w[32];
     const int slot = list[blockIdx.x];
     const uint32_t* c = cand + (int64_t)slot * nwords;
@@ -144,48 +154,105 @@ __global__ void __launch_bounds__(1024) k_cand_scan(const uint32_t* __restrict__
         if (t < nwords) w[t] = carry + ex;
         carry += tot;
     }
-    if (threadIdx.x == 0) ncand[slot] = carry;
+    if (threadIdx.x == 0) nbits[slot] = carry;
 }
 
-// candidate map -> ordered candidate records (model, star); one thread per 32-model word
-template <typename T>
-__global__ void __launch_bounds__(256) k_expand(const uint32_t* __restrict__ cand, const int* __restrict__ wpre,
-                                                const int64_t* __restrict__ base, const int* __restrict__ list,
-                                                int64_t nwords, PoolArrays<T> pool) {
-    const int slot = list[blockIdx.y];
-    const int64_t w = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (w >= nwords) return;
-    uint32_t word = cand[(int64_t)slot * nwords + w];
-    if (!word) return;
-    int64_t pos = base[slot] + wpre[(int64_t)slot * nwords + w];
-    while (word) {
-        const int b = __ffs(word) - 1;
-        word &= word - 1;
-        pool.model[pos] = (int)(w * 32 + b);
-        pool.star[pos] = slot;
-        pos++;
+// ---- passes over the n records the sweep appended --------------------------------------------------------
+template <typename T> struct PassParams {
+    PoolArrays<T> pool;
+    int64_t n;
+    const T* stars;
+    int* star_int;
+    typename Enc<T>::U* red;
+    DevOpts<T> o;
+    int* fixlist;      // k_cull: records refined as likely survivors that are not survivors
+    int* nfix;
+    // k_final
+    int64_t npad;
+    const T* labels;   // [nlabel][npad]
+    const T* ext;      // [batch][nlabel][3]
+    int nlabel;
+    // k_sel
+    uint32_t* cand;
+    int64_t nwords;
+};
+
+// a record is live if its star has not been swept again since (another iteration count, or every model
+// as a candidate)
+template <typename T> __device__ __forceinline__ bool rec_live(const PassParams<T>& p, int tag) {
+    return tag_epoch(tag) == (p.star_int[tag_slot(tag) * SI_COUNT + SI_EPOCH] & 0xff);
+}
+
+// The exact cull (brutus/fitting.py:758-759) against the final per-star maximum of lnl_p, the survivor
+// counts, and the convergence reductions of the flux iterations the sweep already ran (:798-799):
+//   "lerr <= ltol"  <=>  max{lnl_new_i : |lnl_new_i - lnl_old_i| > ltol} <= max lnl_new + ln(ltol_subthresh)
+template <typename T> __global__ void __launch_bounds__(kTile) k_cull(const PassParams<T> p) {
+    __shared__ StarAgg<T, 2> agg;
+    const int which[2] = {RED_FL, RED_FB};
+    agg.init();
+    __syncthreads();
+    int64_t lo, hi;
+    pass_range(p.n, lo, hi);
+    for (int64_t base = lo; base < hi; base += kPassStep) {
+        int tag[kPassU], slot[kPassU];
+        bool live[kPassU], surv[kPassU];
+        T lp[kPassU], lnew[kPassU], lold[kPassU], thr[kPassU];
+#pragma unroll
+        for (int u = 0; u < kPassU; u++) {
+            const int64_t q = base + u * kTile + threadIdx.x;
+            tag[u] = q < hi ? p.pool.sflag[q] : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < kPassU; u++) {
+            const int64_t q = base + u * kTile + threadIdx.x;
+            live[u] = tag[u] != -1 && rec_live(p, tag[u]);
+            slot[u] = live[u] ? tag_slot(tag[u]) : -1;
+            lp[u] = live[u] ? p.pool.lp[q] : T(0);
+            lnew[u] = live[u] ? p.pool.lold[q] : T(0);
+            lold[u] = live[u] ? p.pool.lprev[q] : T(0);
+            thr[u] = live[u] ? Enc<T>::dec(p.red[(int64_t)slot[u] * kNumRed + RED_LP]) + p.o.ln_init : T(0);
+        }
+#pragma unroll
+        for (int u = 0; u < kPassU; u++) {
+            const int64_t q = base + u * kTile + threadIdx.x;
+            surv[u] = live[u] && lp[u] > thr[u];
+            T v[2] = {Num<T>::neg_inf(), Num<T>::neg_inf()};
+            if (surv[u]) {
+                v[0] = (lnew[u] == lnew[u]) ? lnew[u] : Num<T>::neg_inf();
+                v[1] = (tabs(lnew[u] - lold[u]) > p.o.ltol) ? v[0] : Num<T>::neg_inf();
+                p.pool.sflag[q] = tag[u] | kFlagSurv << 24;
+            }
+            // refined as a likely survivor, but not a survivor: onto the fix-up list (one atomic per warp: per-record
+            // atomics on the single counter cost more than the rest of the pass)
+            const bool fix = !surv[u] && live[u] && (tag_flags(tag[u]) & kFlagFluxed);
+            const unsigned fb = __ballot_sync(0xffffffffu, fix);
+            if (fb) {
+                const int lane = threadIdx.x & 31, lead = __ffs(fb) - 1;
+                int at = 0;
+                if (lane == lead) at = atomicAdd(p.nfix, __popc(fb));
+                at = __shfl_sync(0xffffffffu, at, lead);
+                if (fix) p.fixlist[at + __popc(fb & ((1u << lane) - 1u))] = (int)q;
+            }
+            agg.add(p.red, which, p.star_int + SI_NSURV, SI_COUNT, slot[u], surv[u], v, surv[u]);
+        }
     }
-}
-
-// start of the flux loops of a group of stars (brutus/fitting.py:778-781)
-__global__ void k_flux_begin(int* star_int, const int* list, int nlist, const int* nsurv) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nlist) return;
-    const int slot = list[t];
-    star_int[slot * SI_COUNT + SI_ACTIVE] = nsurv[slot] > 0 ? 1 : 0;
-    star_int[slot * SI_COUNT + SI_NFLUX] = 0;
+    agg.flush(p.red, which, p.star_int + SI_NSURV, SI_COUNT);
 }
 
 // Convergence control of the flux loops, on the device (one CTA): "lerr > ltol" (:781, :798-799) restated
-// on the two max-reductions of the k_flux launch that just ran `nit` iterations.  *any_out = 1 if some
-// star of the group needs another iteration.
+// on the two max-reductions of the `nit` iterations that just ran (first: the ones inside the sweep).
+// *any_out = 1 if some star of the group needs another iteration.
 template <typename T>
 __global__ void __launch_bounds__(1024) k_flux_ctl(int* star_int, typename Enc<T>::U* red, const int* list, int nlist,
-                                                   int nit, int max_iter, T ln_sub, int* any_out) {
+                                                   int first, int nit, int max_iter, T ln_sub, int* any_out) {
     int any = 0;
     for (int t = threadIdx.x; t < nlist; t += blockDim.x) {
         const int slot = list[t];
         int* si = star_int + slot * SI_COUNT;
+        if (first) {   // start of the star's flux loop (:778-781)
+            si[SI_ACTIVE] = si[SI_NSURV] > 0 ? 1 : 0;
+            si[SI_NFLUX] = 0;
+        }
         if (si[SI_ACTIVE]) {
             typename Enc<T>::U* r = red + (int64_t)slot * kNumRed;
             const int nf = si[SI_NFLUX] + nit;
@@ -201,76 +268,170 @@ __global__ void __launch_bounds__(1024) k_flux_ctl(int* star_int, typename Enc<T
     if (threadIdx.x == 0) *any_out = any;
 }
 
-// brutus/fitting.py:808-810: the survivors' flux-phase results replace the mag-fit values
-template <typename T> __global__ void k_flux_scatter(SurvArrays<T> sv, int64_t n, PoolArrays<T> pool) {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const int64_t q = sv.q[t];
-    pool.av[q] = sv.av[t];
-    pool.rv[q] = sv.rv[t];
-    pool.chi2[q] = sv.chi2[t];
-    pool.scale[q] = sv.scale[t];
-    pool.sden[q] = sv.sden[t];
-}
-
-template <typename T> struct FinalParams {
-    const T* stars;
-    PoolArrays<T> pool;
-    int64_t ncand;
-    typename Enc<T>::U* red;
-    int dim_prior;
-    int64_t npad;
-    const T* labels;   // [nlabel][npad]
-    const T* ext;      // [batch][nlabel][3]
-    int nlabel;
-};
-
 // lnlike / lnprob of every candidate from its final (chi2, scale, s_den), per-star max(lnprob) (:990)
-template <typename T> __global__ void __launch_bounds__(kTile) k_final(const FinalParams<T> p) {
-    const int64_t q = (int64_t)blockIdx.x * kTile + threadIdx.x;
-    const bool inr = q < p.ncand;
-    int slot = -1;
-    T lp = Num<T>::neg_inf();
-    if (inr) {
-        slot = p.pool.star[q];
-        const T* __restrict__ srow = p.stars + (int64_t)slot * kStarStride;
-        T ext = T(0);
-        if (p.nlabel > 0)
-            ext = ext_prior<T>(p.labels, p.ext + (int64_t)slot * p.nlabel * 3, p.nlabel, p.npad, p.pool.model[q]);
-        T lnl;
-        lnl_lnprob<T>(p.pool.chi2[q], p.pool.sden[q], p.pool.scale[q], (p.pool.flag[q] & kFlagSurv) != 0, srow,
-                      p.dim_prior, ext, lnl, lp);
-        p.pool.lnl[q] = lnl;
-        p.pool.lnprob[q] = lp;
+template <typename T> __global__ void __launch_bounds__(kTile) k_final(const PassParams<T> p) {
+    __shared__ StarAgg<T, 1> agg;
+    const int which[1] = {RED_LNP};
+    agg.init();
+    __syncthreads();
+    int64_t lo, hi;
+    pass_range(p.n, lo, hi);
+    for (int64_t base = lo; base < hi; base += kPassStep) {
+        int tag[kPassU], slot[kPassU];
+        bool live[kPassU];
+        T chi2[kPassU], sden[kPassU], scale[kPassU];
+#pragma unroll
+        for (int u = 0; u < kPassU; u++) {
+            const int64_t q = base + u * kTile + threadIdx.x;
+            tag[u] = q < hi ? p.pool.sflag[q] : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < kPassU; u++) {
+            const int64_t q = base + u * kTile + threadIdx.x;
+            live[u] = tag[u] != -1 && rec_live(p, tag[u]);
+            slot[u] = live[u] ? tag_slot(tag[u]) : -1;
+            chi2[u] = live[u] ? p.pool.chi2[q] : T(1);
+            sden[u] = live[u] ? p.pool.sden[q] : T(1);
+            scale[u] = live[u] ? p.pool.scale[q] : T(1);
+        }
+#pragma unroll
+        for (int u = 0; u < kPassU; u++) {
+            const int64_t q = base + u * kTile + threadIdx.x;
+            T lp[1] = {Num<T>::neg_inf()};
+            if (live[u]) {
+                const T* __restrict__ srow = p.stars + (int64_t)slot[u] * kStarStride;
+                T ext = T(0);
+                if (p.nlabel > 0)
+                    ext = ext_prior<T>(p.labels, p.ext + (int64_t)slot[u] * p.nlabel * 3, p.nlabel, p.npad, p.pool.model[q]);
+                T lnl;
+                lnl_lnprob<T>(chi2[u], sden[u], scale[u], (tag_flags(tag[u]) & kFlagSurv) != 0, srow, p.o.dim_prior, ext, lnl, lp[0]);
+                p.pool.lnl[q] = lnl;
+                p.pool.lnprob[q] = lp[0];
+            }
+            agg.add(p.red, which, nullptr, 0, slot[u], live[u], lp, false);
+        }
     }
-    cta_star_max<T>(p.red, RED_LNP, slot, inr, lp);
+    agg.flush(p.red, which, nullptr, 0);
 }
 
-template <typename T> struct SelParams {
+// brutus/fitting.py:990-991: lnprob > max(lnprob) + ln(wt_thresh).  Selected records are flagged; the bit of a
+// candidate that fails is cleared, which turns the sweep's candidate map into the selection map.
+template <typename T> __global__ void __launch_bounds__(kTile) k_sel(const PassParams<T> p) {
+    const int64_t hi = p.n;
+    {   // one step per CTA, in pool order: the CTAs in flight stay within a narrow window of every array
+        const int64_t base = (int64_t)blockIdx.x * kPassStep;
+        int tag[kPassU];
+        T lnp[kPassU], thr[kPassU];
+        bool live[kPassU];
+#pragma unroll
+        for (int u = 0; u < kPassU; u++) {
+            const int64_t q = base + u * kTile + threadIdx.x;
+            tag[u] = q < hi ? p.pool.sflag[q] : -1;
+            lnp[u] = q < hi ? p.pool.lnprob[q] : T(0);
+        }
+#pragma unroll
+        for (int u = 0; u < kPassU; u++) {
+            live[u] = tag[u] != -1 && rec_live(p, tag[u]);
+            thr[u] = live[u] ? Enc<T>::dec(p.red[(int64_t)tag_slot(tag[u]) * kNumRed + RED_LNP]) + p.o.ln_wt : T(0);
+        }
+#pragma unroll
+        for (int u = 0; u < kPassU; u++) {
+            if (!live[u]) continue;
+            const int64_t q = base + u * kTile + threadIdx.x;
+            if (lnp[u] > thr[u]) {
+                p.pool.sflag[q] = tag[u] | kFlagSel << 24;
+            } else {
+                const int i = p.pool.model[q];
+                atomicAnd(&p.cand[(int64_t)tag_slot(tag[u]) * p.nwords + (i >> 5)], ~(1u << (i & 31)));
+            }
+        }
+    }
+}
+
+// O = element type of the outputs: double for the full-length B1 arrays (the reference returns float64),
+// T for the compacted B2 records (no point shipping more bits than were computed).
+template <typename T, typename O> struct OutParams {
     PoolArrays<T> pool;
-    int64_t ncand;
-    const typename Enc<T>::U* red;
-    T ln_wt;
-    int* blk;      // per 256-record block: count, then (after k_scan_blocks) exclusive offset
-    int* nsel;     // [batch] per-star selected count
-    int* sel_q;    // ordered list of selected pool entries
+    int64_t n;
+    const int* star_int;
+    // compacted records: rows of a [11][ld] matrix: lnl, scale, av, chi2, rv, icov(ss, sa, sr, aa, ar, rr); only the
+    // first `nrows` are produced (3, 5 or 11).  Full-length: separate arrays indexed by model, icov 9 per model.
+    O *o_lnl, *o_chi2, *o_scale, *o_av, *o_rv, *o_icov;
+    int64_t ld;
+    int nrows;
+    int* o_idx;    // model index of each record
+    int* o_star;   // optional: star slot of each record (device posterior)
+    const uint32_t* sel;   // selection map and its per-word prefix
+    const int* wpre;
+    int64_t nwords;
+    const int64_t* base;   // [batch] first output position of each star
+    int* ord;              // [nsel] pool index of the t-th selected record in (star, model) order
+    int64_t nsel;
 };
 
-// brutus/fitting.py:990-991: lnprob > max(lnprob) + ln(wt_thresh)
-template <typename T> __device__ __forceinline__ bool sel_flag(const SelParams<T>& p, int64_t q, int& slot) {
-    slot = -1;
-    if (q >= p.ncand) return false;
-    slot = p.pool.star[q];
-    return p.pool.lnprob[q] > Enc<T>::dec(p.red[(int64_t)slot * kNumRed + RED_LNP]) + p.ln_wt;
+// selected records -> their (star, model)-ordered position: rank of the model's bit in the selection map.
+// ord[t] = pool index of the t-th selected record.  The posterior reads the pool through it (no copy of the
+// records); the records-out path gathers through it so that its 12 output streams are written coalesced.
+template <typename T> __global__ void __launch_bounds__(kTile) k_ord(const OutParams<T, T> p) {
+    const PoolArrays<T>& pl = p.pool;
+    const int64_t hi = p.n;
+    // one step per CTA, in pool order: the CTAs in flight stay within a narrow window of every array
+    const int64_t base = (int64_t)blockIdx.x * kPassStep;
+    int tag[kPassU], model[kPassU];
+#pragma unroll
+    for (int u = 0; u < kPassU; u++) {
+        const int64_t q = base + u * kTile + threadIdx.x;
+        tag[u] = q < hi ? pl.sflag[q] : 0;
+        model[u] = q < hi ? pl.model[q] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < kPassU; u++) {
+        const int slot = tag_slot(tag[u]);
+        if ((tag_flags(tag[u]) & kFlagSel) && tag_epoch(tag[u]) == (p.star_int[slot * SI_COUNT + SI_EPOCH] & 0xff)) {
+            const int64_t w = (int64_t)slot * p.nwords + (model[u] >> 5);
+            const int64_t t = p.base[slot] + p.wpre[w] + __popc(p.sel[w] & ((1u << (model[u] & 31)) - 1u));
+            p.ord[t] = (int)(base + u * kTile + threadIdx.x);
+        }
+    }
 }
 
-template <typename T> __global__ void __launch_bounds__(kTile) k_sel_count(const SelParams<T> p) {
+// compacted, ordered records of the selection: one thread per output position, gathering from the pool
+template <typename T> __global__ void __launch_bounds__(kTile) k_out(const OutParams<T, T> p) {
+    const PoolArrays<T>& pl = p.pool;
+    const int64_t o = (int64_t)blockIdx.x * kTile + threadIdx.x;
+    if (o >= p.nsel) return;
+    const int64_t q = p.ord[o];
+    p.o_idx[o] = pl.model[q];
+    if (p.o_star) p.o_star[o] = tag_slot(pl.sflag[q]);
+    const T lnl = pl.lnl[q], sc = pl.scale[q], av = pl.av[q];
+    if (p.nrows <= 3) { p.o_lnl[o] = lnl; p.o_scale[o] = sc; p.o_av[o] = av; return; }
+    const T chi2 = pl.chi2[q], rv = pl.rv[q];
+    if (p.nrows <= 5) { p.o_lnl[o] = lnl; p.o_scale[o] = sc; p.o_av[o] = av; p.o_chi2[o] = chi2; p.o_rv[o] = rv; return; }
+    const T ss = pl.sden[q], sa = pl.isa[q], sr = pl.isr[q], aa = pl.iaa[q], ar = pl.iar[q], rr = pl.irr[q];
+    p.o_lnl[o] = lnl; p.o_scale[o] = sc; p.o_av[o] = av; p.o_chi2[o] = chi2; p.o_rv[o] = rv;
+    T* w6 = p.o_icov + o;
+    w6[0] = ss; w6[p.ld] = sa; w6[2 * p.ld] = sr; w6[3 * p.ld] = aa; w6[4 * p.ld] = ar; w6[5 * p.ld] = rr;
+}
+
+// every model of one star (B1): record -> position `model` of the full-length float64 arrays
+template <typename T> __global__ void __launch_bounds__(kTile) k_out_full(const OutParams<T, double> p) {
     const int64_t q = (int64_t)blockIdx.x * kTile + threadIdx.x;
-    int slot;
-    const bool f = sel_flag(p, q, slot);
-    const int n = __syncthreads_count(f);
-    if (threadIdx.x == 0) p.blk[blockIdx.x] = n;
-    cta_star_count(p.nsel, slot, f);
+    if (q >= p.n) return;
+    const int tag = p.pool.sflag[q];
+    const int slot = tag_slot(tag);
+    if (tag_epoch(tag) != (p.star_int[slot * SI_COUNT + SI_EPOCH] & 0xff)) return;
+    const PoolArrays<T>& pl = p.pool;
+    const int64_t t = pl.model[q];
+    p.o_lnl[t] = (double)pl.lnl[q];
+    p.o_chi2[t] = (double)pl.chi2[q];
+    p.o_scale[t] = (double)pl.scale[q];
+    p.o_av[t] = (double)pl.av[q];
+    p.o_rv[t] = (double)pl.rv[q];
+    if (!p.o_icov) return;
+    double* w = p.o_icov + t * 9;
+    const double ss = (double)pl.sden[q], sa = (double)pl.isa[q], sr = (double)pl.isr[q], aa = (double)pl.iaa[q],
+                 ar = (double)pl.iar[q], rr = (double)pl.irr[q];
+    w[0] = ss; w[1] = sa; w[2] = sr; w[3] = sa; w[4] = aa; w[5] = ar; w[6] = sr; w[7] = ar; w[8] = rr;
 }
 
 // in-place exclusive scan of n ints by one CTA; total -> *tot
@@ -286,22 +447,6 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(int* v, int64_t n, int64_t
         carry += total;
     }
     if (threadIdx.x == 0) *tot = carry;
-}
-
-template <typename T> __global__ void __launch_bounds__(kTile) k_sel_write(const SelParams<T> p) {
-    __shared__ int s_w[kTile / 32];
-    const int64_t q = (int64_t)blockIdx.x * kTile + threadIdx.x;
-    int slot;
-    const bool f = sel_flag(p, q, slot);
-    const unsigned bal = __ballot_sync(0xffffffffu, f);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) s_w[w] = __popc(bal);
-    __syncthreads();
-    if (f) {
-        int pre = __popc(bal & ((1u << lane) - 1u));
-        for (int k = 0; k < w; k++) pre += s_w[k];
-        p.sel_q[p.blk[blockIdx.x] + pre] = (int)q;
-    }
 }
 
 // =================================================================================================
@@ -334,6 +479,7 @@ struct EngineBase {
                           const double* par, const double* perr, const double* coords, const double* ext_mean,
                           const double* ext_std, const bf_options* opt, const bf_post_options* po, int32_t* ndim,
                           int32_t* n_iter, int64_t* nsel, double* levid, double* chi2min, bf_draws* out) = 0;
+    virtual const char* get_trace() = 0;
 };
 
 #define CK(call)                                                                               \
@@ -480,11 +626,10 @@ template <typename T> struct Engine : EngineBase {
     int batch_cap = 0;
     int64_t pool_cap = 0;
     const KTable<T>* kt = nullptr;
-    int* h_pin = nullptr;       // small pinned scratch for counters
 
     DevBuf<float> d_grid, d_rows;
     DevBuf<T> d_labels, d_stars, d_ext, d_poolT;
-    DevBuf<int> d_star_int, d_list, d_wpre, d_poolI, d_nsurv, d_nsel, d_ctr, d_blk;
+    DevBuf<int> d_star_int, d_list, d_wpre, d_poolI, d_ctr, d_blk;
     DevBuf<uint32_t> d_cand;
     DevBuf<int64_t> d_ncand, d_base, d_tot;
     DevBuf<U> d_red, d_probe;
@@ -497,39 +642,92 @@ template <typename T> struct Engine : EngineBase {
     DevBuf<int> d_seg;
     DevBuf<char> d_cubtmp;
     DevBuf<GalStar<T>> d_gstar;
-    DevBuf<int> d_rstar, d_nsel2, d_sel2, d_oidx;
+    DevBuf<int> d_rstar, d_nsel2, d_sel2, d_oidx, d_ord;
     DevBuf<int64_t> d_off2;
     DevBuf<double> d_cdf, d_ptot, d_odbl;
     PinVec<int> h_nsel2;
 
-    std::vector<T> h_stars, h_ext;
-    std::vector<int> h_list, h_kpred;
-    std::vector<int64_t> h_base;
-    PinVec<int> h_int, h_nsurv, h_nsel;      // control read-backs: mapped pinned memory (k_publish)
+    // host staging, all in pinned memory: what the hot loop uploads (star rows, lists, per-star ints) is copied
+    // by the DMA engine straight from these buffers, and the control read-backs land in them (k_publish)
+    PinVec<T> h_stars, h_ext;
+    PinVec<int> h_list, h_int, h_ctr;
+    PinVec<int64_t> h_base, h_ncand;
     PinVec<U> h_red, h_probe;
-    PinVec<int64_t> h_ncand;
+    std::vector<int> h_kpred;
+
+    // ---- optional per-kernel timing (BRUTUS_B200_TRACE=1): CUDA events around every launch, summed per kernel
+    // name over a call; bf_get_trace() returns the table.  Off by default: recording events costs nothing on the
+    // device but the bookkeeping is not free on the host.
+    bool trace_on = false;
+    std::vector<cudaEvent_t> trace_pool;
+    struct TraceRec { const char* name; size_t e0, e1; };
+    std::vector<TraceRec> trace_recs;
+    std::map<std::string, std::pair<double, int64_t>> trace_acc;
+    size_t trace_next = 0;
+    cudaEvent_t trace_event() {
+        if (trace_next == trace_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); trace_pool.push_back(e); }
+        return trace_pool[trace_next++];
+    }
+    struct TraceScope {
+        Engine* e; size_t i0 = 0; const char* name;
+        TraceScope(Engine* eng, const char* nm) : e(eng), name(nm) {
+            if (e->trace_on) { cudaEvent_t ev = e->trace_event(); i0 = e->trace_next - 1; cudaEventRecord(ev, e->stream); }
+        }
+        ~TraceScope() {
+            if (e->trace_on) { cudaEvent_t ev = e->trace_event(); cudaEventRecord(ev, e->stream); e->trace_recs.push_back({name, i0, e->trace_next - 1}); }
+        }
+    };
+    void trace_collect() {   // end of a call: the stream is idle
+        if (!trace_on) return;
+        cudaStreamSynchronize(stream);
+        for (const TraceRec& r : trace_recs) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, trace_pool[r.e0], trace_pool[r.e1]) == cudaSuccess) {
+                auto& a = trace_acc[r.name];
+                a.first += ms; a.second += 1;
+            }
+        }
+        trace_recs.clear();
+        trace_next = 0;
+    }
+    std::string trace_text;
+    const char* get_trace() override {
+        trace_text.clear();
+        char b[256];
+        for (const auto& kv : trace_acc) {
+            snprintf(b, sizeof b, "%-24s %8lld launches %12.3f ms\n", kv.first.c_str(), (long long)kv.second.second, kv.second.first);
+            trace_text += b;
+        }
+        trace_acc.clear();
+        return trace_text.c_str();
+    }
+#define TRACE(name) TraceScope trace_scope_(this, name)
 
     // device -> mapped pinned host, on the compute stream, without touching a copy engine
     void publish(void* host_dst, const void* dev_src, size_t bytes) {
+        TRACE("k_publish");
         const size_t nw = bytes / 4;
         if (!nw) return;
         k_publish<<<(unsigned)((nw + 255) / 256), 256, 0, stream>>>((const uint32_t*)dev_src, (uint32_t*)host_dst, nw);
         stats.kernel_launches++;
     }
 
-    enum { CTR_NSV = 0, CTR_ANY = 1, CTR_COUNT = 64 };
+    // d_ctr: [0..1] records appended to the pool (64 bit), [2] fix-up list length, [3] length of the list of
+    // active survivors (k_flux_more), [4..] "any star active" flags
+    enum { CTR_POOL = 0, CTR_NFIX = 2, CTR_NLIST = 3, CTR_ANY = 4, CTR_COUNT = 16 };
     static constexpr int kShipBatch = 256;   // stars per sub-batch of the records-out path (D2H pipelining)
 
     ~Engine() override {
         cudaSetDevice(device);
         d_grid.release(); d_rows.release(); d_labels.release(); d_stars.release(); d_ext.release();
         d_poolT.release(); d_star_int.release(); d_list.release(); d_wpre.release(); d_poolI.release();
-        d_nsurv.release(); d_nsel.release(); d_ctr.release(); d_blk.release(); d_cand.release();
+        d_ctr.release(); d_blk.release(); d_cand.release();
         d_probe.release(); d_ncand.release(); d_base.release(); d_tot.release(); d_red.release(); d_out.release(); d_flush.release();
         d_lnprior.release(); d_feh.release(); d_loga.release(); d_lnp1.release(); d_lnp2.release(); d_gstar.release();
         d_lnb1.release(); d_keys.release(); d_keys_sorted.release(); d_clip.release(); d_seg.release(); d_cubtmp.release();
-        d_rstar.release(); d_nsel2.release(); d_sel2.release(); d_oidx.release(); d_off2.release(); d_cdf.release();
+        d_ord.release(); d_rstar.release(); d_nsel2.release(); d_sel2.release(); d_oidx.release(); d_off2.release(); d_cdf.release();
         d_ptot.release(); d_odbl.release(); h_nsel2.release();
+        for (cudaEvent_t e : trace_pool) cudaEventDestroy(e);
         if (evP0) cudaEventDestroy(evP0);
         if (evP1) cudaEventDestroy(evP1);
         if (ev0) cudaEventDestroy(ev0);
@@ -543,8 +741,8 @@ template <typename T> struct Engine : EngineBase {
         }
         if (arena) cudaFreeHost(arena);
         if (draw_arena) cudaFreeHost(draw_arena);
-        if (h_pin) cudaFreeHost(h_pin);
-        h_int.release(); h_nsurv.release(); h_nsel.release(); h_red.release(); h_probe.release(); h_ncand.release();
+        h_stars.release(); h_ext.release(); h_list.release(); h_int.release(); h_ctr.release(); h_base.release();
+        h_ncand.release(); h_red.release(); h_probe.release();
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -560,7 +758,8 @@ template <typename T> struct Engine : EngineBase {
             CK(cudaEventCreateWithFlags(&ev_rec[k], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&ev_cp[k], cudaEventDisableTiming));
         }
-        CK(cudaHostAlloc((void**)&h_pin, CTR_COUNT * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+        if (const char* e = getenv("BRUTUS_B200_TRACE")) trace_on = atoi(e) != 0;
+        CK(h_ctr.resize(CTR_COUNT));
         CK(d_ctr.ensure(CTR_COUNT));
         CK(d_tot.ensure(2));
         return BF_OK;
@@ -568,22 +767,14 @@ template <typename T> struct Engine : EngineBase {
 
     PoolArrays<T> pool() {
         PoolArrays<T> q;
-        q.model = d_poolI.p; q.star = d_poolI.p + pool_cap; q.flag = d_poolI.p + 2 * pool_cap;
+        q.model = d_poolI.p; q.sflag = d_poolI.p + pool_cap;
         T* b = d_poolT.p;
-        q.av = b; q.rv = b + pool_cap; q.chi2 = b + 2 * pool_cap; q.scale = b + 3 * pool_cap;
-        q.sden = b + 4 * pool_cap; q.lnl = b + 5 * pool_cap; q.lnprob = b + 6 * pool_cap;
+        T** f[kPoolReals] = {&q.av, &q.rv, &q.chi2, &q.scale, &q.sden, &q.lp, &q.eta, &q.lold, &q.lprev,
+                             &q.isa, &q.isr, &q.iaa, &q.iar, &q.irr, &q.lnl, &q.lnprob};
+        for (int k = 0; k < kPoolReals; k++) *f[k] = b + (size_t)k * pool_cap;
         return q;
     }
-    int* selq() { return d_poolI.p + 3 * pool_cap; }
-    SurvArrays<T> surv() {
-        SurvArrays<T> v;
-        int* a = d_poolI.p + 4 * pool_cap;
-        v.q = a; v.model = a + pool_cap; v.star = a + 2 * pool_cap;
-        T* b = d_poolT.p + 7 * pool_cap;
-        v.av = b; v.rv = b + pool_cap; v.eta = b + 2 * pool_cap; v.lold = b + 3 * pool_cap;
-        v.chi2 = b + 4 * pool_cap; v.scale = b + 5 * pool_cap; v.sden = b + 6 * pool_cap;
-        return v;
-    }
+    int* fixlist() { return d_poolI.p + (size_t)kPoolInts * pool_cap; }
 
     int set_grid(const float* co, int64_t nm, int nf, int layout, bool on_device) override {
         CK(cudaSetDevice(device));
@@ -618,18 +809,19 @@ template <typename T> struct Engine : EngineBase {
         size_t fr = 0, tot = 0;
         CK(cudaMemGetInfo(&fr, &tot));
         // Star batch.  Large batches amortise the host round trips of a batch (iteration-count verification,
-        // candidate / survivor / selection counts) and the tails of its kernels: 1024 stars measured +3.5 % over
-        // 256.  The records-out path works in sub-batches of kShipBatch so that the D2H of one sub-batch overlaps
-        // the kernels of the next (run_catalogue's batch_limit).
+        // survivor / selection counts) and the tails of its kernels: 1024 stars measured +3.5 % over 256.  The
+        // records-out path works in sub-batches of kShipBatch so that the D2H of one sub-batch overlaps the
+        // kernels of the next (run_catalogue's batch_limit).
         int want = 1024;
         if (const char* e = getenv("BRUTUS_B200_BATCH")) want = std::max(1, std::min(4096, atoi(e)));
         const size_t per_star = (size_t)8 * nwords;
         batch_cap = (int)std::max<size_t>(1, std::min<size_t>(want, (fr / 8) / per_star));
-        // candidate pool + flux working set: 7 ints + 14 T per record, at most ~1/4 of the free memory
-        const size_t rec = 7 * sizeof(int) + 14 * sizeof(T) + 1;
+        // candidate pool: kPoolInts + 1 ints + kPoolReals T per record, at most ~1/4 of the free memory
+        const size_t rec = (kPoolInts + 1) * sizeof(int) + kPoolReals * sizeof(T);
         int64_t cap = (int64_t)std::min<size_t>((fr / 4) / rec, (size_t)1 << 30);
         if (const char* e = getenv("BRUTUS_B200_POOL")) cap = std::max<int64_t>(1, atoll(e));
-        pool_cap = std::max<int64_t>(npad, std::min<int64_t>(cap, (int64_t)batch_cap * npad));
+        // at least one star with every model as a candidate, swept twice (a stale set of records plus the live one)
+        pool_cap = std::max<int64_t>(2 * npad, std::min<int64_t>(cap, (int64_t)batch_cap * npad + npad));
         CK(d_stars.ensure((size_t)batch_cap * kStarStride));
         CK(d_star_int.ensure((size_t)batch_cap * SI_COUNT));
         CK(d_list.ensure((size_t)batch_cap));
@@ -637,23 +829,19 @@ template <typename T> struct Engine : EngineBase {
         CK(d_wpre.ensure((size_t)batch_cap * nwords));
         CK(d_ncand.ensure((size_t)batch_cap));
         CK(d_base.ensure((size_t)batch_cap));
-        CK(d_nsurv.ensure((size_t)batch_cap));
-        CK(d_nsel.ensure((size_t)batch_cap));
         CK(d_red.ensure((size_t)batch_cap * kNumRed));
         CK(d_probe.ensure((size_t)batch_cap * 2 * kProbeIter));
-        CK(d_poolI.ensure((size_t)7 * pool_cap));
-        CK(d_poolT.ensure((size_t)14 * pool_cap));
+        CK(d_poolI.ensure((size_t)(kPoolInts + 1) * pool_cap));
+        CK(d_poolT.ensure((size_t)kPoolReals * pool_cap));
         CK(d_blk.ensure((size_t)(pool_cap / kTile + 2)));
-        h_stars.resize((size_t)batch_cap * kStarStride);
+        CK(h_stars.resize((size_t)batch_cap * kStarStride));
         CK(h_int.resize((size_t)batch_cap * SI_COUNT));
-        h_list.resize(batch_cap);
+        CK(h_list.resize(batch_cap));
         h_kpred.assign(batch_cap, 0);
         CK(h_red.resize((size_t)batch_cap * kNumRed));
         CK(h_probe.resize((size_t)batch_cap * 2 * kProbeIter));
         CK(h_ncand.resize(batch_cap));
-        h_base.resize(batch_cap);
-        CK(h_nsurv.resize(batch_cap));
-        CK(h_nsel.resize(batch_cap));
+        CK(h_base.resize(batch_cap));
         return BF_OK;
     }
 
@@ -672,7 +860,7 @@ template <typename T> struct Engine : EngineBase {
         CK(cudaStreamSynchronize(stream));
         tmp.release();
         CK(d_ext.ensure((size_t)batch_cap * nl * 3));
-        h_ext.resize((size_t)batch_cap * nl * 3);
+        CK(h_ext.resize((size_t)batch_cap * nl * 3));
         return BF_OK;
     }
 
@@ -695,7 +883,7 @@ template <typename T> struct Engine : EngineBase {
         o.avmin = (T)opt->avlim[0]; o.avmax = (T)opt->avlim[1];
         o.rvmin = (T)opt->rvlim[0]; o.rvmax = (T)opt->rvlim[1];
         o.mtol = (T)(2.5 * opt->ltol);
-        o.ln_init = (T)std::log(opt->init_thresh);
+        o.ln_init = (T)(opt->init_thresh > 0 ? std::log(opt->init_thresh) : -INFINITY);
         o.ltol = (T)opt->ltol;
         o.ln_sub = (T)std::log(opt->ltol_subthresh);
         o.ln_wt = (T)(opt->wt_thresh > 0 ? std::log(opt->wt_thresh) : -INFINITY);
@@ -703,6 +891,8 @@ template <typename T> struct Engine : EngineBase {
         max_iter = opt->max_iter > 0 ? opt->max_iter : 64;
         return BF_OK;
     }
+
+    static unsigned pass_ctas(int64_t n) { return (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + kPassStep - 1) / kPassStep, kPassCtas)); }
 
     void phase_begin() { cudaEventRecord(evA, stream); }
     double phase_end() {  // synchronises the stream
@@ -724,7 +914,7 @@ template <typename T> struct Engine : EngineBase {
         for (size_t k = 0; k < (size_t)ns * 2 * kProbeIter; k++) h_probe[k] = Enc<T>::enc(-std::numeric_limits<T>::infinity());
         CK(cudaMemcpyAsync(d_probe.p, h_probe.data(), (size_t)ns * 2 * kProbeIter * sizeof(U), cudaMemcpyHostToDevice, stream));
         phase_begin();
-        kt->kprobe(pp, stream);
+        { TRACE("k_kprobe"); kt->kprobe(pp, stream); }
         stats.kernel_launches++;
         CK(cudaGetLastError());
         publish(h_probe.data(), d_probe.p, (size_t)ns * 2 * kProbeIter * sizeof(U));
@@ -738,150 +928,201 @@ template <typename T> struct Engine : EngineBase {
             // The probe only chooses between 1 and 2 for the first full sweep.  A sweep with K iterations tells
             // whether the FULL grid converged at K-1 and at K, and the reference stops at the FIRST converged
             // iteration, so K is only ever raised two at a time from iterations already known not to have
-            // converged (sweep()): starting a star at K >= 3 on the word of a subsample would leave its early
-            // iterations unverified.
+            // converged (process_group): starting a star at K >= 3 on the word of a subsample would leave its
+            // early iterations unverified.
             h_int[s * SI_COUNT + SI_KSPEC] = std::min(std::min(k, 2), max_iter);
             h_kpred[s] = k;   // the subsample's prediction steers how far a later sweep reaches (never past known + 2)
         }
         return BF_OK;
     }
 
-    // ---- phase 1: the full-grid sweep for the stars in `lst` (slots), with verified speculation of the
-    // mag-iteration count (skipped for stars whose count is already exact), then the candidate scan.
-    // On return h_ncand / h_red hold the candidate counts and the per-star maxima of those stars.
-    int sweep(int ns, std::vector<int> lst, std::vector<char>& exact, const DevOpts<T>& o, int max_iter, int* n_mag) {
-        bool first_pass = true;
-        while (!lst.empty()) {
-            const int nl = (int)lst.size();
-            for (int k = 0; k < nl; k++) h_list[k] = lst[k];
-            CK(cudaMemcpyAsync(d_list.p, h_list.data(), (size_t)nl * sizeof(int), cudaMemcpyHostToDevice, stream));
-            CK(cudaMemcpyAsync(d_star_int.p, h_int.data(), (size_t)ns * SI_COUNT * sizeof(int), cudaMemcpyHostToDevice, stream));
-            k_reset_red<T><<<(nl * kNumRed + 255) / 256, 256, 0, stream>>>(d_red.p, d_list.p, nl, (1u << kNumRed) - 1u);
-            stats.kernel_launches++;
-            if (!first_pass) stats.resweeps += nl;
-            SweepParams<T> sp;
-            sp.grid = d_grid.p; sp.npad = npad; sp.nmodel = nmodel; sp.stars = d_stars.p;
-            sp.star_int = d_star_int.p; sp.list = d_list.p; sp.nlist = nl; sp.o = o; sp.red = d_red.p;
-            sp.cand = d_cand.p; sp.nwords = nwords; sp.labels = d_labels.p; sp.ext = d_ext.p; sp.nlabel = nlabel;
-            phase_begin();
-            kt->magfit(sp, stream);
-            CK(cudaGetLastError());
-            CK(cudaEventRecord(evB, stream));
-            stats.kernel_launches++; stats.magfit_launches++; stats.magfit_star_passes += nl;
-            k_cand_scan<<<nl, 1024, 0, stream>>>(d_cand.p, d_wpre.p, d_list.p, nwords, d_ncand.p);
-            stats.kernel_launches++;
-            CK(cudaGetLastError());
-            publish(h_red.data(), d_red.p, (size_t)ns * kNumRed * sizeof(U));
-            publish(h_ncand.data(), d_ncand.p, (size_t)ns * sizeof(int64_t));
-            CK(cudaStreamSynchronize(stream));
-            {
-                float ms = 0.f;
-                CK(cudaEventElapsedTime(&ms, evA, evB));
-                stats.ms_magfit += ms;
-            }
-            stats.d2h_bytes += (size_t)ns * (kNumRed * sizeof(U) + sizeof(int64_t));
-            std::vector<int> next;
-            for (int k = 0; k < nl; k++) {
-                const int s = lst[k];
-                int& ksp = h_int[s * SI_COUNT + SI_KSPEC];
-                if (n_mag) n_mag[s] = ksp;
-                if (exact[s]) continue;
-                const U* r = &h_red[(size_t)s * kNumRed];
-                // brutus/fitting.py:252-263 restated on the two max-reductions.  Invariant: every iteration below
-                // ksp - 1 is already known NOT to have converged on the full grid (first sweep at ksp <= 2, then
-                // +2 only after a sweep that saw ksp - 1 and ksp unconverged), so the first converged iteration
-                // among {ksp - 1, ksp} is the reference's stopping iteration.
-                const bool conv_prev = ksp >= 2 && !(Enc<T>::dec(r[RED_B0]) > Enc<T>::dec(r[RED_L0]) + o.ln_init);
-                const bool conv_last = !(Enc<T>::dec(r[RED_B1]) > Enc<T>::dec(r[RED_L1]) + o.ln_init);
-                if (conv_prev) {           // the reference would have stopped one iteration earlier
-                    ksp -= 1; exact[s] = 1; next.push_back(s);
-                } else if (!conv_last && ksp < max_iter) {
-                    // next sweep: iterations (ksp, ksp + 1) if the probe expects convergence at ksp + 1, else
-                    // (ksp + 1, ksp + 2); either way contiguous with what is known
-                    ksp = std::min(h_kpred[s] == ksp + 1 ? ksp + 1 : ksp + 2, max_iter); next.push_back(s);
-                } else {
-                    exact[s] = 1;
-                }
-            }
-            lst.swap(next);
-            first_pass = false;
-        }
-        return BF_OK;
-    }
-
-    // ---- phase 2 for the stars [g0, g1) whose candidates fit in the pool: expand, re-fit, flux loops,
-    // final lnprob.  Returns the number of candidate records through *tot_out.
-    int fit_group(int ns, int g0, int g1, const DevOpts<T>& o, int max_iter, int64_t* tot_out) {
+    // ---- the stars (slots) [g0, g1) of the uploaded batch, from the sweep to the selection map ----------------
+    // 1. the fused sweep (k_sweep) with verified speculation of the mag-iteration count: stars whose count was
+    //    wrong are swept again (their earlier records go stale: SI_EPOCH);
+    // 2. exact cull + convergence test of the flux iterations the sweep ran (k_cull, k_flux_ctl), the rare
+    //    fix-ups and further flux iterations (k_fixup, k_flux_more);
+    // 3. lnlike / lnprob / per-star maximum (k_final), first selection of lnpost (k_sel), and the scan of the
+    //    selection map that orders the output (k_cand_scan).
+    // *fits = false: the group's records did not fit in the pool; h_ncand[g0..g1) then hold the stars'
+    // candidate counts for regrouping.  On success h_ncand hold the selection counts, *nrec the pool fill.
+    int process_group(int ns, int g0, int g1, const DevOpts<T>& o, int max_iter, std::vector<char>& exact,
+                      int* n_mag, bool* fits, int64_t* nrec) {
         const PoolArrays<T> pl = pool();
         const int ng = g1 - g0;
-        int64_t tot = 0;
-        for (int s = g0; s < g1; s++) { h_base[s] = tot; tot += h_ncand[s]; }
-        *tot_out = tot;
-        for (int s = 0; s < ns; s++) h_list[s] = s;
-        CK(cudaMemcpyAsync(d_list.p, h_list.data(), (size_t)ns * sizeof(int), cudaMemcpyHostToDevice, stream));
-        CK(cudaMemcpyAsync(d_base.p + g0, h_base.data() + g0, (size_t)ng * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
-        CK(cudaMemsetAsync(d_ctr.p, 0, CTR_COUNT * sizeof(int), stream));
-        CK(cudaMemsetAsync(d_nsurv.p + g0, 0, (size_t)ng * sizeof(int), stream));
-        CK(cudaMemsetAsync(d_nsel.p + g0, 0, (size_t)ng * sizeof(int), stream));
-        const int* glist = d_list.p + g0;
-        phase_begin();
-        if (tot > 0) {
-            k_expand<T><<<dim3((unsigned)((nwords + 255) / 256), ng), 256, 0, stream>>>(d_cand.p, d_wpre.p, d_base.p, glist, nwords, pl);
-            RefitParams<T> rp;
-            rp.rows = d_rows.p; rp.stars = d_stars.p; rp.star_int = d_star_int.p; rp.o = o; rp.pool = pl;
-            rp.ncand = tot; rp.red = d_red.p; rp.sv = surv(); rp.nsv = d_ctr.p + CTR_NSV; rp.nsurv = d_nsurv.p;
-            kt->refit(rp, stream);
-            stats.kernel_launches += 2;
-            CK(cudaGetLastError());
-        }
-        publish(h_pin, d_ctr.p, sizeof(int));
-        publish(h_nsurv.data() + g0, d_nsurv.p + g0, (size_t)ng * sizeof(int));
-        stats.ms_select += phase_end();
-        const int64_t nsv = h_pin[0];
-        stats.candidates += tot;
-        stats.survivors += nsv;
-        // ---- flux-space iterations until every star of the group converges (:781-803); the per-star
-        // convergence test runs on the device, the host only polls "anything still active?" ----
-        phase_begin();
-        k_flux_begin<<<(ng + 255) / 256, 256, 0, stream>>>(d_star_int.p, glist, ng, d_nsurv.p);
-        k_reset_red<T><<<(ng * kNumRed + 255) / 256, 256, 0, stream>>>(d_red.p, glist, ng, (1u << RED_FL) | (1u << RED_FB) | (1u << RED_LNP));
-        stats.kernel_launches += 2;
-        bool first = true;
-        int done_iter = 0;
-        while (nsv > 0 && done_iter < max_iter) {
-            int any_slot = CTR_ANY;
-            const int rounds = first ? 2 : 3;
-            for (int r = 0; r < rounds && done_iter < max_iter; r++) {
-                FluxParams<T> xp;
-                xp.rows = d_rows.p; xp.stars = d_stars.p; xp.star_int = d_star_int.p; xp.o = o; xp.sv = surv();
-                xp.nsv = nsv; xp.red = d_red.p;
-                xp.nit = first ? std::min(2, max_iter) : 1;
-                kt->flux(xp, stream);
-                any_slot = CTR_ANY + r;
-                k_flux_ctl<T><<<1, 1024, 0, stream>>>(d_star_int.p, d_red.p, glist, ng, xp.nit, max_iter, o.ln_sub, d_ctr.p + any_slot);
-                stats.kernel_launches += 2;
-                done_iter += xp.nit;
-                first = false;
+        const int nit_first = std::min(2, max_iter);
+        bool redo_all = true;
+        while (redo_all) {
+            redo_all = false;
+            for (int s = g0; s < g1; s++) {
+                int* si = &h_int[s * SI_COUNT];
+                si[SI_EPOCH] = 0; si[SI_NSURV] = 0; si[SI_ACTIVE] = 0; si[SI_NFLUX] = 0;
             }
+            CK(cudaMemsetAsync(d_ctr.p, 0, CTR_COUNT * sizeof(int), stream));
+            // ---- 1. sweep ----
+            std::vector<int> lst(ng);
+            for (int k = 0; k < ng; k++) lst[k] = g0 + k;
+            bool first_pass = true;
+            int64_t count = 0;
+            while (!lst.empty()) {
+                const int nl = (int)lst.size();
+                for (int k = 0; k < nl; k++) h_list[k] = lst[k];
+                CK(cudaMemcpyAsync(d_list.p, h_list.data(), (size_t)nl * sizeof(int), cudaMemcpyHostToDevice, stream));
+                CK(cudaMemcpyAsync(d_star_int.p, h_int.data(), (size_t)ns * SI_COUNT * sizeof(int), cudaMemcpyHostToDevice, stream));
+                { TRACE("k_reset_red"); k_reset_red<T><<<(nl * kNumRed + 255) / 256, 256, 0, stream>>>(d_red.p, d_list.p, nl, (1u << kNumRed) - 1u); }
+                stats.kernel_launches++;
+                if (!first_pass) stats.resweeps += nl;
+                SweepParams<T> sp;
+                sp.grid = d_grid.p; sp.npad = npad; sp.nmodel = nmodel; sp.stars = d_stars.p;
+                sp.star_int = d_star_int.p; sp.list = d_list.p; sp.nlist = nl; sp.o = o; sp.red = d_red.p;
+                sp.cand = d_cand.p; sp.nwords = nwords; sp.labels = d_labels.p; sp.ext = d_ext.p; sp.nlabel = nlabel;
+                sp.pool = pl; sp.pool_cap = pool_cap; sp.pool_count = (unsigned long long*)(d_ctr.p + CTR_POOL);
+                sp.nit_first = nit_first;
+                phase_begin();
+                { TRACE("k_sweep"); CK((cudaError_t)kt->sweep(sp, stream)); }
+                CK(cudaGetLastError());
+                CK(cudaEventRecord(evB, stream));
+                stats.kernel_launches++; stats.magfit_launches++; stats.magfit_star_passes += nl;
+                publish(h_red.data(), d_red.p, (size_t)ns * kNumRed * sizeof(U));
+                publish(h_ctr.data(), d_ctr.p, CTR_COUNT * sizeof(int));
+                CK(cudaStreamSynchronize(stream));
+                {
+                    float ms = 0.f;
+                    CK(cudaEventElapsedTime(&ms, evA, evB));
+                    stats.ms_magfit += ms;
+                }
+                stats.d2h_bytes += (size_t)ns * kNumRed * sizeof(U) + CTR_COUNT * sizeof(int);
+                std::memcpy(&count, &h_ctr[CTR_POOL], sizeof(int64_t));
+                std::vector<int> next;
+                for (int k = 0; k < nl; k++) {
+                    const int s = lst[k];
+                    int& ksp = h_int[s * SI_COUNT + SI_KSPEC];
+                    if (n_mag) n_mag[s] = ksp;
+                    if (exact[s]) continue;
+                    const U* r = &h_red[(size_t)s * kNumRed];
+                    // brutus/fitting.py:252-263 restated on the two max-reductions.  Invariant: every iteration below
+                    // ksp - 1 is already known NOT to have converged on the full grid (first sweep at ksp <= 2, then
+                    // +2 only after a sweep that saw ksp - 1 and ksp unconverged), so the first converged iteration
+                    // among {ksp - 1, ksp} is the reference's stopping iteration.
+                    const bool conv_prev = ksp >= 2 && !(Enc<T>::dec(r[RED_B0]) > Enc<T>::dec(r[RED_L0]) + o.ln_init);
+                    const bool conv_last = !(Enc<T>::dec(r[RED_B1]) > Enc<T>::dec(r[RED_L1]) + o.ln_init);
+                    if (conv_prev) {           // the reference would have stopped one iteration earlier
+                        ksp -= 1; exact[s] = 1; next.push_back(s);
+                    } else if (!conv_last && ksp < max_iter) {
+                        // next sweep: iterations (ksp, ksp + 1) if the probe expects convergence at ksp + 1, else
+                        // (ksp + 1, ksp + 2); either way contiguous with what is known
+                        ksp = std::min(h_kpred[s] == ksp + 1 ? ksp + 1 : ksp + 2, max_iter); next.push_back(s);
+                    } else {
+                        exact[s] = 1;
+                    }
+                }
+                for (int s : next) h_int[s * SI_COUNT + SI_EPOCH] += 1;   // their records so far are stale
+                lst.swap(next);
+                first_pass = false;
+            }
+            for (int k = 0; k < ng; k++) h_list[k] = g0 + k;
+            CK(cudaMemcpyAsync(d_list.p, h_list.data(), (size_t)ng * sizeof(int), cudaMemcpyHostToDevice, stream));
+            if (count > pool_cap) {   // records were dropped: report the candidate counts, the caller splits the group
+                { TRACE("k_cand_scan"); k_cand_scan<<<ng, 1024, 0, stream>>>(d_cand.p, d_wpre.p, d_list.p, nwords, d_ncand.p); }
+                stats.kernel_launches++;
+                CK(cudaGetLastError());
+                publish(h_ncand.data() + g0, d_ncand.p + g0, (size_t)ng * sizeof(int64_t));
+                CK(cudaStreamSynchronize(stream));
+                *fits = false;
+                return BF_OK;
+            }
+            const int64_t n = count;
+            const unsigned nblk = (unsigned)((n + kTile - 1) / kTile);
+            PassParams<T> pp{};
+            pp.pool = pl; pp.n = n; pp.stars = d_stars.p; pp.star_int = d_star_int.p; pp.red = d_red.p; pp.o = o;
+            pp.fixlist = fixlist(); pp.nfix = d_ctr.p + CTR_NFIX;
+            pp.npad = npad; pp.labels = d_labels.p; pp.ext = d_ext.p; pp.nlabel = nlabel;
+            pp.cand = d_cand.p; pp.nwords = nwords;
+            // ---- 2. exact cull, flux-loop control ----
+            phase_begin();
+            { TRACE("k_reset_red"); k_reset_red<T><<<(ng * kNumRed + 255) / 256, 256, 0, stream>>>(d_red.p, d_list.p, ng, (1u << RED_FL) | (1u << RED_FB) | (1u << RED_LNP)); }
+            if (n > 0) { TRACE("k_cull"); k_cull<T><<<pass_ctas(n), kTile, 0, stream>>>(pp); }
+            { TRACE("k_flux_ctl"); k_flux_ctl<T><<<1, 1024, 0, stream>>>(d_star_int.p, d_red.p, d_list.p, ng, 1, nit_first, max_iter, o.ln_sub, d_ctr.p + CTR_ANY); }
+            stats.kernel_launches += 3;
             CK(cudaGetLastError());
-            publish(h_pin, d_ctr.p + any_slot, sizeof(int));
-            CK(cudaStreamSynchronize(stream));
-            if (!h_pin[0]) break;
-        }
-        if (nsv > 0) {
-            k_flux_scatter<T><<<(unsigned)((nsv + 255) / 256), 256, 0, stream>>>(surv(), nsv, pl);
-            stats.kernel_launches++;
-        }
-        // ---- lnlike / lnprob of every candidate, per-star max ----
-        if (tot > 0) {
-            FinalParams<T> fp;
-            fp.stars = d_stars.p; fp.pool = pl; fp.ncand = tot; fp.red = d_red.p; fp.dim_prior = o.dim_prior;
-            fp.npad = npad; fp.labels = d_labels.p; fp.ext = d_ext.p; fp.nlabel = nlabel;
-            k_final<T><<<(unsigned)((tot + kTile - 1) / kTile), kTile, 0, stream>>>(fp);
+            publish(h_ctr.data(), d_ctr.p, CTR_COUNT * sizeof(int));
+            stats.ms_select += phase_end();
+            const int nfix = h_ctr[CTR_NFIX];
+            int any = h_ctr[CTR_ANY];
+            stats.candidates += n;
+            stats.fixups += nfix;
+            phase_begin();
+            RecParams<T> rp{};
+            rp.rows = d_rows.p; rp.stars = d_stars.p; rp.star_int = d_star_int.p; rp.o = o; rp.pool = pl; rp.red = d_red.p;
+            if (nfix > 0) {
+                rp.n = nfix; rp.list = fixlist();
+                { TRACE("k_fixup"); kt->fixup(rp, stream); }
+                stats.kernel_launches++;
+                CK(cudaGetLastError());
+            }
+            // ---- further flux-space iterations for the stars that have not converged (:781-803); the per-star
+            // convergence test runs on the device, the host only polls "anything still active?".  The first
+            // extra iteration walks the whole pool and lists the active stars' survivors (in the memory of the
+            // fix-up list, consumed by now); later ones visit that list only. ----
+            int done_iter = nit_first;
+            bool have_list = false;
+            rp.n = n;
+            while (any && done_iter < max_iter) {
+                int any_slot = CTR_ANY;
+                for (int r = 0; r < 3 && done_iter < max_iter; r++) {
+                    if (!have_list) {
+                        rp.list = nullptr; rp.nlist = nullptr; rp.list_out = fixlist(); rp.nlist_out = d_ctr.p + CTR_NLIST;
+                        have_list = true;
+                    } else {
+                        rp.list = fixlist(); rp.nlist = d_ctr.p + CTR_NLIST; rp.list_out = nullptr; rp.nlist_out = nullptr;
+                    }
+                    { TRACE("k_flux_more"); kt->flux_more(rp, stream); }
+                    any_slot = CTR_ANY + 1 + r;
+                    { TRACE("k_flux_ctl"); k_flux_ctl<T><<<1, 1024, 0, stream>>>(d_star_int.p, d_red.p, d_list.p, ng, 0, 1, max_iter, o.ln_sub, d_ctr.p + any_slot); }
+                    stats.kernel_launches += 2;
+                    stats.flux_more_launches++;
+                    done_iter += 1;
+                }
+                CK(cudaGetLastError());
+                publish(h_ctr.data(), d_ctr.p, CTR_COUNT * sizeof(int));
+                CK(cudaStreamSynchronize(stream));
+                any = h_ctr[any_slot];
+            }
+            // ---- 3. lnlike / lnprob, per-star maximum, first selection, selection map scan ----
+            if (n > 0) {
+                { TRACE("k_final"); k_final<T><<<pass_ctas(n), kTile, 0, stream>>>(pp); }
+                { TRACE("k_sel"); k_sel<T><<<(unsigned)((n + kPassStep - 1) / kPassStep), kTile, 0, stream>>>(pp); }
+                stats.kernel_launches += 2;
+            }
+            { TRACE("k_cand_scan"); k_cand_scan<<<ng, 1024, 0, stream>>>(d_cand.p, d_wpre.p, d_list.p, nwords, d_ncand.p); }
             stats.kernel_launches++;
             CK(cudaGetLastError());
+            publish(h_ncand.data() + g0, d_ncand.p + g0, (size_t)ng * sizeof(int64_t));
+            publish(h_red.data(), d_red.p, (size_t)ns * kNumRed * sizeof(U));
+            publish(h_int.data(), d_star_int.p, (size_t)ns * SI_COUNT * sizeof(int));
+            stats.ms_flux += phase_end();
+            stats.d2h_bytes += (size_t)ns * (kNumRed * sizeof(U) + SI_COUNT * sizeof(int)) + ng * sizeof(int64_t);
+            // ---- was the sweep's candidate set a superset of the selection?  It is whenever the final
+            // max(lnprob) did not fall more than `slack` below the provisional one; otherwise redo the group
+            // with every model of those stars as a candidate (rare: counted in stats.fallbacks) ----
+            for (int s = g0; s < g1; s++) {
+                const double sl = (double)h_stars[(size_t)s * kStarStride + SR_SC + SC_SLACK];
+                if (!std::isfinite(sl)) continue;
+                const double M = (double)Enc<T>::dec(h_red[(size_t)s * kNumRed + RED_LNP]);
+                const double M0 = (double)Enc<T>::dec(h_red[(size_t)s * kNumRed + RED_M0]);
+                if (!(M >= M0 - sl)) {
+                    stats.fallbacks++;
+                    h_stars[(size_t)s * kStarStride + SR_SC + SC_SLACK] = (T)INFINITY;
+                    redo_all = true;
+                }
+            }
+            if (redo_all) {
+                CK(cudaMemcpyAsync(d_stars.p, h_stars.data(), (size_t)ns * kStarStride * sizeof(T), cudaMemcpyHostToDevice, stream));
+                continue;
+            }
+            for (int s = g0; s < g1; s++) stats.survivors += h_int[s * SI_COUNT + SI_NSURV];
+            *nrec = n;
         }
-        stats.ms_flux += phase_end();
+        *fits = true;
         return BF_OK;
     }
 
@@ -903,12 +1144,12 @@ template <typename T> struct Engine : EngineBase {
             prep_star(flux + (size_t)s * nfilt, errv + (size_t)s * nfilt, mask + (size_t)s * nfilt, nfilt,
                       par ? par[s] : NAN, perr ? perr[s] : NAN, apply_clip, slack, sp);
             for (int k = 0; k < kStarStride; k++) h_stars[(size_t)s * kStarStride + k] = (T)sp.row[k];
-            h_int[s * SI_COUNT + SI_NDIM] = sp.ndim;
+            int* si = &h_int[s * SI_COUNT];
+            for (int k = 0; k < SI_COUNT; k++) si[k] = 0;
+            si[SI_NDIM] = sp.ndim;
             // initial speculation: 2 mag iterations (what the reference needs in the common case)
-            h_int[s * SI_COUNT + SI_KSPEC] = std::min(2, max_iter);
+            si[SI_KSPEC] = std::min(2, max_iter);
             h_kpred[s] = 0;
-            h_int[s * SI_COUNT + SI_ACTIVE] = 0;
-            h_int[s * SI_COUNT + SI_NFLUX] = 0;
             if (ndim_out) ndim_out[s] = sp.ndim;
             if (mask_out) std::memcpy(mask_out + (size_t)s * nfilt, sp.clean, nfilt);
             for (int l = 0; l < nlabel; l++) {
@@ -936,29 +1177,29 @@ template <typename T> struct Engine : EngineBase {
         const int saved_labels = nlabel;
         nlabel = 0;  // loglike itself applies no label priors
         int32_t nd;
-        // slack = +inf: every model is a candidate, so the pool holds the whole grid in model order
+        // slack = +inf: every model is a candidate, so the pool holds a record of every model
         fill_rows(1, flux, errv, mask, &par, &perr, nullptr, nullptr, 0, INFINITY, max_iter, &nd, mask_out);
         rc = upload_stars(1);
         int nm = 0;
         std::vector<char> exact(1, 0);
         CK(cudaEventRecord(ev0, stream));
         if (!rc) rc = probe_k(1, o, max_iter);
-        if (!rc) rc = sweep(1, std::vector<int>(1, 0), exact, o, max_iter, &nm);
         int64_t tot = 0;
-        if (!rc) rc = fit_group(1, 0, 1, o, max_iter, &tot);
+        bool fits = true;
+        if (!rc) rc = process_group(1, 0, 1, o, max_iter, exact, &nm, &fits, &tot);
         nlabel = saved_labels;
         if (rc) return rc;
-        if (tot != nmodel) { err = "internal: full-length pass did not keep every model"; return BF_E_INVALID; }
+        if (!fits) { err = "bf_loglike_full: candidate pool too small for one star"; return BF_E_NOMEM; }
+        if (tot < nmodel) { err = "internal: full-length pass did not keep every model"; return BF_E_INVALID; }
         const size_t per = icov ? 14 : 5;
         CK(d_out.ensure((size_t)nmodel * per));
-        RecordParams<T, double> rp{};
-        rp.rows = d_rows.p; rp.stars = d_stars.p; rp.o = o; rp.pool = pool();
-        rp.sel_q = nullptr; rp.nrec = nmodel; rp.ld = 0; rp.nrows = 11; rp.o_idx = nullptr;
+        OutParams<T, double> op{};
+        op.pool = pool(); op.n = tot; op.star_int = d_star_int.p;
         double* b = d_out.p;
-        rp.o_lnl = b; rp.o_chi2 = b + nmodel; rp.o_scale = b + 2 * nmodel; rp.o_av = b + 3 * nmodel; rp.o_rv = b + 4 * nmodel;
-        rp.o_icov = icov ? b + 5 * nmodel : nullptr;
+        op.o_lnl = b; op.o_chi2 = b + nmodel; op.o_scale = b + 2 * nmodel; op.o_av = b + 3 * nmodel; op.o_rv = b + 4 * nmodel;
+        op.o_icov = icov ? b + 5 * nmodel : nullptr;
         phase_begin();
-        kt->records_full(rp, stream);
+        { TRACE("k_out_full"); k_out_full<T><<<(unsigned)((tot + kTile - 1) / kTile), kTile, 0, stream>>>(op); }
         stats.kernel_launches++;
         CK(cudaGetLastError());
         CK(cudaEventRecord(ev1, stream));
@@ -967,16 +1208,15 @@ template <typename T> struct Engine : EngineBase {
         CK(cudaEventElapsedTime(&ms, ev0, ev1));
         stats.ms_device = ms;
         const size_t nb = (size_t)nmodel * sizeof(double);
-        CK(cudaMemcpy(lnl, rp.o_lnl, nb, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(chi2, rp.o_chi2, nb, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(scale, rp.o_scale, nb, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(av, rp.o_av, nb, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(rv, rp.o_rv, nb, cudaMemcpyDeviceToHost));
-        if (icov) CK(cudaMemcpy(icov, rp.o_icov, nb * 9, cudaMemcpyDeviceToHost));
-        int hi[SI_COUNT];
-        CK(cudaMemcpy(hi, d_star_int.p, sizeof hi, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(lnl, op.o_lnl, nb, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(chi2, op.o_chi2, nb, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(scale, op.o_scale, nb, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(av, op.o_av, nb, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(rv, op.o_rv, nb, cudaMemcpyDeviceToHost));
+        if (icov) CK(cudaMemcpy(icov, op.o_icov, nb * 9, cudaMemcpyDeviceToHost));
         stats.d2h_bytes += nb * per;
-        if (diag) { diag[0] = nd; diag[1] = nm; diag[2] = hi[SI_NFLUX]; diag[3] = h_nsurv[0]; }
+        if (diag) { diag[0] = nd; diag[1] = nm; diag[2] = h_int[SI_NFLUX]; diag[3] = h_int[SI_NSURV]; }
+        trace_collect();
         return BF_OK;
     }
 
@@ -1000,29 +1240,28 @@ template <typename T> struct Engine : EngineBase {
         return BF_OK;
     }
 
-    // ---- the catalogue pipeline shared by bf_sweep_batch and bf_fit_batch: star batches -> sweep -> groups of
-    // stars whose candidates fit in the pool -> flux loops -> first selection -> ordered records in a device
-    // staging buffer; `consume` then ships them (B2) or integrates the priors over them (device posterior).
+    // ---- the catalogue pipeline shared by bf_sweep_batch and bf_fit_batch: star batches -> groups of stars
+    // whose candidate records fit in the pool -> process_group -> ordered records of the first selection in a
+    // device staging buffer; `consume` then ships them (B2) or integrates the priors over them (device posterior).
     struct GroupCtx {
         int64_t s0;          // catalogue index of slot 0 of the batch
         int ns, g0, g1;      // stars in the batch; slots [g0, g1) of this group
         int64_t nsel_tot;    // records of the group (first selection)
-        int buf;             // staging buffer used
+        const int* ord;      // [nsel_tot] pool index of each selected record, in (star, model) order
+        int buf;             // staging buffer used (records-out path only)
         T* rows;             // [11][nsel_tot]
         int* idx;            // [nsel_tot] model index
-        int* rstar;          // [nsel_tot] star slot (only when requested)
         DevOpts<T> o;
     };
 
     template <typename Consumer>
     int run_catalogue(int64_t nstar, const double* flux, const double* errv, const uint8_t* mask,
                       const double* par, const double* perr, const double* ext_mean, const double* ext_std,
-                      const bf_options* opt, int record_rows, bool want_rstar, int32_t* ndim, int32_t* n_iter,
+                      const bf_options* opt, int record_rows, bool want_rows, int32_t* ndim, int32_t* n_iter,
                       int64_t* n_surv, double* max_lnprob, int64_t* offsets, int batch_limit, Consumer&& consume) {
         DevOpts<T> o; int max_iter;
         int rc = make_opts(opt, o, max_iter);
         if (rc) return rc;
-        const PoolArrays<T> pl = pool();
         const double slack = opt->select_slack;
         std::vector<int> nm(batch_cap);
         std::vector<char> exact(batch_cap);
@@ -1039,97 +1278,84 @@ template <typename T> struct Engine : EngineBase {
             rc = upload_stars(ns);
             if (rc) return rc;
             CK(cudaEventRecord(ev0, stream));
-            std::vector<int> all(ns);
-            for (int s = 0; s < ns; s++) { all[s] = s; exact[s] = 0; }
+            for (int s = 0; s < ns; s++) exact[s] = 0;
             rc = probe_k(ns, o, max_iter);
             if (rc) return rc;
-            rc = sweep(ns, all, exact, o, max_iter, nm.data());
-            if (rc) return rc;
-            // groups of consecutive stars whose candidates fit in the pool together
-            int g0 = 0;
-            while (g0 < ns) {
-                int g1 = g0;
-                int64_t cnt = 0;
-                while (g1 < ns && (g1 == g0 || cnt + h_ncand[g1] <= pool_cap)) { cnt += h_ncand[g1]; g1++; }
-                if (cnt > pool_cap) { err = "internal: candidate pool too small"; return BF_E_NOMEM; }
+            // groups of consecutive stars whose candidate records fit in the pool together: the whole batch
+            // first; a group that overflows is split by its (now known) candidate counts
+            std::deque<std::pair<int, int>> groups;
+            groups.emplace_back(0, ns);
+            while (!groups.empty()) {
+                const int g0 = groups.front().first, g1 = groups.front().second;
+                groups.pop_front();
                 const int ng = g1 - g0;
-                int64_t tot = 0;
-                rc = fit_group(ns, g0, g1, o, max_iter, &tot);
+                int64_t nrec = 0;
+                bool fits = true;
+                rc = process_group(ns, g0, g1, o, max_iter, exact, nm.data(), &fits, &nrec);
                 if (rc) return rc;
-                // ---- first selection of lnpost (brutus/fitting.py:988-991): count ----
-                SelParams<T> sp;
-                sp.pool = pl; sp.ncand = tot; sp.red = d_red.p; sp.ln_wt = o.ln_wt; sp.blk = d_blk.p;
-                sp.nsel = d_nsel.p; sp.sel_q = selq();
-                const int64_t nblk = (tot + kTile - 1) / kTile;
-                phase_begin();
-                if (tot > 0) {
-                    k_sel_count<T><<<(unsigned)nblk, kTile, 0, stream>>>(sp);
-                    k_scan_blocks<<<1, 1024, 0, stream>>>(d_blk.p, nblk, d_tot.p);
-                    stats.kernel_launches += 2;
-                    CK(cudaGetLastError());
-                }
-                publish(h_nsel.data() + g0, d_nsel.p + g0, (size_t)ng * sizeof(int));
-                publish(h_red.data(), d_red.p, (size_t)ns * kNumRed * sizeof(U));
-                publish(h_int.data(), d_star_int.p, (size_t)ns * SI_COUNT * sizeof(int));
-                stats.ms_select += phase_end();
-                stats.d2h_bytes += (size_t)ns * (kNumRed * sizeof(U) + SI_COUNT * sizeof(int)) + ng * sizeof(int);
-                // ---- was the sweep's candidate set a superset of the selection?  It is whenever the final
-                // max(lnprob) did not fall more than `slack` below the provisional one; otherwise redo those
-                // stars with every model as a candidate (rare: counted in stats.fallbacks) ----
-                std::vector<int> redo;
-                for (int s = g0; s < g1; s++) {
-                    const double sl = (double)h_stars[(size_t)s * kStarStride + SR_SC + SC_SLACK];
-                    if (!std::isfinite(sl)) continue;
-                    const double M = (double)Enc<T>::dec(h_red[(size_t)s * kNumRed + RED_LNP]);
-                    const double M0 = (double)Enc<T>::dec(h_red[(size_t)s * kNumRed + RED_M0]);
-                    if (!(M >= M0 - sl)) redo.push_back(s);
-                }
-                if (!redo.empty()) {
-                    stats.fallbacks += (int64_t)redo.size();
-                    for (int s : redo) h_stars[(size_t)s * kStarStride + SR_SC + SC_SLACK] = (T)INFINITY;
-                    CK(cudaMemcpyAsync(d_stars.p, h_stars.data(), (size_t)ns * kStarStride * sizeof(T), cudaMemcpyHostToDevice, stream));
-                    rc = sweep(ns, redo, exact, o, max_iter, nullptr);
-                    if (rc) return rc;
-                    continue;  // regroup from g0 with the new candidate counts
+                if (!fits) {
+                    if (ng == 1) { err = "internal: candidate pool too small for one star"; return BF_E_NOMEM; }
+                    stats.regroups++;
+                    // headroom: stale records of re-swept stars are gone now (the counts are exact), what remains
+                    // is the run-to-run variation of the candidate superset
+                    std::vector<std::pair<int, int>> parts;
+                    int a = g0;
+                    int64_t cnt = 0;
+                    for (int s = g0; s < g1; s++) {
+                        const int64_t need = h_ncand[s] + h_ncand[s] / 16 + 64;
+                        if (s > a && cnt + need > pool_cap) { parts.emplace_back(a, s); a = s; cnt = 0; }
+                        cnt += need;
+                    }
+                    parts.emplace_back(a, g1);
+                    if (parts.size() == 1) { parts.clear(); parts.emplace_back(g0, g0 + ng / 2); parts.emplace_back(g0 + ng / 2, g1); }
+                    for (size_t k = parts.size(); k-- > 0;) groups.push_front(parts[k]);
+                    continue;
                 }
                 int64_t nsel_tot = 0;
                 for (int s = g0; s < g1; s++) {
                     if (n_iter) { n_iter[2 * (s0 + s)] = nm[s]; n_iter[2 * (s0 + s) + 1] = h_int[s * SI_COUNT + SI_NFLUX]; }
-                    if (n_surv) n_surv[s0 + s] = h_nsurv[s];
+                    if (n_surv) n_surv[s0 + s] = h_int[s * SI_COUNT + SI_NSURV];
                     if (max_lnprob) {
                         T v = Enc<T>::dec(h_red[(size_t)s * kNumRed + RED_LNP]);
                         max_lnprob[s0 + s] = (v <= Num<T>::kNegBig) ? -1e300 : (double)v;
                     }
-                    offsets[s0 + s + 1] = offsets[s0 + s] + h_nsel[s];
-                    nsel_tot += h_nsel[s];
+                    h_base[s] = nsel_tot;
+                    offsets[s0 + s + 1] = offsets[s0 + s] + h_ncand[s];
+                    nsel_tot += h_ncand[s];
                 }
                 stats.selected += nsel_tot;
-                // ---- ordered compaction + records into a device staging buffer ----
+                // ---- ordered records of the selection into a device staging buffer ----
                 GroupCtx gc{};
                 gc.s0 = s0; gc.ns = ns; gc.g0 = g0; gc.g1 = g1; gc.nsel_tot = nsel_tot; gc.o = o;
                 if (nsel_tot > 0) {
-                    const int buf = grp & 1;
-                    grp++;
-                    CK(cudaStreamWaitEvent(stream, ev_cp[buf], 0));  // staging buffer free again?
                     phase_begin();
-                    k_sel_write<T><<<(unsigned)nblk, kTile, 0, stream>>>(sp);
-                    CK(d_stage[buf].ensure((size_t)nsel_tot * (sizeof(int) + 11 * sizeof(T))));
-                    if (want_rstar) CK(d_rstar.ensure((size_t)nsel_tot));
-                    RecordParams<T, T> rp{};
-                    rp.rows = d_rows.p; rp.stars = d_stars.p; rp.o = o; rp.pool = pl;
-                    rp.sel_q = selq(); rp.nrec = nsel_tot;
-                    T* b = (T*)d_stage[buf].p;                                   // [11][nsel_tot] rows, then idx
-                    rp.o_idx = (int*)(d_stage[buf].p + (size_t)11 * nsel_tot * sizeof(T));
-                    rp.o_star = want_rstar ? d_rstar.p : nullptr;
-                    rp.ld = nsel_tot; rp.nrows = record_rows;
-                    rp.o_lnl = b; rp.o_scale = b + nsel_tot; rp.o_av = b + 2 * nsel_tot; rp.o_chi2 = b + 3 * nsel_tot;
-                    rp.o_rv = b + 4 * nsel_tot; rp.o_icov = b + 5 * nsel_tot;
-                    kt->records(rp, stream);
-                    stats.kernel_launches += 2;
+                    CK(cudaMemcpyAsync(d_base.p + g0, h_base.data() + g0, (size_t)ng * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+                    CK(d_ord.ensure((size_t)nsel_tot));
+                    OutParams<T, T> op{};
+                    op.pool = pool(); op.n = nrec; op.star_int = d_star_int.p;
+                    op.sel = d_cand.p; op.wpre = d_wpre.p; op.nwords = nwords; op.base = d_base.p;
+                    op.ord = d_ord.p; op.nsel = nsel_tot;
+                    { TRACE("k_ord"); k_ord<T><<<(unsigned)((nrec + kPassStep - 1) / kPassStep), kTile, 0, stream>>>(op); }
+                    stats.kernel_launches++;
+                    gc.ord = d_ord.p;
+                    if (want_rows) {   // records-out: the ordered [11][nsel_tot] matrix + model indices in a staging buffer
+                        const int buf = grp & 1;
+                        grp++;
+                        CK(cudaStreamWaitEvent(stream, ev_cp[buf], 0));  // staging buffer free again?
+                        CK(d_stage[buf].ensure((size_t)nsel_tot * (sizeof(int) + 11 * sizeof(T))));
+                        T* b = (T*)d_stage[buf].p;                                   // [11][nsel_tot] rows, then idx
+                        op.o_idx = (int*)(d_stage[buf].p + (size_t)11 * nsel_tot * sizeof(T));
+                        op.o_star = nullptr;
+                        op.ld = nsel_tot; op.nrows = record_rows;
+                        op.o_lnl = b; op.o_scale = b + nsel_tot; op.o_av = b + 2 * nsel_tot; op.o_chi2 = b + 3 * nsel_tot;
+                        op.o_rv = b + 4 * nsel_tot; op.o_icov = b + 5 * nsel_tot;
+                        { TRACE("k_out"); k_out<T><<<(unsigned)((nsel_tot + kTile - 1) / kTile), kTile, 0, stream>>>(op); }
+                        stats.kernel_launches++;
+                        CK(cudaEventRecord(ev_rec[buf], stream));
+                        gc.buf = buf; gc.rows = b; gc.idx = op.o_idx;
+                    }
                     CK(cudaGetLastError());
-                    CK(cudaEventRecord(ev_rec[buf], stream));
                     CK(cudaEventRecord(evB, stream));
-                    gc.buf = buf; gc.rows = b; gc.idx = rp.o_idx; gc.rstar = rp.o_star;
                 }
                 rc = consume(gc);
                 if (rc) return rc;
@@ -1139,7 +1365,6 @@ template <typename T> struct Engine : EngineBase {
                     CK(cudaEventElapsedTime(&msr, evA, evB));
                     stats.ms_select += msr;
                 }
-                g0 = g1;
             }
             CK(cudaEventRecord(ev1, stream));
             CK(cudaEventSynchronize(ev1));
@@ -1182,10 +1407,11 @@ template <typename T> struct Engine : EngineBase {
         };
         int ship_batch = kShipBatch;
         if (const char* e = getenv("BRUTUS_B200_SHIP_BATCH")) ship_batch = std::max(1, atoi(e));
-        int rc = run_catalogue(nstar, flux, errv, mask, par, perr, ext_mean, ext_std, opt, record_rows, false, ndim,
+        int rc = run_catalogue(nstar, flux, errv, mask, par, perr, ext_mean, ext_std, opt, record_rows, true, ndim,
                                n_iter, n_surv, max_lnprob, offsets, opt->skip_d2h ? batch_cap : ship_batch, ship);
         if (rc) return rc;
         CK(cudaStreamSynchronize(copy_stream));
+        trace_collect();
         out->n = opt->skip_d2h ? 0 : written;
         out->stride = arena_cap;
         out->elem_size = (int32_t)sizeof(T);
@@ -1354,7 +1580,8 @@ template <typename T> struct Engine : EngineBase {
             }
             const int64_t n1 = g.nsel_tot;
             PostParams<T> pp{};
-            pp.rows = g.rows; pp.ld = n1; pp.idx = g.idx; pp.rstar = g.rstar; pp.n1 = n1;
+            if (n1 > 0) CK(d_rstar.ensure((size_t)n1));
+            pp.ord = g.ord; pp.pool = pool(); pp.rstar = d_rstar.p; pp.n1 = n1;
             pp.lnprior = have_prior[0] ? d_lnprior.p : nullptr;
             pp.feh = have_prior[1] ? d_feh.p : nullptr;
             pp.loga = have_prior[2] ? d_loga.p : nullptr;
@@ -1379,9 +1606,9 @@ template <typename T> struct Engine : EngineBase {
                 CK(d_lnb1.ensure((size_t)n1));
                 pp.lnp1 = d_lnp1.p; pp.lnp2 = d_lnp2.p; pp.sel2 = d_sel2.p; pp.cdf = d_cdf.p; pp.lnb1 = d_lnb1.p;
                 const unsigned nb1 = (unsigned)((n1 + kTile - 1) / kTile);
-                k_post_mle<T><<<nb1, kTile, 0, stream>>>(pp);
-                k_post_count<T><<<nb1, kTile, 0, stream>>>(pp);
-                k_scan_blocks<<<1, 1024, 0, stream>>>(d_blk.p, nb1, d_tot.p);
+                { TRACE("k_post_mle"); k_post_mle<T><<<nb1, kTile, 0, stream>>>(pp); }
+                { TRACE("k_post_count"); k_post_count<T><<<nb1, kTile, 0, stream>>>(pp); }
+                { TRACE("k_scan_blocks"); k_scan_blocks<<<1, 1024, 0, stream>>>(d_blk.p, nb1, d_tot.p); }
                 stats.kernel_launches += 3;
                 CK(cudaGetLastError());
             }
@@ -1410,7 +1637,7 @@ template <typename T> struct Engine : EngineBase {
                     pp.n2 = n2; pp.keys = d_keys.p;
                     CK(cudaMemcpyAsync(d_off2.p + g.g0, h_off2.data() + g.g0, (size_t)(ng + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
                     const unsigned nb1 = (unsigned)((n1 + kTile - 1) / kTile);
-                    k_post_write<T><<<nb1, kTile, 0, stream>>>(pp);
+                    { TRACE("k_post_write"); k_post_write<T><<<nb1, kTile, 0, stream>>>(pp); }
                     k_post_keys<T><<<(unsigned)((n2 + 255) / 256), 256, 0, stream>>>(pp);
                     size_t tmp_bytes = 0;
                     CK(cub::DeviceSegmentedRadixSort::SortKeysDescending(nullptr, tmp_bytes, d_keys.p, d_keys_sorted.p, (int)n2, nseg,
@@ -1422,8 +1649,8 @@ template <typename T> struct Engine : EngineBase {
                     k_post_thr<T><<<(nseg + 255) / 256, 256, 0, stream>>>(d_keys_sorted.p, d_seg.p, d_seg.p + 2 * nseg, nseg, po->nsel_max, d_clip.p);
                     pp.clip_thr = d_clip.p;
                     CK(cudaMemsetAsync(d_nsel2.p + g.g0, 0, (size_t)ng * sizeof(int), stream));
-                    k_post_count<T><<<nb1, kTile, 0, stream>>>(pp);
-                    k_scan_blocks<<<1, 1024, 0, stream>>>(d_blk.p, nb1, d_tot.p);
+                    { TRACE("k_post_count"); k_post_count<T><<<nb1, kTile, 0, stream>>>(pp); }
+                    { TRACE("k_scan_blocks"); k_scan_blocks<<<1, 1024, 0, stream>>>(d_blk.p, nb1, d_tot.p); }
                     stats.kernel_launches += 7;
                     CK(cudaGetLastError());
                     publish(h_nsel2.data() + g.g0, d_nsel2.p + g.g0, (size_t)ng * sizeof(int));
@@ -1441,15 +1668,15 @@ template <typename T> struct Engine : EngineBase {
             CK(cudaMemcpyAsync(d_off2.p + g.g0, h_off2.data() + g.g0, (size_t)(ng + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
             if (n2 > 0) {
                 const unsigned nb1 = (unsigned)((n1 + kTile - 1) / kTile);
-                k_post_write<T><<<nb1, kTile, 0, stream>>>(pp);
-                if (pp.zov) k_post_mc<T, true><<<(unsigned)((n2 + kTile - 1) / kTile), kTile, 0, stream>>>(pp);
-                else k_post_mc<T, false><<<(unsigned)((n2 + kTile - 1) / kTile), kTile, 0, stream>>>(pp);
+                { TRACE("k_post_write"); k_post_write<T><<<nb1, kTile, 0, stream>>>(pp); }
+                if (pp.zov) { TRACE("k_post_mc"); k_post_mc<T, true><<<(unsigned)((n2 + kTile - 1) / kTile), kTile, 0, stream>>>(pp); }
+                else { TRACE("k_post_mc"); k_post_mc<T, false><<<(unsigned)((n2 + kTile - 1) / kTile), kTile, 0, stream>>>(pp); }
                 stats.kernel_launches += 2;
             }
-            k_post_cdf<T><<<ng, 1024, 0, stream>>>(pp);
+            { TRACE("k_post_cdf"); k_post_cdf<T><<<ng, 1024, 0, stream>>>(pp); }
             const int dthreads = std::min(kTile, (nd + 31) / 32 * 32);   // the kernel strides over the draws
-            if (pp.zov) k_post_draw<T, true><<<ng, dthreads, 0, stream>>>(pp);
-            else k_post_draw<T, false><<<ng, dthreads, 0, stream>>>(pp);
+            if (pp.zov) { TRACE("k_post_draw"); k_post_draw<T, true><<<ng, dthreads, 0, stream>>>(pp); }
+            else { TRACE("k_post_draw"); k_post_draw<T, false><<<ng, dthreads, 0, stream>>>(pp); }
             stats.kernel_launches += 2;
             CK(cudaGetLastError());
             CK(cudaEventRecord(evP1, stream));
@@ -1470,10 +1697,11 @@ template <typename T> struct Engine : EngineBase {
             stats.d2h_bytes += cnt * (sizeof(int) + 17 * sizeof(double)) + 2 * (size_t)ng * sizeof(double);
             return BF_OK;
         };
-        int rc = run_catalogue(nstar, flux, errv, mask, par, perr, ext_mean, ext_std, opt, 11, true, ndim, n_iter,
+        int rc = run_catalogue(nstar, flux, errv, mask, par, perr, ext_mean, ext_std, opt, 11, false, ndim, n_iter,
                                nullptr, nullptr, offsets.data(), batch_cap, post);
         d_zov.release(); d_uov.release();
         if (rc) return rc;
+        trace_collect();
         out->model_idx = hidx;
         out->scale = hd; out->av = hd + ntot; out->rv = hd + 2 * ntot; out->lnprob = hd + 3 * ntot; out->dist = hd + 4 * ntot;
         out->red = hd + 5 * ntot; out->dred = hd + 6 * ntot; out->logwt = hd + 7 * ntot; out->cov_sar = hd + 8 * ntot;
@@ -1623,6 +1851,8 @@ int bf_flush_l2(bf_handle* h) {
     if (!h) return BF_E_INVALID;
     return h->eng->flush_l2();
 }
+
+const char* bf_get_trace(bf_handle* h) { return h ? h->eng->get_trace() : ""; }
 
 int bf_get_stats(const bf_handle* h, bf_stats* out) {
     if (!h || !out) return BF_E_INVALID;

@@ -8,9 +8,13 @@
 //                                        to 16 B): per-candidate gathers touch 3-4 sectors instead of 3*NB
 //   stars  T [batch][kStarStride]       per-star normalised photometry, see the star row below
 //   cand   u32 [batch][npad/32]         candidate bitmap written by the sweep (superset of everything
-//                                        that can survive the cull or pass the selection threshold)
+//                                        that can survive the cull or pass the selection threshold); the
+//                                        bits of candidates that fail the selection are cleared later, and
+//                                        the rank of a bit gives a record its (star, model)-ordered position
 //   red    U [batch][kNumRed]           per-star max-reductions, order-preserving unsigned encoding
-//   pool   candidate records (SoA)      one record per candidate (star, model), ascending (star, model)
+//   pool   candidate records (SoA)      one COMPLETE record per candidate (star, model), appended by the
+//                                        sweep itself in groups of <= 32 (one warp flush), in no particular
+//                                        order: fitted values, flux-loop state and the precision matrix
 //
 // Nothing of size O(Nmodel x stars) other than the 1-bit candidate map is ever written.
 #pragma once
@@ -46,9 +50,12 @@ enum StarScalar {
     SC_COUNT
 };
 constexpr int kStarStride = SR_SC + 16;
+// star rows staged in shared memory use a padded stride: rows stay 16-byte aligned (the sweep reads them
+// with broadcast LDS.128) and lanes that read rows of DIFFERENT stars (the dense phase) spread over the banks
+constexpr int kStarSmem = kStarStride + 4;
 
 // per-star ints
-enum StarInt { SI_NDIM = 0, SI_KSPEC, SI_ACTIVE, SI_NFLUX, SI_COUNT = 4 };
+enum StarInt { SI_NDIM = 0, SI_KSPEC, SI_ACTIVE, SI_NFLUX, SI_EPOCH, SI_NSURV, SI_COUNT = 8 };
 
 // per-star reductions
 enum Red {
@@ -68,8 +75,15 @@ enum Red {
 };
 constexpr int kSweepRed = 6;     // RED_L0 .. RED_M0 are produced by the sweep
 
-// candidate record flags
-constexpr int kFlagSurv = 1;     // survived the cull (brutus/fitting.py:758-759)
+// candidate record tag (PoolArrays::sflag): star slot | sweep epoch of the star << 16 | flags << 24.
+// A star that is swept again (other iteration count) bumps its epoch; records of older epochs are stale.
+constexpr int kFlagFluxed = 1;   // the sweep ran the first flux iterations on it (it was a likely survivor)
+constexpr int kFlagSurv = 2;     // survived the cull (brutus/fitting.py:758-759)
+constexpr int kFlagSel = 4;      // passed lnpost's first selection (brutus/fitting.py:988-991)
+__host__ __device__ constexpr int tag_slot(int t) { return t & 0xffff; }
+__host__ __device__ constexpr int tag_epoch(int t) { return (t >> 16) & 0xff; }
+__host__ __device__ constexpr int tag_flags(int t) { return (t >> 24) & 0xff; }
+__host__ __device__ constexpr int make_tag(int slot, int epoch, int flags) { return slot | (epoch & 0xff) << 16 | flags << 24; }
 
 // ---- order-preserving float -> unsigned encoding (so atomicMax works on floats) ---------------
 template <typename T> struct Enc;
@@ -193,12 +207,120 @@ __device__ __forceinline__ P2<float> ld2(const float* p) { P2<float> r; r.v = *r
 __device__ __forceinline__ P2<double> ld2(const double* p) { return mk2(p[0], p[1]); }
 
 
-// ---- per-star aggregation inside a CTA of candidate records ------------------------------------------
-// Records are sorted by star, so most CTAs see one or two stars.  Values for the star of the CTA's first
-// record are combined in shared memory and published by ONE global atomic per CTA; records of other
-// stars (CTAs that straddle a star boundary) fall back to warp-level / per-thread global atomics.
-// Without this, the per-star global atomics of a few million consecutive records serialise on one or
-// two L2 addresses.  All threads of the CTA must call these (they contain __syncthreads()).
+// ---- per-star aggregation over candidate records --------------------------------------------------------
+// The pool is appended by warp flushes of the sweep: consecutive records belong to the ~32 stars of one
+// star chunk, in short runs (a flush holds a handful of stars).  Per-record -- or even per-run -- global
+// atomics on the per-star maxima would serialise on a few dozen L2 addresses (measured: 7 ms per 1 000
+// stars for the cull pass alone).  Instead every CTA walks a long CONTIGUOUS range of records and combines
+// in three levels: lanes of a run with one redux (float), runs into a small per-CTA table in shared memory,
+// and the table into global memory once at the end of the range.
+constexpr int kAggSlots = 64;
+constexpr int kPassCtas = 148 * 8;   // CTAs of a pass over the pool (each takes a contiguous range of records)
+
+// lanes [start, end) holding the same star slot as this lane (records of a star are contiguous in a flush)
+__device__ __forceinline__ unsigned run_mask(int slot, int lane, int& start) {
+    const int prev = __shfl_up_sync(0xffffffffu, slot, 1);
+    const unsigned starts = __ballot_sync(0xffffffffu, lane == 0 || prev != slot);
+    start = 31 - __clz(starts & (0xffffffffu >> (31 - lane)));
+    const unsigned above = lane == 31 ? 0u : (starts & (0xffffffffu << (lane + 1)));
+    const unsigned upto = above ? ((1u << (__ffs(above) - 1)) - 1u) : 0xffffffffu;
+    return upto & ~((1u << start) - 1u);
+}
+
+template <typename T, int NR> struct StarAgg {
+    using U = typename Enc<T>::U;
+    int tag[kAggSlots];
+    int cnt[kAggSlots];
+    U v[NR][kAggSlots];
+    __device__ __forceinline__ void init() {
+        for (int t = threadIdx.x; t < kAggSlots; t += blockDim.x) {
+            tag[t] = -1; cnt[t] = 0;
+#pragma unroll
+            for (int k = 0; k < NR; k++) v[k][t] = U(0);   // 0 encodes below every value
+        }
+    }
+    // table entry of `slot`, or -1 when its hash bucket belongs to another star (then: global atomics).
+    // Plain reads first: almost every call finds its star already in the table and its maximum unchanged, and
+    // shared-memory atomics are what bounds these passes otherwise.
+    __device__ __forceinline__ int claim(int slot) {
+        const int h = slot & (kAggSlots - 1);
+        const int cur = *(volatile int*)&tag[h];
+        if (cur == slot) return h;
+        if (cur != -1) return -1;
+        const int old = atomicCAS(&tag[h], -1, slot);
+        return (old == -1 || old == slot) ? h : -1;
+    }
+    // call with every lane of the warp; `which[k]` are the RED_* indices of the NR maxima
+    __device__ __forceinline__ void add(U* red, const int (&which)[NR], int* cnt_glob, int cnt_stride, int slot,
+                                        bool have, const T (&val)[NR], bool count_flag) {
+        const int lane = threadIdx.x & 31;
+        int start;
+        const unsigned mask = run_mask(slot, lane, start);
+        U m[NR];
+#pragma unroll
+        for (int k = 0; k < NR; k++) m[k] = (have && val[k] == val[k]) ? Enc<T>::enc(val[k]) : U(0);
+        warp_combine(m, mask);
+        const int nc = __popc(__ballot_sync(0xffffffffu, count_flag) & mask);
+        if (lane != start || slot < 0) return;
+        const int h = claim(slot);
+#pragma unroll
+        for (int k = 0; k < NR; k++) {
+            if (m[k] == U(0)) continue;
+            if (h >= 0) { if (m[k] > *(volatile U*)&v[k][h]) atomicMax(&v[k][h], m[k]); }
+            else atomicMax(&red[(int64_t)slot * kNumRed + which[k]], m[k]);
+        }
+        if (cnt_glob && nc > 0) {
+            if (h >= 0) atomicAdd(&cnt[h], nc);
+            else atomicAdd(&cnt_glob[(int64_t)slot * cnt_stride], nc);
+        }
+    }
+    __device__ __forceinline__ void flush(U* red, const int (&which)[NR], int* cnt_glob, int cnt_stride) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < kAggSlots; t += blockDim.x) {
+            const int slot = tag[t];
+            if (slot < 0) continue;
+#pragma unroll
+            for (int k = 0; k < NR; k++)
+                if (v[k][t] != U(0)) atomicMax(&red[(int64_t)slot * kNumRed + which[k]], v[k][t]);
+            if (cnt_glob && cnt[t] > 0) atomicAdd(&cnt_glob[(int64_t)slot * cnt_stride], cnt[t]);
+        }
+    }
+    // float: one redux per maximum; double (verification path): shuffle over the run
+    __device__ __forceinline__ static void warp_combine(unsigned int (&m)[NR], unsigned mask) {
+#pragma unroll
+        for (int k = 0; k < NR; k++) m[k] = __reduce_max_sync(mask, m[k]);
+    }
+    __device__ __forceinline__ static void warp_combine(unsigned long long (&m)[NR], unsigned mask) {
+#pragma unroll
+        for (int k = 0; k < NR; k++) {
+            const unsigned long long x0 = m[k];
+            unsigned long long x = x0;
+            for (int j = 0; j < 32; j++) {
+                const unsigned long long y = __shfl_sync(0xffffffffu, x0, j);
+                if ((mask >> j & 1u) && y > x) x = y;
+            }
+            m[k] = x;
+        }
+    }
+};
+
+// The passes are streams of small dependent loads (tag -> star -> fields); a thread works on kPassU records at
+// a time so that their loads overlap (one record per thread left the passes at a quarter of the HBM bandwidth).
+constexpr int kPassU = 4;
+constexpr int kPassStep = kTile * kPassU;
+
+// the contiguous range of records [lo, hi) of this CTA, in whole kPassStep-record steps
+__device__ __forceinline__ void pass_range(int64_t n, int64_t& lo, int64_t& hi) {
+    int64_t per = (n + gridDim.x - 1) / gridDim.x;
+    per = (per + kPassStep - 1) / kPassStep * kPassStep;
+    lo = (int64_t)blockIdx.x * per;
+    hi = lo + per < n ? lo + per : n;
+    if (lo > hi) lo = hi;
+}
+
+// Same, for kernels whose records ARE sorted by star (the posterior works on the ordered selection), so most
+// CTAs see one or two stars: values for the star of the CTA's first record are combined in shared memory and
+// published by ONE global atomic per CTA.  All threads of the CTA must call these (they contain __syncthreads()).
 template <typename T>
 __device__ __forceinline__ void cta_star_max(typename Enc<T>::U* red, int which, int slot, bool have, T v) {
     using U = typename Enc<T>::U;
@@ -285,6 +407,18 @@ __device__ __forceinline__ T ext_prior(const T* __restrict__ labels, const T* __
 }
 
 // ---- kernel parameter blocks ----------------------------------------------------------------------
+// Candidate pool (SoA, one entry per (star, model) the sweep flagged, unordered).
+template <typename T> struct PoolArrays {
+    int *model;       // model index
+    int *sflag;       // make_tag(star slot, epoch, flags)
+    T *av, *rv, *chi2, *scale, *sden;   // current fit (flux-phase values once kFlagFluxed)
+    T *lp;            // cull statistic lnl_p at the magnitude-fit (Av, Rv)      (brutus/fitting.py:747-756)
+    T *eta, *lold, *lprev;              // flux-loop state: stepsize, lnl_new of the last two iterations (:778-803)
+    T *isa, *isr, *iaa, *iar, *irr;     // precision matrix icov_sar at the current fit; ss = sden (:563-574)
+    T *lnl, *lnprob;  // written by k_final; until then, for fluxed records: the magnitude-fit (Av, Rv)
+};
+constexpr int kPoolInts = 2, kPoolReals = 16;
+
 template <typename T> struct SweepParams {
     const float* grid;        // [3][NB][npad]
     int64_t npad, nmodel;
@@ -299,62 +433,25 @@ template <typename T> struct SweepParams {
     const T* labels;          // [nlabel][npad]
     const T* ext;             // [batch][nlabel][3]
     int nlabel;
+    PoolArrays<T> pool;
+    int64_t pool_cap;
+    unsigned long long* pool_count;   // [1] records appended so far (keeps counting past pool_cap)
+    int nit_first;            // flux iterations the sweep runs on likely survivors: min(2, max_iter)
 };
 
-template <typename T> struct PoolArrays {
-    int *model, *star, *flag;                // [cap]
-    T *av, *rv, *chi2, *scale, *sden, *lnl, *lnprob;
-};
-
-// compact working set of the flux loops: one entry per survivor of the cull, any order
-template <typename T> struct SurvArrays {
-    int *q, *model, *star;                   // q = index of the survivor's candidate record
-    T *av, *rv, *eta, *lold, *chi2, *scale, *sden;
-};
-
-// re-fit of the candidates (exact mag fit of the (star, model) pairs flagged by the sweep)
-template <typename T> struct RefitParams {
+// passes over the n records of the pool that need the model's coefficients again (both rare)
+template <typename T> struct RecParams {
     const float* rows;        // [npad][row_stride]
     const T* stars;
     const int* star_int;
     DevOpts<T> o;
     PoolArrays<T> pool;
-    int64_t ncand;
-    const typename Enc<T>::U* red;
-    SurvArrays<T> sv;         // survivors are appended here (CTA-granular, any order)
-    int* nsv;                 // [1] total survivors appended
-    int* nsurv;               // [batch] per-star survivor count
-};
-
-template <typename T> struct FluxParams {
-    const float* rows;
-    const T* stars;
-    const int* star_int;
-    DevOpts<T> o;
-    SurvArrays<T> sv;
-    int64_t nsv;
-    int nit;                 // flux iterations executed by this launch (2 first, then 1)
+    int64_t n;                // records of the pool (k_flux_more) / entries of `list` (k_fixup)
+    const int* list;          // k_fixup: pool indices to redo; k_flux_more: the active survivors, or null = whole pool
+    const int* nlist;         // k_flux_more with a list: its length (device)
+    int* list_out;            // k_flux_more over the whole pool: receives the active survivors' indices
+    int* nlist_out;
     typename Enc<T>::U* red;
-};
-
-// O = element type of the outputs: double for the full-length B1 arrays (the reference returns
-// float64), T for the compacted B2 records (no point shipping more bits than were computed).
-template <typename T, typename O> struct RecordParams {
-    const float* rows;
-    const T* stars;
-    DevOpts<T> o;
-    PoolArrays<T> pool;
-    // mode A (compacted records): nrec selected pool entries sel_q[0..nrec)
-    // mode B (full-length, one star whose candidates are all models): sel_q == nullptr, nrec = nmodel
-    const int* sel_q;
-    int64_t nrec;
-    // outputs.  Mode A: rows of a [11][ld] matrix: lnl, scale, av, chi2, rv, icov(ss,sa,sr,aa,ar,rr);
-    // only the first `nrows` are produced (3, 5 or 11).  Mode B: separate arrays, icov 9 per model.
-    O *o_lnl, *o_chi2, *o_scale, *o_av, *o_rv, *o_icov;
-    int64_t ld;
-    int nrows;
-    int* o_idx;   // mode A: model index of each record
-    int* o_star;  // mode A, optional: star slot of each record (device posterior)
 };
 
 // Kernel launchers instantiated once per band count (inst.cu, -DBF_NB=n).
@@ -372,11 +469,9 @@ template <typename T> struct ProbeParams {
 
 template <typename T> struct KTable {
     void (*kprobe)(const ProbeParams<T>&, cudaStream_t);
-    void (*magfit)(const SweepParams<T>&, cudaStream_t);
-    void (*refit)(const RefitParams<T>&, cudaStream_t);
-    void (*flux)(const FluxParams<T>&, cudaStream_t);
-    void (*records)(const RecordParams<T, T>&, cudaStream_t);          // compacted records (B2)
-    void (*records_full)(const RecordParams<T, double>&, cudaStream_t); // full-length float64 (B1)
+    int (*sweep)(const SweepParams<T>&, cudaStream_t);      // returns a cudaError_t (dynamic shared memory opt-in)
+    void (*fixup)(const RecParams<T>&, cudaStream_t);
+    void (*flux_more)(const RecParams<T>&, cudaStream_t);
 };
 
 }  // namespace bf

@@ -10,17 +10,13 @@
 
 namespace bf {
 const KTable<float>* BF_CAT(ktable_f32_, BF_NB)() {
-    static const KTable<float> t = {&launch_kprobe<float, BF_NB>, &launch_magfit<float, BF_NB>, &launch_refit<float, BF_NB>,
-                                    &launch_flux<float, BF_NB>,
-                                    &launch_records<float, BF_NB, float>,
-                                    &launch_records<float, BF_NB, double>};
+    static const KTable<float> t = {&launch_kprobe<float, BF_NB>, &launch_sweep<float, BF_NB>, &launch_fixup<float, BF_NB>,
+                                    &launch_flux_more<float, BF_NB>};
     return &t;
 }
 const KTable<double>* BF_CAT(ktable_f64_, BF_NB)() {
-    static const KTable<double> t = {&launch_kprobe<double, BF_NB>, &launch_magfit<double, BF_NB>, &launch_refit<double, BF_NB>,
-                                     &launch_flux<double, BF_NB>,
-                                     &launch_records<double, BF_NB, double>,
-                                     &launch_records<double, BF_NB, double>};
+    static const KTable<double> t = {&launch_kprobe<double, BF_NB>, &launch_sweep<double, BF_NB>, &launch_fixup<double, BF_NB>,
+                                     &launch_flux_more<double, BF_NB>};
     return &t;
 }
 }  // namespace bf

@@ -22,8 +22,6 @@
 namespace bf {
 
 // Star-independent per-model quantities, hoisted out of the star loop.
-constexpr int kRefitTile = kTile;  // threads per CTA of k_refit (128 measured neutral: finer survivor appends scatter the flux gathers)
-constexpr int kFluxTile = 64;    // threads per CTA of k_flux (see the kernel)
 template <typename T, int NB> struct ModelRegs {
     static constexpr int NP = (NB + 1) / 2;
     P2<T> ncb[NP];  // -(b_j - bbar), b_j = mu_j + Abar r0_j  (model magnitudes at the prior-mean reddening)
@@ -60,36 +58,47 @@ __device__ __forceinline__ void finish_model(const T (&mu)[NB + 1], const T (&R)
     }
 }
 
-// from the coefficient-major grid (fully coalesced: thread = model)
-template <typename T, int NB>
-__device__ __forceinline__ void load_model(const float* __restrict__ grid, int64_t npad, int64_t i,
-                                           const DevOpts<T>& o, ModelRegs<T, NB>& m) {
-    T mu[NB + 1], R[NB + 1], D[NB + 1];
-#pragma unroll
-    for (int j = 0; j < NB; j++) {
-        mu[j] = (T)__ldg(grid + (int64_t)(0 * NB + j) * npad + i);
-        R[j] = (T)__ldg(grid + (int64_t)(1 * NB + j) * npad + i);
-        D[j] = (T)__ldg(grid + (int64_t)(2 * NB + j) * npad + i);
-    }
-    finish_model<T, NB>(mu, R, D, o, m);
-}
+// floats per model in the CTA's shared-memory tile of raw coefficients ([c][band], like `rows`): a multiple
+// of 4 whose quarter is odd, so that the 16-byte accesses of 8 consecutive models hit 8 different bank groups
+__host__ __device__ constexpr int tile_stride(int nb) { return (row_stride(nb) / 4) % 2 == 0 ? row_stride(nb) + 4 : row_stride(nb); }
 
-// from the model-major copy of the grid (3-4 sectors per model: the per-candidate gathers)
+// ModelRegs from a model's 3 NB raw coefficients v = [mu | R | D]
 template <typename T, int NB>
-__device__ __forceinline__ void load_model_row(const float* __restrict__ rows, int64_t i, const DevOpts<T>& o,
-                                               ModelRegs<T, NB>& m) {
-    constexpr int RS = row_stride(NB);
-    float v[RS];
-    const float4* __restrict__ p4 = reinterpret_cast<const float4*>(rows + i * RS);
-#pragma unroll
-    for (int k = 0; k < RS / 4; k++) {
-        float4 t = __ldg(p4 + k);
-        v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
-    }
+__device__ __forceinline__ void model_from_coeffs(const float (&v)[row_stride(NB)], const DevOpts<T>& o, ModelRegs<T, NB>& m) {
     T mu[NB + 1], R[NB + 1], D[NB + 1];
 #pragma unroll
     for (int j = 0; j < NB; j++) { mu[j] = (T)v[j]; R[j] = (T)v[NB + j]; D[j] = (T)v[2 * NB + j]; }
     finish_model<T, NB>(mu, R, D, o, m);
+}
+
+// a model's coefficients from the coefficient-major grid (fully coalesced: thread = model)
+template <int NB>
+__device__ __forceinline__ void load_coeffs(const float* __restrict__ grid, int64_t npad, int64_t i, float (&v)[row_stride(NB)]) {
+#pragma unroll
+    for (int k = 0; k < row_stride(NB); k++) v[k] = k < 3 * NB ? __ldg(grid + (int64_t)k * npad + i) : 0.f;
+}
+
+template <typename T, int NB>
+__device__ __forceinline__ void load_model(const float* __restrict__ grid, int64_t npad, int64_t i,
+                                           const DevOpts<T>& o, ModelRegs<T, NB>& m) {
+    float v[row_stride(NB)];
+    load_coeffs<NB>(grid, npad, i, v);
+    model_from_coeffs<T, NB>(v, o, m);
+}
+
+// from a contiguous, 16-byte aligned row of row_stride(NB) floats: the model-major copy of the grid in HBM
+// (3-4 sectors per model: the per-record gathers) or the CTA's tile in shared memory
+template <typename T, int NB>
+__device__ __forceinline__ void load_model_row(const float* __restrict__ row, const DevOpts<T>& o, ModelRegs<T, NB>& m) {
+    constexpr int RS = row_stride(NB);
+    float v[RS];
+    const float4* __restrict__ p4 = reinterpret_cast<const float4*>(row);
+#pragma unroll
+    for (int k = 0; k < RS / 4; k++) {
+        float4 t = p4[k];
+        v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+    }
+    model_from_coeffs<T, NB>(v, o, m);
 }
 
 // Result of the flux-space MLE at fixed (A, rho): brutus/fitting.py:430-576 (_get_sed_mle), normalised.
@@ -323,72 +332,263 @@ __global__ void __launch_bounds__(kTile) k_kprobe(const ProbeParams<T> p) {
         atomicMax(&p.out[(int64_t)first * 2 * kProbeIter + t], s_red[t / (2 * kProbeIter)][t % (2 * kProbeIter)]);
 }
 
-// =================================================================================================
-// Kernel 1: full-grid magnitude-space fit (brutus/fitting.py:728-741 -> _optimize_fit_mag :34-271,
-// then _get_sed_mle :267, the cull statistic :745-756 and a provisional lnprob) for a list of stars.
-// grid = (model tiles, star chunks); each thread keeps its model in registers and loops over the
-// chunk's stars, whose rows sit in shared memory (broadcast reads).
-//
-// Nothing per (model, star) is stored except ONE BIT: whether the pair can still matter, i.e. whether
-// it may survive the cull (lnl_p > max + ln init_thresh) or pass lnpost's first selection
-// (lnprob > max + ln wt_thresh).  Both tests are relative to per-star maxima that are only known after
-// the sweep, so they are evaluated against a running maximum (warp-local maximum combined with the
-// per-star global maximum published by the CTAs that already finished): a running maximum never
-// exceeds the final one, hence the flagged set is a superset; the exact tests are re-applied when
-// the flagged pairs are re-fitted (k_refit).
-//
-// The number of mag iterations applied to every model of a star is a grid-wide decision in the
-// reference (:246-263).  It is speculated here (SI_KSPEC) and verified afterwards from two plain
-// max-reductions per iteration:  "err < tol"  <=>  max{logwt_i : max(|dAv_i|,|dRv_i|) >= tol} <=
-// max logwt + ln(init_thresh).
-// Per-star reductions: lane s of every warp keeps the warp's maxima for star s of the chunk
-// (kStarChunk == 32), so the star loop contains no shared-memory atomics.
-// =================================================================================================
+// residuals at an arbitrary (A, rho): e'_j = cm_j - cb_j - (A r_j - Abar r0_j), r_j = r0_j + (rho - Rbar) D_j
 template <typename T, int NB>
-// up to 8 bands: capped at 80 registers (3 CTAs = 24 warps per SM); left to itself ptxas takes 94 and the
-// kernel loses a third of its warps (measured 15.8 -> 16.4 ms per 1 000 stars)
-__global__ void __launch_bounds__(kTile, (NB <= 8 ? 3 : 2)) k_magfit(const SweepParams<T> p) {
-    using U = typename Enc<T>::U;
+__device__ __forceinline__ void resid_at(const ModelRegs<T, NB>& m, const DevOpts<T>& o,
+                                         const T* __restrict__ srow, T A, T rho, P2<T> (&e)[(NB + 1) / 2],
+                                         P2<T> (&r)[(NB + 1) / 2]) {
     constexpr int NP = (NB + 1) / 2;
+    const P2<T> drho = bc2(rho - o.Rbar), A2 = bc2(A), nAbar = bc2(-o.Abar);
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        r[p] = fma2(drho, m.D[p], m.r0[p]);
+        const P2<T> red = fma2(A2, r[p], mul2(nAbar, m.r0[p]));
+        e[p] = sub2(add2(ld2(srow + SR_CM + 2 * p), m.ncb[p]), red);
+    }
+}
+
+// One iteration of the flux-space refinement of a survivor (brutus/fitting.py:784-803 with
+// _optimize_fit_flux :385-420 and _get_sed_mle :423): a (dAv, dRv) step from the current model / residuals
+// (r, r4), then the MLE at the new (A, rho).  Returns lnl_new = -chi2/2 (:792-795).  Shared by the sweep's
+// dense phase and k_flux_more, so an iteration gives the same bits wherever it runs.
+template <typename T, int NB>
+__device__ __forceinline__ T flux_step(const ModelRegs<T, NB>& m, const DevOpts<T>& o, const T* __restrict__ srow,
+                                       T c, T eta, T& A, T& rho, P2<T> (&e)[(NB + 1) / 2], P2<T> (&r)[(NB + 1) / 2],
+                                       Mle<T, NB>& r4) {
+    constexpr int NP = (NB + 1) / 2;
+    P2<T> an = bc2(T(0)), ad = bc2(T(0)), rn = bc2(T(0)), rd = bc2(T(0));
+    const P2<T> sh = bc2(r4.shat);
+#pragma unroll
+    for (int pp = 0; pp < NP; pp++) {
+        const P2<T> Ms = mul2(sh, r4.gb[pp]);                        // M_j / sigma_j
+        const P2<T> tj = sub2(ld2(srow + SR_AL + 2 * pp), Ms);       // resid_j / sigma_j
+        const P2<T> rM = mul2(r[pp], Ms), DM = mul2(m.D[pp], Ms);
+        an = fma2(rM, tj, an);
+        ad = fma2(rM, rM, ad);
+        rn = fma2(DM, tj, rn);
+        rd = fma2(DM, DM, rd);
+    }
+    T dA = Num<T>::div(fma(T(kFac), hsum2(an), (o.Abar - A) * o.PA), fma(T(kFac * kFac), hsum2(ad), o.PA)) * eta;
+    T dR = Num<T>::div(fma(T(kFac), hsum2(rn), (o.Rbar - rho) * o.PR), fma(T(kFac * kFac), hsum2(rd), o.PR)) * eta;
+    dA = tmax(dA, o.avmin - A);
+    dA = tmin(dA, o.avmax - A);
+    A += dA;
+    dR = tmax(dR, o.rvmin - rho);
+    dR = tmin(dR, o.rvmax - rho);
+    rho += dR;
+    resid_at<T, NB>(m, o, srow, A, rho, e, r);
+    mle_from_resid<T, NB>(e, c, srow, r4);          // :423
+    return T(-0.5) * r4.chi2;
+}
+
+// Off-diagonal and reddening entries of icov_sar at the current fit (brutus/fitting.py:526-574), from the
+// reddening vector r and the MLE r4 at (A, rho): ic = (sa, sr, aa, ar, rr); ss = r4.den E^2 is the caller's.
+template <typename T, int NB>
+__device__ __forceinline__ void icov_terms(const ModelRegs<T, NB>& m, const DevOpts<T>& o, const T* __restrict__ srow,
+                                           T A, const P2<T> (&r)[(NB + 1) / 2], const Mle<T, NB>& r4, T (&ic)[5]) {
+    constexpr int NP = (NB + 1) / 2;
+    // cross terms in sigma-normalised units; see the header comment and DESIGN.md
+    P2<T> sa = bc2(T(0)), sr = bc2(T(0)), ar = bc2(T(0)), aden = bc2(T(0)), rden = bc2(T(0));
+    const P2<T> sh = bc2(r4.shat), kA = bc2(T(kC2) * A), one = bc2(T(1));
+#pragma unroll
+    for (int pp = 0; pp < NP; pp++) {
+        const P2<T> Ms = mul2(sh, r4.gb[pp]);
+        const P2<T> tj = sub2(ld2(srow + SR_AL + 2 * pp), Ms);
+        const P2<T> x = mul2(kA, r[pp]);
+        const P2<T> h = mk2(Num<T>::exp2(lo2(x)), Num<T>::exp2(hi2(x)));   // F0_j / F_j = 10^(0.4 A r_j)   (:529-530)
+        const P2<T> mmr = sub2(Ms, tj);                                     // (models - resid)/sigma         (:539-542)
+        sa = fma2(mul2(r[pp], r4.gb[pp]), mmr, sa);
+        sr = fma2(mul2(m.D[pp], r4.gb[pp]), mmr, sr);
+        const P2<T> DM = mul2(m.D[pp], Ms), rM = mul2(r[pp], Ms);
+        ar = fma2(DM, sub2(mul2(Ms, sub2(one, h)), tj), ar);                // drvecs (reddening - resid)/var (:550-551)
+        aden = fma2(rM, rM, aden);
+        rden = fma2(DM, DM, rden);
+    }
+    const T f = T(kFac), E = r4.E;
+    ic[0] = f * E * hsum2(sa);
+    ic[1] = f * E * hsum2(sr);
+    ic[2] = f * f * hsum2(aden) + o.PA + T(1. / (0.05 * 0.05));
+    ic[3] = f * hsum2(ar);
+    ic[4] = f * f * hsum2(rden) + o.PR + T(1. / (0.1 * 0.1));
+}
+
+template <typename T>
+__device__ __forceinline__ void store_fit(const PoolArrays<T>& pl, int64_t q, T A, T rho, T chi2, T s, T sden, const T (&ic)[5]) {
+    pl.av[q] = A; pl.rv[q] = rho; pl.chi2[q] = chi2; pl.scale[q] = s; pl.sden[q] = sden;
+    pl.isa[q] = ic[0]; pl.isr[q] = ic[1]; pl.iaa[q] = ic[2]; pl.iar[q] = ic[3]; pl.irr[q] = ic[4];
+}
+
+// =================================================================================================
+// Kernel 1: the fused sweep.  grid = (model tiles, star chunks); each thread keeps its model in registers
+// and loops over the chunk's stars, whose rows sit in shared memory (broadcast reads).
+//
+// MAIN LOOP, every (model, star): the magnitude-space fit (brutus/fitting.py:728-741 -> _optimize_fit_mag
+// :34-271), _get_sed_mle at the fitted (Av, Rv) (:267), the cull statistic (:745-756) and a provisional
+// lnprob.  Per star it produces six max-reductions (lane s of every warp keeps the warp's maxima for star s
+// of the chunk, kStarChunk == 32, so the star loop contains no shared-memory atomics) and ONE BIT per pair:
+// whether the pair can still matter, i.e. whether it may survive the cull (lnl_p > max + ln init_thresh) or
+// pass lnpost's first selection (lnprob > max + ln wt_thresh).  Both tests are relative to per-star maxima
+// that are only known after the sweep, so they are evaluated against a running maximum (warp-local maximum
+// combined with the per-star global maximum published by the CTAs that already finished): a running maximum
+// never exceeds the final one, hence the flagged set is a superset; the exact tests are applied to the
+// flagged pairs' records afterwards (k_cull, k_sel).
+//
+// The number of mag iterations applied to every model of a star is a grid-wide decision in the reference
+// (:246-263).  It is speculated (SI_KSPEC) and verified afterwards from two plain max-reductions per
+// iteration:  "err < tol"  <=>  max{logwt_i : max(|dAv_i|,|dRv_i|) >= tol} <= max logwt + ln(init_thresh).
+//
+// DENSE PHASE, flagged pairs only (~15 % on the locus mock, clustered): a flagged lane pushes (star, lane,
+// Av, Rv) into its WARP's ring buffer in shared memory; whenever 32 entries are queued the warp processes
+// them with all 32 lanes busy: the entry's model comes from the CTA's shared-memory tile of coefficients,
+// its star row from shared memory (no global gathers, no divergence).  For each entry: the flux MLE at the
+// magnitude fit; for likely survivors of the cull the first `nit_first` iterations of the flux-space
+// refinement (:778-803) -- the reference always runs at least two, and two is what most stars need; the
+// precision matrix icov_sar (:526-574); and the complete record is appended to the candidate pool.  What
+// used to be four passes of latency-bound gathers over the candidates (re-fit, flux loop, scatter, records)
+// is arithmetic on data already on the SM.
+// =================================================================================================
+constexpr int kQueue = 64;   // ring-buffer entries per warp (a flush is triggered at 32; at most 31 + 32 queued)
+
+template <typename T, int NB> struct SweepSmem {
+    static constexpr int RS = tile_stride(NB);
+    static constexpr size_t off_star = 0;
+    static constexpr size_t off_tile = off_star + sizeof(T) * kStarChunk * kStarSmem;
+    static constexpr size_t off_qav = off_tile + sizeof(float) * kTile * RS;
+    static constexpr size_t off_qrv = off_qav + sizeof(T) * (kTile / 32) * kQueue;
+    static constexpr size_t off_qlp = off_qrv + sizeof(T) * (kTile / 32) * kQueue;
+    static constexpr size_t off_qkey = off_qlp + sizeof(T) * (kTile / 32) * kQueue;
+    static constexpr size_t off_red = off_qkey + sizeof(uint32_t) * (kTile / 32) * kQueue;   // [warp][star][kSweepRed] of T
+    static constexpr size_t off_snap = off_red + sizeof(T) * (kTile / 32) * kStarChunk * kSweepRed;
+    static constexpr size_t off_int = off_snap + sizeof(T) * kStarChunk * 2;
+    static constexpr size_t bytes = off_int + sizeof(int) * kStarChunk * 3;
+};
+
+// The dense phase for entries [head, head + n) of the warp's ring buffer (n <= 32; lanes >= n idle).
+template <typename T, int NB>
+__device__ __forceinline__ void dense_flush(const SweepParams<T>& p, const DevOpts<T>& o, const T* __restrict__ s_star,
+                                            const float* __restrict__ tile_w, const int* __restrict__ s_tag,
+                                            const T* __restrict__ q_av, const T* __restrict__ q_rv,
+                                            const T* __restrict__ q_lp, const uint32_t* __restrict__ q_key, int head,
+                                            int n, int64_t model0, int lane) {
+    constexpr int NP = (NB + 1) / 2;
+    constexpr int RS = tile_stride(NB);
+    const bool act = lane < n;
+    const int qi = (head + (act ? lane : 0)) & (kQueue - 1);   // idle lanes shadow entry 0 (results discarded)
+    const uint32_t key = q_key[qi];
+    T A = q_av[qi], rho = q_rv[qi];
+    // the cull statistic exactly as the main loop computed it: the exact cull test (k_cull) compares it with the
+    // per-star maximum of the same quantity, so survival never hinges on the rounding of a second evaluation
+    const T lp = q_lp[qi];
+    __syncwarp();   // the ring entries may be overwritten once every lane has read its own
+    const int s = key & 31, ml = (key >> 5) & 31;
+    const bool fluxed = ((key >> 10) & 1u) != 0u && p.nit_first > 0;
+    const T* __restrict__ srow = s_star + s * kStarSmem;
+    ModelRegs<T, NB> m;
+    load_model_row<T, NB>(tile_w + ml * RS, o, m);
+    const T c = srow[SR_SC + SC_MBAR] - m.bbar;
+    P2<T> e[NP], r[NP];
+    Mle<T, NB> r4;
+    resid_at<T, NB>(m, o, srow, A, rho, e, r);
+    mle_from_resid<T, NB>(e, c, srow, r4);
+    const T Am = A, rhom = rho;
+    T eta = T(1), lold = Num<T>::kNegBig, lprev = Num<T>::kNegBig;   // stepsize 1, lnl_old = -1e300 (:778-779)
+    if (fluxed) {
+        for (int it = 0; it < p.nit_first; it++) {
+            const T lnew = flux_step<T, NB>(m, o, srow, c, eta, A, rho, e, r, r4);
+            lprev = lold;
+            if (lnew < lold) eta = eta / T(1.2);            // :802
+            lold = lnew;                                    // :803
+        }
+    }
+    T ic[5];
+    icov_terms<T, NB>(m, o, srow, A, r, r4, ic);
+    // append: one atomic per flush, coalesced stores
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(p.pool_count, (unsigned long long)n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const int64_t q = (int64_t)base + lane;
+    if (act && q < p.pool_cap) {
+        const PoolArrays<T>& pl = p.pool;
+        pl.model[q] = (int)(model0 + ml);
+        pl.sflag[q] = s_tag[s] | (fluxed ? kFlagFluxed << 24 : 0);
+        store_fit<T>(pl, q, A, rho, r4.chi2, r4.s, r4.den * r4.E * r4.E, ic);
+        pl.lp[q] = lp;
+        pl.eta[q] = eta; pl.lold[q] = lold; pl.lprev[q] = lprev;
+        pl.lnl[q] = Am; pl.lnprob[q] = rhom;   // the magnitude fit, kept for k_fixup until k_final overwrites it
+    }
+}
+
+// up to 8 bands: capped at 80 registers (3 CTAs = 24 warps per SM); left to itself ptxas takes more and the
+// kernel loses a third of its warps (measured 15.8 -> 16.4 ms per 1 000 stars in round 1).  The float64
+// instantiation (verification) takes what it needs.
+template <typename T, int NB> constexpr int sweep_min_ctas() { return sizeof(T) == 8 ? 1 : (NB <= 8 ? 3 : 2); }
+
+template <typename T, int NB>
+__global__ void __launch_bounds__(kTile, (sweep_min_ctas<T, NB>())) k_sweep(const SweepParams<T> p) {
+    using U = typename Enc<T>::U;
+    using SM = SweepSmem<T, NB>;
+    constexpr int NP = (NB + 1) / 2;
+    constexpr int RS = SM::RS;
     static_assert(kStarChunk == 32, "lane <-> star mapping of the reductions");
-    __shared__ __align__(16) T s_star[kStarChunk][kStarStride];
-    __shared__ int s_slot[kStarChunk];
-    __shared__ int s_kspec[kStarChunk];
-    __shared__ T s_snap[kStarChunk][2];
-    __shared__ U s_red[kStarChunk][kSweepRed];
+    extern __shared__ __align__(16) unsigned char smem[];
+    T* s_star = reinterpret_cast<T*>(smem + SM::off_star);                 // [32][kStarSmem]
+    float* s_tile = reinterpret_cast<float*>(smem + SM::off_tile);         // [256][RS]
+    T* s_qav = reinterpret_cast<T*>(smem + SM::off_qav);                   // [8][kQueue]
+    T* s_qrv = reinterpret_cast<T*>(smem + SM::off_qrv);
+    T* s_qlp = reinterpret_cast<T*>(smem + SM::off_qlp);
+    uint32_t* s_qkey = reinterpret_cast<uint32_t*>(smem + SM::off_qkey);
+    T* s_red = reinterpret_cast<T*>(smem + SM::off_red);                   // [8][32][kSweepRed]: per-warp maxima
+    T* s_snap = reinterpret_cast<T*>(smem + SM::off_snap);                 // [32][2]
+    int* s_slot = reinterpret_cast<int*>(smem + SM::off_int);              // [32]
+    int* s_kspec = s_slot + kStarChunk;
+    int* s_tag = s_kspec + kStarChunk;
 
     const int first = blockIdx.y * kStarChunk;
     const int nst = min(kStarChunk, p.nlist - first);
     for (int t = threadIdx.x; t < nst * kStarStride; t += kTile) {
         int s = t / kStarStride, k = t - s * kStarStride;
-        s_star[s][k] = p.stars[(int64_t)p.list[first + s] * kStarStride + k];
+        s_star[s * kStarSmem + k] = p.stars[(int64_t)p.list[first + s] * kStarStride + k];
     }
     for (int t = threadIdx.x; t < nst; t += kTile) {
         int slot = p.list[first + t];
         s_slot[t] = slot;
         s_kspec[t] = p.star_int[slot * SI_COUNT + SI_KSPEC];
+        s_tag[t] = make_tag(slot, p.star_int[slot * SI_COUNT + SI_EPOCH], 0);
         // running per-star maxima published so far (benign race: any value <= the final maximum is valid)
         const volatile U* rr = p.red + (int64_t)slot * kNumRed;
-        s_snap[t][0] = Enc<T>::dec(rr[RED_LP]);
-        s_snap[t][1] = Enc<T>::dec(rr[RED_M0]);
+        s_snap[2 * t] = Enc<T>::dec(rr[RED_LP]);
+        s_snap[2 * t + 1] = Enc<T>::dec(rr[RED_M0]);
     }
-    for (int t = threadIdx.x; t < kStarChunk * kSweepRed; t += kTile)
-        s_red[t / kSweepRed][t % kSweepRed] = Enc<T>::enc(Num<T>::neg_inf());
-    __syncthreads();
 
     const int64_t i = (int64_t)blockIdx.x * kTile + threadIdx.x;  // npad is a multiple of kTile
     const bool valid = i < p.nmodel;
     const DevOpts<T> o = p.o;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    float* tile_w = s_tile + wrp * 32 * RS;                         // this warp's 32 models
+    {   // coefficients: coalesced from the coefficient-major grid into the tile (conflict-free 16-byte stores)
+        float v[row_stride(NB)];
+        load_coeffs<NB>(p.grid, p.npad, i, v);
+        float4* dst = reinterpret_cast<float4*>(tile_w + lane * RS);
+#pragma unroll
+        for (int k = 0; k < row_stride(NB) / 4; k++) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    }
+    __syncthreads();
     ModelRegs<T, NB> m;
-    load_model<T, NB>(p.grid, p.npad, i, o, m);
-    const int lane = threadIdx.x & 31;
+    load_model_row<T, NB>(tile_w + lane * RS, o, m);
     const int64_t word = i >> 5;
+    const int64_t model0 = i - lane;
     const T ninf = Num<T>::neg_inf();
     const T ln_init_c = o.ln_init - T(kCandMargin);
-    T acc0 = ninf, acc1 = ninf, acc2 = ninf, acc3 = ninf, acc4 = ninf, acc5 = ninf;  // lane s <-> star s
+    T* w_red = s_red + wrp * kStarChunk * kSweepRed;               // lane s stores the warp's maxima for star s
+    T* q_av = s_qav + wrp * kQueue;
+    T* q_rv = s_qrv + wrp * kQueue;
+    T* q_lp = s_qlp + wrp * kQueue;
+    uint32_t* q_key = s_qkey + wrp * kQueue;
+    int qh = 0, qn = 0;                                             // ring buffer head / fill (warp-uniform)
+    const unsigned lt_mask = (1u << lane) - 1u;
 
     for (int s = 0; s < nst; s++) {
-        const T* __restrict__ srow = s_star[s];
+        const T* __restrict__ srow = s_star + s * kStarSmem;
         const T c = srow[SR_SC + SC_MBAR] - m.bbar;
         T A, rho, l0, b0, l1, b1;
         P2<T> e[NP];
@@ -408,269 +608,161 @@ __global__ void __launch_bounds__(kTile, (NB <= 8 ? 3 : 2)) k_magfit(const Sweep
         l1 = warp_max_fast(l1); b1 = warp_max_fast(b1);
         const T lpm = warp_max_fast(lp);
         const T lqm = warp_max_fast(lq);
-        if (lane == s) { acc0 = l0; acc1 = b0; acc2 = l1; acc3 = b1; acc4 = lpm; acc5 = lqm; }
-        // --- candidate bit ---
-        const T thr1 = Num<T>::max(s_snap[s][0], lpm) + ln_init_c;
-        const T thr2 = Num<T>::max(s_snap[s][1], lqm) + o.ln_wt - srow[SR_SC + SC_SLACK];
-        const bool cand = valid && (lp > thr1 || lq > thr2);
+        if (lane == s) {
+            T* w = w_red + s * kSweepRed;
+            w[0] = l0; w[1] = b0; w[2] = l1; w[3] = b1; w[4] = lpm; w[5] = lqm;
+        }
+        // --- candidate bit, queue ---
+        const T thr1 = Num<T>::max(s_snap[2 * s], lpm) + ln_init_c;
+        const T thr2 = Num<T>::max(s_snap[2 * s + 1], lqm) + o.ln_wt - srow[SR_SC + SC_SLACK];
+        const bool likely = lp > thr1;                              // may survive the cull
+        const bool cand = valid && (likely || lq > thr2);
         const unsigned bal = __ballot_sync(0xffffffffu, cand);
         if (lane == 0) p.cand[(int64_t)slot * p.nwords + word] = bal;
-    }
-    // NaN maxima (every lane NaN) must not poison the unsigned-encoded atomics
-    if (lane < nst) {
-        if (acc0 == acc0) atomicMax(&s_red[lane][0], Enc<T>::enc(acc0));
-        if (acc1 == acc1) atomicMax(&s_red[lane][1], Enc<T>::enc(acc1));
-        if (acc2 == acc2) atomicMax(&s_red[lane][2], Enc<T>::enc(acc2));
-        if (acc3 == acc3) atomicMax(&s_red[lane][3], Enc<T>::enc(acc3));
-        if (acc4 == acc4) atomicMax(&s_red[lane][4], Enc<T>::enc(acc4));
-        if (acc5 == acc5) atomicMax(&s_red[lane][5], Enc<T>::enc(acc5));
-    }
-    __syncthreads();
-    for (int t = threadIdx.x; t < nst * kSweepRed; t += kTile) {
-        int s = t / kSweepRed, k = t % kSweepRed;
-        const int map[kSweepRed] = {RED_L0, RED_B0, RED_L1, RED_B1, RED_LP, RED_M0};
-        atomicMax(&p.red[(int64_t)s_slot[s] * kNumRed + map[k]], s_red[s][k]);
-    }
-}
-
-// =================================================================================================
-// Kernel 2: exact re-fit of the candidates.  One thread per candidate record (star, model): repeats the
-// sweep's arithmetic for the pair, applies the exact cull test (:758-759) against the now final
-// per-star maximum, initialises the record and appends the survivors to the compact flux working set
-// (stepsize 1, lnl_old = -1e300, :778-779).
-// =================================================================================================
-template <typename T, int NB>
-// up to 8 bands: 64 registers -> 4 CTAs per SM: the kernel waits on gathers (ncu: long_scoreboard 6.7 per issue),
-// occupancy helps; more bands need more registers (3 CTAs up to 12 bands, 2 beyond, to stay clear of spills)
-__global__ void __launch_bounds__(kRefitTile, (NB <= 8 ? 4 : (NB <= 12 ? 3 : 2)) * kTile / kRefitTile) k_refit(const RefitParams<T> p) {
-    constexpr int NP = (NB + 1) / 2;
-    const int64_t q = (int64_t)blockIdx.x * kRefitTile + threadIdx.x;
-    const bool inr = q < p.ncand;
-    bool surv = false;
-    int slot = -1, model = 0;
-    T Av = T(0), Rv = T(0), chi2 = T(0), scale = T(0), sden = T(0);
-    if (inr) {
-        slot = p.pool.star[q];
-        const int64_t i = p.pool.model[q];
-        const DevOpts<T> o = p.o;
-        const T* __restrict__ srow = p.stars + (int64_t)slot * kStarStride;
-        ModelRegs<T, NB> m;
-        load_model_row<T, NB>(p.rows, i, o, m);
-        const T c = srow[SR_SC + SC_MBAR] - m.bbar;
-        T A, rho, l0, b0, l1, b1;
-        P2<T> e[NP];
-        magfit_one<T, NB>(m, o, srow, p.star_int[slot * SI_COUNT + SI_KSPEC], c, e, A, rho, l0, b0, l1, b1);
-        Mle<T, NB> r4;
-        mle_from_resid<T, NB>(e, c, srow, r4);
-        const T lp = cull_lnl(r4.chi2, r4.s, srow);
-        surv = lp > Enc<T>::dec(p.red[(int64_t)slot * kNumRed + RED_LP]) + o.ln_init;
-        p.pool.av[q] = A;
-        p.pool.rv[q] = rho;
-        p.pool.chi2[q] = chi2 = r4.chi2;
-        p.pool.scale[q] = scale = r4.s;
-        p.pool.sden[q] = sden = r4.den * r4.E * r4.E;
-        p.pool.flag[q] = surv ? kFlagSurv : 0;
-        Av = A; Rv = rho; model = (int)i;
-    }
-    // append the survivors to the compact flux working set: one global atomic per CTA
-    __shared__ int s_w[kRefitTile / 32];
-    __shared__ int s_base;
-    const unsigned bal = __ballot_sync(0xffffffffu, surv);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) s_w[w] = __popc(bal);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int n = 0;
-        for (int k = 0; k < kRefitTile / 32; k++) n += s_w[k];
-        s_base = n ? atomicAdd(p.nsv, n) : 0;
-    }
-    __syncthreads();
-    if (surv) {
-        int pos = s_base + __popc(bal & ((1u << lane) - 1u));
-        for (int k = 0; k < w; k++) pos += s_w[k];
-        p.sv.q[pos] = (int)q;
-        p.sv.model[pos] = model;
-        p.sv.star[pos] = slot;
-        p.sv.av[pos] = Av;
-        p.sv.rv[pos] = Rv;
-        p.sv.eta[pos] = T(1);                 // stepsize 1, lnl_old = -1e300 (:778-779)
-        p.sv.lold[pos] = Num<T>::kNegBig;
-        p.sv.chi2[pos] = chi2;
-        p.sv.scale[pos] = scale;
-        p.sv.sden[pos] = sden;
-    }
-    cta_star_count(p.nsurv, slot, surv);
-}
-
-// residuals at an arbitrary (A, rho): e'_j = cm_j - cb_j - (A r_j - Abar r0_j), r_j = r0_j + (rho - Rbar) D_j
-template <typename T, int NB>
-__device__ __forceinline__ void resid_at(const ModelRegs<T, NB>& m, const DevOpts<T>& o,
-                                         const T* __restrict__ srow, T A, T rho, P2<T> (&e)[(NB + 1) / 2],
-                                         P2<T> (&r)[(NB + 1) / 2]) {
-    constexpr int NP = (NB + 1) / 2;
-    const P2<T> drho = bc2(rho - o.Rbar), A2 = bc2(A), nAbar = bc2(-o.Abar);
-#pragma unroll
-    for (int p = 0; p < NP; p++) {
-        r[p] = fma2(drho, m.D[p], m.r0[p]);
-        const P2<T> red = fma2(A2, r[p], mul2(nAbar, m.r0[p]));
-        e[p] = sub2(add2(ld2(srow + SR_CM + 2 * p), m.ncb[p]), red);
-    }
-}
-
-// =================================================================================================
-// Kernel 3: flux-space refinement of the survivors (brutus/fitting.py:778-803 with
-// _optimize_fit_flux :274-427).  One thread per survivor; `nit` iterations are executed in
-// registers, and the convergence reductions are recorded for the last one:
-//   "lerr <= ltol"  <=>  max{lnl_new_i : |lnl_new_i - lnl_old_i| > ltol} <= max lnl_new + ln(ltol_subthresh)
-// Stars whose loop has converged (SI_ACTIVE == 0, decided on the device by k_flux_ctl) are skipped.
-// =================================================================================================
-template <typename T, int NB>
-// 80 registers -> 24 warps per SM (16 at the natural 90 registers; 64 registers spill and measured slower).
-// CTAs of kFluxTile = 64 threads: every thread waits on a two-level gather and then runs ~650 dependent
-// instructions, and the per-star reductions at the end need CTA-wide barriers, so with 256-thread CTAs the
-// warps that finish early idle at the barrier while their registers stay allocated (ncu: issue 26 %, DRAM
-// 22 %).  Measured per 1 000 stars: 256 threads 8.6 ms, 128: 7.7, 64: 7.4, 32: 8.5 (global atomics per CTA).
-__global__ void __launch_bounds__(kFluxTile, (NB <= 8 ? 3 : 2) * kTile / kFluxTile) k_flux(const FluxParams<T> p) {
-    constexpr int NP = (NB + 1) / 2;
-    const int64_t t = (int64_t)blockIdx.x * kFluxTile + threadIdx.x;
-    const bool inrange = t < p.nsv;
-    int slot = inrange ? p.sv.star[t] : -1;
-    const bool act = inrange && p.star_int[slot * SI_COUNT + SI_ACTIVE] != 0;
-    const DevOpts<T> o = p.o;
-    T v1 = Num<T>::neg_inf(), v2 = Num<T>::neg_inf();
-    if (act) {
-        const int64_t i = p.sv.model[t];
-        const T* __restrict__ srow = p.stars + (int64_t)slot * kStarStride;
-        ModelRegs<T, NB> m;
-        load_model_row<T, NB>(p.rows, i, o, m);
-        const T c = srow[SR_SC + SC_MBAR] - m.bbar;
-        T A = p.sv.av[t], rho = p.sv.rv[t], eta = p.sv.eta[t], lold = p.sv.lold[t];
-        P2<T> e[NP], r[NP];
-        Mle<T, NB> r4;
-        resid_at<T, NB>(m, o, srow, A, rho, e, r);
-        mle_from_resid<T, NB>(e, c, srow, r4);
-        T lnew = lold;
-        for (int it = 0; it < p.nit; it++) {
-            // one (dAv, dRv) step from the current model / residuals (:385-420)
-            P2<T> an = bc2(T(0)), ad = bc2(T(0)), rn = bc2(T(0)), rd = bc2(T(0));
-            const P2<T> sh = bc2(r4.shat);
-#pragma unroll
-            for (int pp = 0; pp < NP; pp++) {
-                const P2<T> Ms = mul2(sh, r4.gb[pp]);                        // M_j / sigma_j
-                const P2<T> tj = sub2(ld2(srow + SR_AL + 2 * pp), Ms);       // resid_j / sigma_j
-                const P2<T> rM = mul2(r[pp], Ms), DM = mul2(m.D[pp], Ms);
-                an = fma2(rM, tj, an);
-                ad = fma2(rM, rM, ad);
-                rn = fma2(DM, tj, rn);
-                rd = fma2(DM, DM, rd);
+        if (bal) {
+            if (cand) {
+                const int pos = (qh + qn + __popc(bal & lt_mask)) & (kQueue - 1);
+                q_av[pos] = A; q_rv[pos] = rho; q_lp[pos] = lp;
+                q_key[pos] = (uint32_t)s | (uint32_t)lane << 5 | (likely ? 1u << 10 : 0u);
             }
-            T dA = Num<T>::div(fma(T(kFac), hsum2(an), (o.Abar - A) * o.PA), fma(T(kFac * kFac), hsum2(ad), o.PA)) * eta;
-            T dR = Num<T>::div(fma(T(kFac), hsum2(rn), (o.Rbar - rho) * o.PR), fma(T(kFac * kFac), hsum2(rd), o.PR)) * eta;
-            dA = tmax(dA, o.avmin - A);
-            dA = tmin(dA, o.avmax - A);
-            A += dA;
-            dR = tmax(dR, o.rvmin - rho);
-            dR = tmin(dR, o.rvmax - rho);
-            rho += dR;
-            resid_at<T, NB>(m, o, srow, A, rho, e, r);
-            mle_from_resid<T, NB>(e, c, srow, r4);          // :423
-            lnew = T(-0.5) * r4.chi2;                       // :792-795
-            if (it == p.nit - 1) {
-                v1 = (lnew == lnew) ? lnew : Num<T>::neg_inf();
-                v2 = (tabs(lnew - lold) > o.ltol) ? v1 : Num<T>::neg_inf();
+            qn += __popc(bal);
+            if (qn >= 32) {
+                __syncwarp();
+                dense_flush<T, NB>(p, o, s_star, tile_w, s_tag, q_av, q_rv, q_lp, q_key, qh, 32, model0, lane);
+                qh = (qh + 32) & (kQueue - 1);
+                qn -= 32;
+                load_model_row<T, NB>(tile_w + lane * RS, o, m);   // this thread's own model again
             }
-            if (lnew < lold) eta = eta / T(1.2);            // :802
-            lold = lnew;                                    // :803
         }
-        p.sv.av[t] = A;
-        p.sv.rv[t] = rho;
-        p.sv.eta[t] = eta;
-        p.sv.lold[t] = lold;
-        p.sv.chi2[t] = r4.chi2;
-        p.sv.scale[t] = r4.s;
-        p.sv.sden[t] = r4.den * r4.E * r4.E;
     }
-    // per-star reductions, one pair of global atomics per CTA and star
-    if (__syncthreads_or(act)) {
-        cta_star_max<T>(p.red, RED_FL, slot, act, v1);
-        cta_star_max<T>(p.red, RED_FB, slot, act, v2);
+    if (qn > 0) {
+        __syncwarp();
+        dense_flush<T, NB>(p, o, s_star, tile_w, s_tag, q_av, q_rv, q_lp, q_key, qh, qn, model0, lane);
+    }
+    __syncthreads();
+    // combine the warps' maxima and publish them; NaN maxima (every lane NaN) must not poison the
+    // unsigned-encoded atomics
+    for (int t = threadIdx.x; t < nst * kSweepRed; t += kTile) {
+        T v = ninf;
+        bool any = false;
+#pragma unroll
+        for (int w = 0; w < kTile / 32; w++) {
+            const T x = s_red[w * kStarChunk * kSweepRed + t];
+            if (x == x) { v = any ? Num<T>::max(v, x) : x; any = true; }
+        }
+        const int s = t / kSweepRed, k = t % kSweepRed;
+        const int map[kSweepRed] = {RED_L0, RED_B0, RED_L1, RED_B1, RED_LP, RED_M0};
+        if (any) atomicMax(&p.red[(int64_t)s_slot[s] * kNumRed + map[k]], Enc<T>::enc(v));
     }
 }
 
 // =================================================================================================
-// Kernel 4: output records.  Recomputes _get_sed_mle (brutus/fitting.py:502-576) at the final
-// (Av, Rv) of each requested candidate to produce the full precision matrix icov_sar.
-// Mode A: compacted records of the selected candidates (6 unique icov entries, element type T);
-// mode B: every model of one star (pool entry q == model q; 9 entries, float64: what loglike returns).
+// Kernel 2 (rare): records the sweep refined as likely survivors that the exact cull test (k_cull, against
+// the final per-star maximum) rejected -- pairs flagged while the running maximum was still low.  A
+// non-survivor keeps its magnitude-fit values (brutus/fitting.py:805-810 scatters survivors only): redo the
+// MLE and icov at the magnitude fit kept in the record.
 // =================================================================================================
-template <typename T, int NB, typename O>
-__global__ void __launch_bounds__(kTile) k_records(const RecordParams<T, O> p) {
+template <typename T, int NB>
+__global__ void __launch_bounds__(kTile) k_fixup(const RecParams<T> p) {
     constexpr int NP = (NB + 1) / 2;
     const int64_t t = (int64_t)blockIdx.x * kTile + threadIdx.x;
-    if (t >= p.nrec) return;
-    const bool modeA = p.sel_q != nullptr;
-    const int64_t q = modeA ? p.sel_q[t] : t;
-    const int slot = p.pool.star[q];
-    const int64_t i = p.pool.model[q];
+    if (t >= p.n) return;
+    const int64_t q = p.list[t];
+    const PoolArrays<T>& pl = p.pool;
+    const int tag = pl.sflag[q];
+    const int slot = tag_slot(tag);
     const DevOpts<T> o = p.o;
     const T* __restrict__ srow = p.stars + (int64_t)slot * kStarStride;
-    const T A = p.pool.av[q], rho = p.pool.rv[q];
-    if (modeA) {
-        p.o_idx[t] = (int)i;
-        if (p.o_star) p.o_star[t] = slot;
-        p.o_lnl[t] = (O)p.pool.lnl[q];
-        p.o_scale[t] = (O)p.pool.scale[q];
-        p.o_av[t] = (O)A;
-        if (p.nrows > 3) {
-            p.o_chi2[t] = (O)p.pool.chi2[q];
-            p.o_rv[t] = (O)rho;
-        }
-        if (p.nrows <= 5) return;
-    } else {
-        p.o_lnl[t] = (O)p.pool.lnl[q];
-        p.o_chi2[t] = (O)p.pool.chi2[q];
-        p.o_scale[t] = (O)p.pool.scale[q];
-        p.o_av[t] = (O)A;
-        p.o_rv[t] = (O)rho;
-        if (!p.o_icov) return;
-    }
     ModelRegs<T, NB> m;
-    load_model_row<T, NB>(p.rows, i, o, m);
+    load_model_row<T, NB>(p.rows + (int64_t)pl.model[q] * row_stride(NB), o, m);
     const T c = srow[SR_SC + SC_MBAR] - m.bbar;
+    const T A = pl.lnl[q], rho = pl.lnprob[q];
     P2<T> e[NP], r[NP];
     Mle<T, NB> r4;
     resid_at<T, NB>(m, o, srow, A, rho, e, r);
     mle_from_resid<T, NB>(e, c, srow, r4);
-    // cross terms (:526-561) in sigma-normalised units; see the header comment and DESIGN.md
-    P2<T> sa = bc2(T(0)), sr = bc2(T(0)), ar = bc2(T(0)), aden = bc2(T(0)), rden = bc2(T(0));
-    const P2<T> sh = bc2(r4.shat), kA = bc2(T(kC2) * A), one = bc2(T(1));
+    T ic[5];
+    icov_terms<T, NB>(m, o, srow, A, r, r4, ic);
+    store_fit<T>(pl, q, A, rho, r4.chi2, r4.s, r4.den * r4.E * r4.E, ic);
+    pl.sflag[q] = tag & ~(kFlagFluxed << 24);
+}
+
+// =================================================================================================
+// Kernel 3 (rare): one more flux iteration for the survivors of the stars whose loop has not converged after
+// the iterations the sweep ran (SI_ACTIVE, decided on the device by k_flux_ctl), with the convergence
+// reductions of that iteration:
+//   "lerr <= ltol"  <=>  max{lnl_new_i : |lnl_new_i - lnl_old_i| > ltol} <= max lnl_new + ln(ltol_subthresh)
+// The first launch of a group walks every record of the pool and writes the indices of the active stars'
+// survivors to `list_out`; further iterations only visit that list (`list`, `nlist`).
+// =================================================================================================
+template <typename T, int NB>
+__global__ void __launch_bounds__(kTile) k_flux_more(const RecParams<T> p) {
+    constexpr int NP = (NB + 1) / 2;
+    __shared__ StarAgg<T, 2> agg;
+    const int which[2] = {RED_FL, RED_FB};
+    agg.init();
+    __syncthreads();
+    const PoolArrays<T>& pl = p.pool;
+    const int64_t n = p.list ? (int64_t)*p.nlist : p.n;
+    int64_t lo, hi;
+    pass_range(n, lo, hi);
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = lo; base < hi; base += kPassStep) {
+        int64_t q[kPassU];
+        int tag[kPassU];
 #pragma unroll
-    for (int pp = 0; pp < NP; pp++) {
-        const P2<T> Ms = mul2(sh, r4.gb[pp]);
-        const P2<T> tj = sub2(ld2(srow + SR_AL + 2 * pp), Ms);
-        const P2<T> x = mul2(kA, r[pp]);
-        const P2<T> h = mk2(Num<T>::exp2(lo2(x)), Num<T>::exp2(hi2(x)));   // F0_j / F_j = 10^(0.4 A r_j)   (:529-530)
-        const P2<T> mmr = sub2(Ms, tj);                                     // (models - resid)/sigma         (:539-542)
-        sa = fma2(mul2(r[pp], r4.gb[pp]), mmr, sa);
-        sr = fma2(mul2(m.D[pp], r4.gb[pp]), mmr, sr);
-        const P2<T> DM = mul2(m.D[pp], Ms), rM = mul2(r[pp], Ms);
-        ar = fma2(DM, sub2(mul2(Ms, sub2(one, h)), tj), ar);                // drvecs (reddening - resid)/var (:550-551)
-        aden = fma2(rM, rM, aden);
-        rden = fma2(DM, DM, rden);
+        for (int u = 0; u < kPassU; u++) {
+            const int64_t t = base + u * kTile + threadIdx.x;
+            q[u] = t < hi ? (p.list ? (int64_t)p.list[t] : t) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < kPassU; u++) tag[u] = q[u] >= 0 ? pl.sflag[q[u]] : 0;
+#pragma unroll
+        for (int u = 0; u < kPassU; u++) {
+            int slot = -1;
+            bool act = false;
+            if (q[u] >= 0 && (tag_flags(tag[u]) & kFlagSurv)) {
+                const int sl = tag_slot(tag[u]);
+                const int* si = p.star_int + sl * SI_COUNT;
+                if (tag_epoch(tag[u]) == (si[SI_EPOCH] & 0xff) && si[SI_ACTIVE] != 0) { act = true; slot = sl; }
+            }
+            if (p.list_out) {   // remember the active survivors: one atomic per warp
+                const unsigned bal = __ballot_sync(0xffffffffu, act);
+                if (bal) {
+                    int at = 0;
+                    if (lane == 0) at = atomicAdd(p.nlist_out, __popc(bal));
+                    at = __shfl_sync(0xffffffffu, at, 0);
+                    if (act) p.list_out[at + __popc(bal & ((1u << lane) - 1u))] = (int)q[u];
+                }
+            }
+            T v[2] = {Num<T>::neg_inf(), Num<T>::neg_inf()};
+            if (act) {
+                const int64_t qq = q[u];
+                const DevOpts<T> o = p.o;
+                const T* __restrict__ srow = p.stars + (int64_t)slot * kStarStride;
+                ModelRegs<T, NB> m;
+                load_model_row<T, NB>(p.rows + (int64_t)pl.model[qq] * row_stride(NB), o, m);
+                const T c = srow[SR_SC + SC_MBAR] - m.bbar;
+                T A = pl.av[qq], rho = pl.rv[qq], eta = pl.eta[qq], lold = pl.lold[qq];
+                P2<T> e[NP], r[NP];
+                Mle<T, NB> r4;
+                resid_at<T, NB>(m, o, srow, A, rho, e, r);
+                mle_from_resid<T, NB>(e, c, srow, r4);
+                const T lnew = flux_step<T, NB>(m, o, srow, c, eta, A, rho, e, r, r4);
+                v[0] = (lnew == lnew) ? lnew : Num<T>::neg_inf();
+                v[1] = (tabs(lnew - lold) > o.ltol) ? v[0] : Num<T>::neg_inf();
+                pl.lprev[qq] = lold;
+                if (lnew < lold) eta = eta / T(1.2);            // :802
+                pl.eta[qq] = eta;
+                pl.lold[qq] = lnew;                              // :803
+                T ic[5];
+                icov_terms<T, NB>(m, o, srow, A, r, r4, ic);
+                store_fit<T>(pl, qq, A, rho, r4.chi2, r4.s, r4.den * r4.E * r4.E, ic);
+            }
+            if (__any_sync(0xffffffffu, act)) agg.add(p.red, which, nullptr, 0, slot, act, v, false);
+        }
     }
-    const O f = (O)kFac, E = (O)r4.E;
-    const O ss = (O)r4.den * E * E;
-    const O dsa = f * E * (O)hsum2(sa), dsr = f * E * (O)hsum2(sr);
-    const O dar = f * (O)hsum2(ar);
-    const O daa = f * f * (O)hsum2(aden) + (O)o.PA + (O)(1. / (0.05 * 0.05));
-    const O drr = f * f * (O)hsum2(rden) + (O)o.PR + (O)(1. / (0.1 * 0.1));
-    if (modeA) {
-        O* w = p.o_icov + t;
-        w[0] = ss; w[p.ld] = dsa; w[2 * p.ld] = dsr; w[3 * p.ld] = daa; w[4 * p.ld] = dar; w[5 * p.ld] = drr;
-    } else {
-        O* w = p.o_icov + t * 9;
-        w[0] = ss; w[1] = dsa; w[2] = dsr; w[3] = dsa; w[4] = daa; w[5] = dar; w[6] = dsr; w[7] = dar; w[8] = drr;
-    }
+    agg.flush(p.red, which, nullptr, 0);
 }
 
 // ---- launchers -------------------------------------------------------------------------------------
@@ -679,21 +771,28 @@ template <typename T, int NB> void launch_kprobe(const ProbeParams<T>& p, cudaSt
     dim3 grid((unsigned)((ntile + p.tile_stride - 1) / p.tile_stride), (unsigned)((p.nstar + kStarChunk - 1) / kStarChunk));
     k_kprobe<T, NB><<<grid, kTile, 0, st>>>(p);
 }
-template <typename T, int NB> void launch_magfit(const SweepParams<T>& p, cudaStream_t st) {
+template <typename T, int NB> int launch_sweep(const SweepParams<T>& p, cudaStream_t st) {
+    static bool configured[64] = {};   // per device: dynamic shared memory above 48 KB needs an opt-in
+    int dev = 0;
+    cudaGetDevice(&dev);
+    constexpr size_t bytes = SweepSmem<T, NB>::bytes;
+    if (dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_sweep<T, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return (int)e;
+        configured[dev] = true;
+    }
     dim3 grid((unsigned)(p.npad / kTile), (unsigned)((p.nlist + kStarChunk - 1) / kStarChunk));
-    k_magfit<T, NB><<<grid, kTile, 0, st>>>(p);
+    k_sweep<T, NB><<<grid, kTile, bytes, st>>>(p);
+    return (int)cudaSuccess;
 }
-template <typename T, int NB> void launch_refit(const RefitParams<T>& p, cudaStream_t st) {
-    if (p.ncand <= 0) return;
-    k_refit<T, NB><<<(unsigned)((p.ncand + kRefitTile - 1) / kRefitTile), kRefitTile, 0, st>>>(p);
+template <typename T, int NB> void launch_fixup(const RecParams<T>& p, cudaStream_t st) {
+    if (p.n <= 0) return;
+    k_fixup<T, NB><<<(unsigned)((p.n + kTile - 1) / kTile), kTile, 0, st>>>(p);
 }
-template <typename T, int NB> void launch_flux(const FluxParams<T>& p, cudaStream_t st) {
-    if (p.nsv <= 0) return;
-    k_flux<T, NB><<<(unsigned)((p.nsv + kFluxTile - 1) / kFluxTile), kFluxTile, 0, st>>>(p);
-}
-template <typename T, int NB, typename O> void launch_records(const RecordParams<T, O>& p, cudaStream_t st) {
-    if (p.nrec <= 0) return;
-    k_records<T, NB, O><<<(unsigned)((p.nrec + kTile - 1) / kTile), kTile, 0, st>>>(p);
+template <typename T, int NB> void launch_flux_more(const RecParams<T>& p, cudaStream_t st) {
+    if (p.n <= 0) return;
+    const int64_t ctas = (p.n + kPassStep - 1) / kPassStep;   // with a list: p.n is an upper bound, the kernel reads *nlist
+    k_flux_more<T, NB><<<(unsigned)(ctas < kPassCtas ? ctas : kPassCtas), kTile, 0, st>>>(p);
 }
 
 }  // namespace bf

@@ -161,11 +161,11 @@ __device__ __forceinline__ T gal_lnprior(const GalDev<T>& G, const GalStar<T>& g
 
 // ---- parameters shared by the posterior kernels ------------------------------------------------------------
 template <typename T> struct PostParams {
-    // records of the first selection (device staging written by k_records, mode A, 11 rows)
-    const T* rows;           // [11][ld]: lnl, scale, av, chi2, rv, icov(ss, sa, sr, aa, ar, rr)
-    int64_t ld;
-    const int* idx;          // model index per record
-    const int* rstar;        // star slot per record
+    // records of the first selection, read in place from the candidate pool: ord[t] = pool index of the t-th
+    // selected record in (star, model) order (k_ord); no copy of the records is made for the posterior
+    const int* ord;
+    PoolArrays<T> pool;
+    int* rstar;              // [n1] star slot per record (written by k_post_mle)
     int64_t n1;
     // static per-model priors / labels ([npad], any may be null)
     const T* lnprior;
@@ -210,12 +210,14 @@ template <typename T> __global__ void __launch_bounds__(kTile) k_post_mle(const 
     int slot = -1;
     T lp = Num<T>::neg_inf();
     if (in) {
-        slot = p.rstar[t];
-        const int64_t i = p.idx[t];
+        const int64_t q = p.ord[t];
+        slot = tag_slot(p.pool.sflag[q]);
+        p.rstar[t] = slot;
+        const int64_t i = p.pool.model[q];
         ModelW<T> w;
         model_weights<T>(p.G, p.feh, p.loga, i, w);
-        const T scale = p.rows[p.ld + t];
-        const T base = p.rows[t] + (p.lnprior ? p.lnprior[i] : T(0));
+        const T scale = p.pool.scale[q];
+        const T base = p.pool.lnl[q] + (p.lnprior ? p.lnprior[i] : T(0));
         lp = base + gal_lnprior<T>(p.G, p.gstar[slot], w, scale, prsqrt(scale));
         p.lnp1[t] = lp;
         p.lnb1[t] = base;
@@ -299,14 +301,14 @@ __device__ __forceinline__ bool inv_sym3(const double (&a)[6], double (&c)[6]) {
 }
 
 template <typename T>
-__device__ __forceinline__ void make_cov(const T* __restrict__ rows, int64_t ld, int64_t t, double scale, Cov3& cv) {
+__device__ __forceinline__ void make_cov(const PoolArrays<T>& pl, int64_t q, double scale, Cov3& cv) {
     double a[6];
-    a[0] = (double)rows[5 * ld + t] * scale * scale;
-    a[1] = (double)rows[6 * ld + t] * scale;
-    a[2] = (double)rows[7 * ld + t] * scale;
-    a[3] = (double)rows[8 * ld + t];
-    a[4] = (double)rows[9 * ld + t];
-    a[5] = (double)rows[10 * ld + t];
+    a[0] = (double)pl.sden[q] * scale * scale;
+    a[1] = (double)pl.isa[q] * scale;
+    a[2] = (double)pl.isr[q] * scale;
+    a[3] = (double)pl.iaa[q];
+    a[4] = (double)pl.iar[q];
+    a[5] = (double)pl.irr[q];
     bool ok = inv_sym3(a, cv.c);
     const double iw2 = 1.0 / (0.02 * 0.02);   // 2 % Gaussian prior (:1044)
     double count = 1.0;
@@ -438,11 +440,12 @@ __device__ __forceinline__ void mc_pair(const PostParams<T>& p, const McCtx<T>& 
 
 template <typename T>
 __device__ __forceinline__ void mc_setup(const PostParams<T>& p, int64_t t, int slot, McCtx<T>& c, Cov3& cv) {
-    const int64_t i = p.idx[t];
-    c.scale = p.rows[p.ld + t];
-    c.av = p.rows[2 * p.ld + t];
-    c.rv = p.rows[4 * p.ld + t];
-    make_cov<T>(p.rows, p.ld, t, (double)c.scale, cv);
+    const int64_t q = p.ord[t];
+    const int64_t i = p.pool.model[q];
+    c.scale = p.pool.scale[q];
+    c.av = p.pool.av[q];
+    c.rv = p.pool.rv[q];
+    make_cov<T>(p.pool, q, (double)c.scale, cv);
 #pragma unroll
     for (int k = 0; k < 6; k++) c.L[k] = (T)cv.L[k];
     model_weights<T>(p.G, p.feh, p.loga, i, c.w);
@@ -492,13 +495,14 @@ template <typename T, bool ZOV> __global__ void __launch_bounds__(kTile, 4) k_po
                 neff += m.inb[1] ? 1 : 0;
             }
         }
-        const int64_t i = p.idx[t];
-        lnp = p.rows[t] + (p.lnprior ? p.lnprior[i] : T(0));                 // lnlike + lnprior (:1024)
+        const int64_t q = p.ord[t];
+        const int64_t i = p.pool.model[q];
+        lnp = p.pool.lnl[q] + (p.lnprior ? p.lnprior[i] : T(0));             // lnlike + lnprior (:1024)
         lnp = neff > 0 ? lnp + acc.value() - plog((T)neff) : Num<T>::kNegBig;  // (:1098-1100; Neff = 0 -> +inf -> -1e300)
         if (!Num<T>::finite(lnp) || lnp < Num<T>::kNegBig) lnp = Num<T>::kNegBig;   // (:1103-1105)
         p.lnp2[u] = lnp;
         // chi2 with the parallax term (:2025-2030), for chi2min
-        T chi2 = p.rows[3 * p.ld + t];
+        T chi2 = p.pool.chi2[q];
         if (c.pivar > T(0)) { const T d = psqrt(c.scale) - c.par; chi2 += d * d * c.pivar; }
         nchi = -chi2;
     }
@@ -588,7 +592,7 @@ template <typename T, bool ZOV> __global__ void __launch_bounds__(kTile) k_post_
     Cov3 cv;
     mc_setup<T>(p, t, slot, c, cv);
     const double sc = (double)c.scale;
-    p.o_idx[o] = p.idx[t];
+    p.o_idx[o] = p.pool.model[p.ord[t]];
     p.o_scale[o] = sc;
     p.o_av[o] = (double)c.av;
     p.o_rv[o] = (double)c.rv;

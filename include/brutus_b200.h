@@ -73,7 +73,7 @@ typedef struct bf_stats {
     int64_t magfit_launches;
     int64_t magfit_star_passes; /* stars x full-grid passes done by those launches         */
     int64_t resweeps;       /* stars whose speculated mag-iteration count was wrong    */
-    int64_t candidates;     /* (star, model) pairs the sweep flagged for the exact re-fit          */
+    int64_t candidates;     /* candidate records the sweep appended ((star, model) pairs that may matter)   */
     int64_t fallbacks;      /* stars redone with every model as a candidate (see select_slack)      */
     int64_t survivors;      /* total models that survived the cull (brutus/fitting.py:758-759)  */
     int64_t selected;       /* total models that passed wt_thresh                     */
@@ -81,6 +81,9 @@ typedef struct bf_stats {
     double ms_post;         /* bf_fit_batch: prior integration, evidence, resampling kernels */
     int64_t selected2;      /* bf_fit_batch: models that passed lnpost's second threshold     */
     int64_t clipped;        /* bf_fit_batch: stars whose second selection was cut to nsel_max */
+    int64_t fixups;         /* records refined as likely survivors that the exact cull rejected (redone)   */
+    int64_t flux_more_launches; /* flux iterations beyond the ones the sweep runs itself (whole-pool passes) */
+    int64_t regroups;       /* star groups split because their candidate records overflowed the pool      */
 } bf_stats;
 
 void bf_default_options(bf_options* opt);
@@ -226,6 +229,12 @@ int bf_get_seds(bf_handle* h, int64_t n, const int32_t* idx, const double* av, c
 
 /* Statistics of the most recent bf_loglike_full / bf_sweep_batch / bf_fit_batch call on this handle. */
 int bf_get_stats(const bf_handle* h, bf_stats* out);
+
+/* Per-kernel device times (CUDA events around every launch) accumulated since the last bf_get_trace on this
+ * handle, one "name launches ms" line per kernel; empty unless the handle was created with BRUTUS_B200_TRACE=1
+ * in the environment.  The reference's only instrumentation is a wall-clock mean per object
+ * (brutus/fitting.py:1717-1731).  The string is owned by the handle and valid until the next call. */
+const char* bf_get_trace(bf_handle* h);
 
 /* Benchmark hygiene: overwrite a 512 MB scratch buffer so that nothing of the previous step stays
  * in the 126 MB L2 (B200_PROFILING.md, "Timing hygiene"). */

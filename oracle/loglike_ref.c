@@ -110,12 +110,14 @@ static double chisquare_logpdf(double x, double df) {
  *   outputs lnl, chi2, scale, av, rv (nmodel), icov (nmodel*9), all float64
  *   diag[0]=Ndim, diag[1]=mag-loop iterations, diag[2]=flux-loop iterations, diag[3]=survivors
  *   surv_out: optional (nmodel) uint8 flag, 1 where the model survived the cull (:758-759)
+ *   lnlp_out: optional (nmodel) cull statistic lnl_p (:747-756); the survivors are lnl_p > max + ln(init_thresh)
+ *             (tests: float32 kernels may flip models within rounding of that threshold)
  * returns 0, or -1 on the ValueError of :691-693, -2 on allocation failure.
  */
 int brutus_ref_loglike(const double *data, const double *err, uint8_t *mask_io, int nfilt,
                        const float *coeffs, int64_t nmodel, const ref_options *o, double parallax,
                        double parallax_err, double *lnl, double *chi2, double *scale, double *av,
-                       double *rv, double *icov, int64_t *diag, uint8_t *surv_out) {
+                       double *rv, double *icov, int64_t *diag, uint8_t *surv_out, double *lnlp_out) {
     if (o->init_thresh > o->ltol_subthresh) return -1; /* :691-693 */
     const int max_iter = o->max_iter > 0 ? o->max_iter : 1000;
 
@@ -296,6 +298,7 @@ int brutus_ref_loglike(const double *data, const double *err, uint8_t *mask_io, 
         int keep = lnl_p[i] > lthr;
         if (keep) sel[nsel++] = i;
         if (surv_out) surv_out[i] = (uint8_t)keep;
+        if (lnlp_out) lnlp_out[i] = lnl_p[i];
     }
 
     /* ---- flux-space iteration on the survivors (:778-803) ---- */
@@ -469,7 +472,7 @@ int brutus_ref_loglike_batch(int nstar, const double *flux, const double *err, c
             int rc = brutus_ref_loglike(flux + (size_t)s * nfilt, err + (size_t)s * nfilt, m, nfilt,
                                         coeffs, nmodel, o, parallax ? parallax[s] : NAN,
                                         parallax_err ? parallax_err[s] : NAN, lnl, chi2, sc, av, rv,
-                                        icov, diag + 4 * (size_t)s, NULL);
+                                        icov, diag + 4 * (size_t)s, NULL, NULL);
             if (rc) { rc_all = rc; continue; }
             int64_t k = 0;
             for (int64_t i = 1; i < nmodel; i++)

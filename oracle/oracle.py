@@ -37,7 +37,7 @@ def _load():
         lib.brutus_ref_loglike.restype = C.c_int
         lib.brutus_ref_loglike.argtypes = [dp, dp, u8p, C.c_int, fp, C.c_int64,
                                            C.POINTER(RefOptions), C.c_double, C.c_double,
-                                           dp, dp, dp, dp, dp, dp, i64p, u8p]
+                                           dp, dp, dp, dp, dp, dp, i64p, u8p, dp]
         lib.brutus_ref_select.restype = C.c_int64
         lib.brutus_ref_select.argtypes = [C.c_int64, dp, dp, dp, C.c_int, C.c_double, C.c_double,
                                           C.c_int, dp, dp, dp, C.c_double, dp, u8p]
@@ -87,11 +87,12 @@ def loglike(data, data_err, data_mask, mag_coeffs, parallax=None, parallax_err=N
     icov = np.empty((n, 3, 3))
     diag = np.zeros(4, dtype=np.int64)
     surv = np.zeros(n, dtype=np.uint8)
+    lnlp = np.zeros(n)
     rc = lib.brutus_ref_loglike(_p(d, C.c_double), _p(e, C.c_double), _p(m, C.c_uint8), nf,
                                 _p(co, C.c_float), n, C.byref(o), par, perr,
                                 _p(lnl, C.c_double), _p(chi2, C.c_double), _p(sc, C.c_double),
                                 _p(av, C.c_double), _p(rv, C.c_double), _p(icov, C.c_double),
-                                _p(diag, C.c_int64), _p(surv, C.c_uint8))
+                                _p(diag, C.c_int64), _p(surv, C.c_uint8), _p(lnlp, C.c_double))
     if rc:
         raise RuntimeError("oracle failed rc=%d" % rc)
     data_mask[...] = m.astype(bool)  # in-place clean-up, brutus/fitting.py:709
@@ -100,7 +101,7 @@ def loglike(data, data_err, data_mask, mag_coeffs, parallax=None, parallax_err=N
         out = out + (sc, av, rv, icov)
     if return_diag:
         out = out + ({"n_iter_mag": int(diag[1]), "n_iter_flux": int(diag[2]),
-                      "n_surv": int(diag[3]), "survivors": surv.astype(bool)},)
+                      "n_surv": int(diag[3]), "survivors": surv.astype(bool), "lnl_p": lnlp},)
     return out
 
 

@@ -49,34 +49,10 @@ def test_sweep_batch_vs_oracle(oracle_mod, precision):
     h.close()
     assert stats["kernel_launches"] > 0
     assert res["offsets"][0] == 0 and res["offsets"][-1] == len(res["model_idx"])
+    import parity
     for i in range(24):
-        ref, lnl, lnprob, sel = _oracle_star(oracle_mod, grid, st, i, labels=lab, ext=(ext_mean, ext_std))
-        lo, hi = res["offsets"][i], res["offsets"][i + 1]
-        idx = res["model_idx"][lo:hi]
-        assert np.all(np.diff(idx) > 0)
-        assert res["ndim"][i] == ref[1]
-        assert tuple(res["n_iter"][i]) == (ref[7]["n_iter_mag"], ref[7]["n_iter_flux"]), i
-        rec = {k: res[k][lo:hi].astype(np.float64) for k in ("lnl", "chi2", "scale", "av", "rv")}
-        rec["icov6"] = res["icov6"][:, lo:hi].T.astype(np.float64)
-        if precision == "f64":
-            assert res["n_surv"][i] == ref[7]["n_surv"]
-            assert np.array_equal(idx, sel), i
-            assert abs(res["max_lnprob"][i] - lnprob.max()) < 1e-8 * max(1, abs(lnprob.max()))
-            for k, r in (("lnl", lnl), ("chi2", ref[2]), ("scale", ref[3]), ("av", ref[4]), ("rv", ref[5])):
-                assert np.max(np.abs(rec[k] - r[sel]) / np.maximum(np.abs(r[sel]), 1e-300)) < 1e-8, (i, k)
-            r6 = _unpack6(ref[6][sel])
-            assert np.max(np.abs(rec["icov6"] - r6) / np.maximum(np.abs(r6), 1e-300)) < 1e-7, i
-        else:
-            thr = lnprob.max() + np.log(1e-3)
-            sym = np.setxor1d(idx, sel)
-            assert np.all(np.abs(lnprob[sym] - thr) < 2e-3 + 2e-5 * abs(thr)), (i, len(sym))
-            common = np.intersect1d(idx, sel)
-            pos = np.searchsorted(idx, common)
-            assert np.max(np.abs(rec["chi2"][pos] - ref[2][common])) < 2e-3 + 2e-5 * np.max(ref[2][common])
-            assert np.max(np.abs(rec["lnl"][pos] - lnl[common])) < 2e-3 + 2e-5 * np.max(np.abs(lnl[common]))
-            assert np.max(np.abs(rec["av"][pos] - ref[4][common])) < 2e-4
-            assert np.max(np.abs(rec["rv"][pos] - ref[5][common])) < 2e-3
-            assert np.max(np.abs(rec["scale"][pos] / ref[3][common] - 1)) < 2e-5
+        ref, lnl, lnprob, sel = parity.oracle_star(oracle_mod, grid, st, i, labels=lab, ext=(ext_mean, ext_std))
+        parity.check_star(res, i, ref, lnl, lnprob, sel, precision, tag=(precision, i))
 
 
 def test_batch_equals_single_star():
