@@ -21,7 +21,8 @@ SYMBOLS = ("bf_default_options", "bf_create", "bf_destroy", "bf_last_error", "bf
            "bf_set_grid_device", "bf_set_labels", "bf_loglike_full", "bf_sweep_batch",
            "bf_get_stats", "bf_flush_l2", "bf_device_count", "bf_version",
            "bf_default_gal_params", "bf_default_post_options", "bf_set_model_priors", "bf_fit_batch",
-           "bf_get_seds", "bf_get_trace")
+           "bf_get_seds", "bf_get_trace", "bf_create_multi", "bf_num_devices", "bf_nccl_unique_id",
+           "bf_nccl_init", "bf_set_grid_bcast", "bf_bcast_host", "bf_allreduce_max")
 
 
 class BrutusCudaError(RuntimeError):
@@ -53,7 +54,8 @@ class Stats(C.Structure):
                 ("survivors", C.c_int64),
                 ("selected", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("ms_post", C.c_double), ("selected2", C.c_int64), ("clipped", C.c_int64),
-                ("fixups", C.c_int64), ("flux_more_launches", C.c_int64), ("regroups", C.c_int64)]
+                ("fixups", C.c_int64), ("flux_more_launches", C.c_int64), ("regroups", C.c_int64),
+                ("unconverged", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -102,6 +104,13 @@ def load():
     lib.bf_default_options.argtypes = [op]
     lib.bf_default_options.restype = None
     lib.bf_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
+    lib.bf_create_multi.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(vp)]
+    lib.bf_num_devices.argtypes = [vp]
+    lib.bf_nccl_unique_id.argtypes = [vp]
+    lib.bf_nccl_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.bf_set_grid_bcast.argtypes = [vp, fp, C.c_int64, C.c_int32, C.c_int32, C.c_int32]
+    lib.bf_bcast_host.argtypes = [vp, vp, C.c_int64, C.c_int]
+    lib.bf_allreduce_max.argtypes = [vp, dp, C.c_int32]
     lib.bf_destroy.argtypes = [vp]
     lib.bf_last_error.argtypes = [vp]
     lib.bf_last_error.restype = C.c_char_p
@@ -154,21 +163,70 @@ def make_options(avlim=(0., 20.), av_gauss=(0., 1e6), rvlim=(1., 8.), rv_gauss=(
 
 
 class Handle:
-    """One sweep engine bound to one CUDA device (not re-entrant)."""
+    """A sweep engine on one CUDA device, or -- ``device`` a sequence of ordinals -- on several devices of this
+    process (``bf_create_multi``: the batch calls shard the stars over them).  Not re-entrant."""
 
     def __init__(self, device=0, precision="f32"):
         self._lib = load()
         self._h = C.c_void_p()
         prec = {"f32": PRECISION_F32, "f64": PRECISION_F64}[precision]
-        rc = self._lib.bf_create(int(device), prec, C.byref(self._h))
+        devs = [int(d) for d in device] if isinstance(device, (list, tuple, np.ndarray)) else [int(device)]
+        arr = (C.c_int * len(devs))(*devs)
+        rc = self._lib.bf_create_multi(arr, len(devs), prec, C.byref(self._h))
         if rc != BF_OK:
             raise BrutusCudaError(self._lib.bf_last_error(None).decode())
         self.precision = precision
-        self.device = int(device)
+        self.devices = devs
+        self.device = devs[0]
         self.nmodel = 0
         self.nfilt = 0
         self.nlabel = 0
+        self.rank, self.world = 0, 1
         self._grid_token = None
+
+    # ---- one process per GPU: NCCL process group inside the library (no PyTorch) ----
+    @staticmethod
+    def nccl_unique_id():
+        """128-byte NCCL id, to be created on rank 0 and handed to every rank."""
+        buf = C.create_string_buffer(128)
+        rc = load().bf_nccl_unique_id(buf)
+        if rc != BF_OK:
+            raise BrutusCudaError(load().bf_last_error(None).decode())
+        return buf.raw
+
+    def nccl_init(self, unique_id, rank, world):
+        self._check(self._lib.bf_nccl_init(self._h, C.c_char_p(bytes(unique_id)), int(rank), int(world)))
+        self.rank, self.world = int(rank), int(world)
+
+    def set_grid_bcast(self, mag_coeffs, shape, root=0):
+        """Replicate the grid held by rank ``root`` (``mag_coeffs`` may be None elsewhere) with one NCCL broadcast."""
+        nmodel, nfilt = int(shape[0]), int(shape[1])
+        ptr, layout = None, LAYOUT_C
+        if self.rank == root:
+            a = np.asarray(mag_coeffs)
+            if a.shape != (nmodel, nfilt, 3):
+                raise ValueError("grid shape %r does not match %r" % (a.shape, tuple(shape)))
+            if a.dtype != np.float32:
+                a = a.astype(np.float32)
+            if a.flags.f_contiguous and not a.flags.c_contiguous:
+                layout = LAYOUT_F
+            elif not a.flags.c_contiguous:
+                a = np.ascontiguousarray(a)
+            ptr = _ptr(a, C.c_float)
+        layout = int(self.bcast_array(np.array([layout], dtype=np.int64), root)[0])
+        self._check(self._lib.bf_set_grid_bcast(self._h, ptr, nmodel, nfilt, layout, int(root)))
+        self.nmodel, self.nfilt, self.nlabel = nmodel, nfilt, 0
+
+    def bcast_array(self, a, root=0):
+        """In-place broadcast of a C-contiguous NumPy array of identical shape/dtype on every rank."""
+        a = np.ascontiguousarray(a)
+        self._check(self._lib.bf_bcast_host(self._h, a.ctypes.data_as(C.c_void_p), a.nbytes, int(root)))
+        return a
+
+    def allreduce_max(self, vals):
+        v = np.ascontiguousarray(vals, dtype=np.float64).copy()
+        self._check(self._lib.bf_allreduce_max(self._h, _ptr(v, C.c_double), v.size))
+        return v
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -223,6 +281,13 @@ class Handle:
         self._lib.bf_get_stats(self._h, C.byref(s))
         return s.as_dict()
 
+    def _warn_unconverged(self):
+        n = self.stats()["unconverged"]
+        if n:
+            import warnings
+            warnings.warn("%d star(s) hit the iteration cap (bf_options.max_iter) before the reference's convergence "
+                          "test passed; their results are those of the last iteration" % n, RuntimeWarning, stacklevel=3)
+
     def trace(self):
         """Per-kernel device times since the last call (needs BRUTUS_B200_TRACE=1 when the handle is created):
         ``{kernel: (launches, ms)}``."""
@@ -248,6 +313,7 @@ class Handle:
             float(parallax_err), C.byref(opts), _ptr(lnl, C.c_double), _ptr(chi2, C.c_double),
             _ptr(sc, C.c_double), _ptr(av, C.c_double), _ptr(rv, C.c_double), _ptr(icov, C.c_double),
             _ptr(mclean, C.c_uint8), _ptr(diag, C.c_int64)))
+        self._warn_unconverged()
         return lnl, chi2, sc, av, rv, icov, mclean.astype(bool), diag
 
     def sweep_batch(self, flux, err, mask, parallax=None, parallax_err=None, ext_mean=None,
@@ -284,6 +350,7 @@ class Handle:
             _ptr(es, C.c_double), C.byref(opts), int(rows), _ptr(ndim, C.c_int32),
             _ptr(nit, C.c_int32), _ptr(nsurv, C.c_int64), _ptr(mx, C.c_double),
             _ptr(offsets, C.c_int64), C.byref(rec)))
+        self._warn_unconverged()
         n = int(rec.n)
         out = dict(ndim=ndim, n_iter=nit, n_surv=nsurv, max_lnprob=mx, offsets=offsets)
         dt = np.float32 if rec.elem_size == 4 else np.float64
@@ -395,6 +462,7 @@ class Handle:
             _ptr(es, C.c_double), C.byref(opts), C.byref(po), _ptr(ndim, C.c_int32),
             _ptr(nit, C.c_int32), _ptr(nsel, C.c_int64), _ptr(levid, C.c_double),
             _ptr(chi2min, C.c_double), C.byref(dr)))
+        self._warn_unconverged()
         del keep
         out = {}
         if ns > 0:

@@ -56,7 +56,7 @@ def build(force=False, verbose=False):
             if verbose and out.strip():
                 print(out)
     _run([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
-                                               "-lcudart_static", "-Xcompiler", "-fPIC"])
+                                               "-lcudart_static", "-ldl", "-lpthread", "-Xcompiler", "-fPIC"])
     return LIB
 
 

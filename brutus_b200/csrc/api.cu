@@ -480,6 +480,11 @@ struct EngineBase {
                           const double* ext_std, const bf_options* opt, const bf_post_options* po, int32_t* ndim,
                           int32_t* n_iter, int64_t* nsel, double* levid, double* chi2min, bf_draws* out) = 0;
     virtual const char* get_trace() = 0;
+    // multi-device calls: the draws of this engine's stars go to [off, off + nstar) of a shared pinned arena
+    virtual void set_ext_arena(char* arena, size_t ntot, size_t off) = 0;
+    virtual int nfilt_() const = 0;
+    virtual int nlabel_() const = 0;
+    virtual const char* records_arena(int64_t* cap) = 0;
 };
 
 #define CK(call)                                                                               \
@@ -593,7 +598,19 @@ static void prep_star(const double* flux, const double* errv, const uint8_t* mas
     }
     double* sc = sp.row + SR_SC;
     sc[SC_MBAR] = mbar;
-    sc[SC_S] = S;
+    // No band with positive flux: the reference's magnitude fit then runs on weights of 1e-50 (:725), against which
+    // the prior precisions dominate completely -- Av and Rv stay at the prior means to ~1e-38 and the loop stops after
+    // one iteration.  With every weight 0 the 2x2 solves would be 0/0; S = 1 (weights still 0) gives exactly that
+    // behaviour: zero steps, one iteration.
+    sc[SC_S] = S > 0. ? S : 1.;
+    // Exactly one band with positive flux: the reference's 2x2 systems are singular up to weights of 1e-50 (the
+    // determinant S a - b^2 is pure rounding noise next to S/sigma_Av^2) and its magnitude-space step is whatever the
+    // cancellation leaves -- in practice zero, one iteration.  That is made explicit here: the band's weight is
+    // dropped from the magnitude fit as well (Av, Rv start the flux phase at the prior means).
+    if (npos == 1) {
+        for (int j = 0; j < nfilt; j++) sp.row[SR_U + j] = 0.;
+        sc[SC_S] = 1.;
+    }
     const bool have = std::isfinite(par) && std::isfinite(perr);  // :750-751
     sc[SC_PAR] = have ? par : 0.;
     sc[SC_PIVAR] = have ? 1. / (perr * perr) : 0.;
@@ -617,6 +634,12 @@ template <typename T> struct Engine : EngineBase {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
     cudaEvent_t ev_rec[2] = {nullptr, nullptr}, ev_cp[2] = {nullptr, nullptr};
+    char* ext_arena = nullptr;  // shared draw arena of a multi-device handle (not owned)
+    size_t ext_ntot = 0, ext_off = 0;   // arena size in draws; this engine's first star
+    void set_ext_arena(char* a, size_t ntot, size_t off) override { ext_arena = a; ext_ntot = ntot; ext_off = off; }
+    const char* records_arena(int64_t* cap) override { *cap = arena_cap; return arena; }
+    int nfilt_() const override { return nfilt; }
+    int nlabel_() const override { return nlabel; }
     char* draw_arena = nullptr; // pinned host memory holding the posterior draws of the last bf_fit_batch
     size_t draw_cap = 0;        // in draws (nstar * ndraws)
     char* arena = nullptr;      // pinned host memory holding the records of the last bf_sweep_batch
@@ -625,6 +648,7 @@ template <typename T> struct Engine : EngineBase {
     int nfilt = 0, nlabel = 0, rs = 0;
     int batch_cap = 0;
     int64_t pool_cap = 0;
+    int max_flux = 1000;         // cap on flux-loop iterations (make_opts)
     const KTable<T>* kt = nullptr;
 
     DevBuf<float> d_grid, d_rows;
@@ -888,7 +912,11 @@ template <typename T> struct Engine : EngineBase {
         o.ln_sub = (T)std::log(opt->ltol_subthresh);
         o.ln_wt = (T)(opt->wt_thresh > 0 ? std::log(opt->wt_thresh) : -INFINITY);
         o.dim_prior = opt->dim_prior;
+        // The reference's loops are unbounded (brutus/fitting.py:173-264, :781-803).  Caps, as a safety net only: 64 mag
+        // iterations (each costs sweeps of the whole grid), 1000 flux iterations (cheap: they revisit a list of
+        // survivors); opt->max_iter > 0 sets both.  Stars that hit a cap are counted in stats.unconverged.
         max_iter = opt->max_iter > 0 ? opt->max_iter : 64;
+        max_flux = opt->max_iter > 0 ? opt->max_iter : 1000;
         return BF_OK;
     }
 
@@ -949,7 +977,7 @@ template <typename T> struct Engine : EngineBase {
                       int* n_mag, bool* fits, int64_t* nrec) {
         const PoolArrays<T> pl = pool();
         const int ng = g1 - g0;
-        const int nit_first = std::min(2, max_iter);
+        const int nit_first = std::min(2, max_flux);
         bool redo_all = true;
         while (redo_all) {
             redo_all = false;
@@ -1012,6 +1040,7 @@ template <typename T> struct Engine : EngineBase {
                         // (ksp + 1, ksp + 2); either way contiguous with what is known
                         ksp = std::min(h_kpred[s] == ksp + 1 ? ksp + 1 : ksp + 2, max_iter); next.push_back(s);
                     } else {
+                        if (!conv_last) stats.unconverged++;   // the cap on mag iterations stopped the loop
                         exact[s] = 1;
                     }
                 }
@@ -1041,7 +1070,7 @@ template <typename T> struct Engine : EngineBase {
             phase_begin();
             { TRACE("k_reset_red"); k_reset_red<T><<<(ng * kNumRed + 255) / 256, 256, 0, stream>>>(d_red.p, d_list.p, ng, (1u << RED_FL) | (1u << RED_FB) | (1u << RED_LNP)); }
             if (n > 0) { TRACE("k_cull"); k_cull<T><<<pass_ctas(n), kTile, 0, stream>>>(pp); }
-            { TRACE("k_flux_ctl"); k_flux_ctl<T><<<1, 1024, 0, stream>>>(d_star_int.p, d_red.p, d_list.p, ng, 1, nit_first, max_iter, o.ln_sub, d_ctr.p + CTR_ANY); }
+            { TRACE("k_flux_ctl"); k_flux_ctl<T><<<1, 1024, 0, stream>>>(d_star_int.p, d_red.p, d_list.p, ng, 1, nit_first, max_flux, o.ln_sub, d_ctr.p + CTR_ANY); }
             stats.kernel_launches += 3;
             CK(cudaGetLastError());
             publish(h_ctr.data(), d_ctr.p, CTR_COUNT * sizeof(int));
@@ -1066,9 +1095,9 @@ template <typename T> struct Engine : EngineBase {
             int done_iter = nit_first;
             bool have_list = false;
             rp.n = n;
-            while (any && done_iter < max_iter) {
+            while (any && done_iter < max_flux) {
                 int any_slot = CTR_ANY;
-                for (int r = 0; r < 3 && done_iter < max_iter; r++) {
+                for (int r = 0; r < 3 && done_iter < max_flux; r++) {
                     if (!have_list) {
                         rp.list = nullptr; rp.nlist = nullptr; rp.list_out = fixlist(); rp.nlist_out = d_ctr.p + CTR_NLIST;
                         have_list = true;
@@ -1077,7 +1106,7 @@ template <typename T> struct Engine : EngineBase {
                     }
                     { TRACE("k_flux_more"); kt->flux_more(rp, stream); }
                     any_slot = CTR_ANY + 1 + r;
-                    { TRACE("k_flux_ctl"); k_flux_ctl<T><<<1, 1024, 0, stream>>>(d_star_int.p, d_red.p, d_list.p, ng, 0, 1, max_iter, o.ln_sub, d_ctr.p + any_slot); }
+                    { TRACE("k_flux_ctl"); k_flux_ctl<T><<<1, 1024, 0, stream>>>(d_star_int.p, d_red.p, d_list.p, ng, 0, 1, max_flux, o.ln_sub, d_ctr.p + any_slot); }
                     stats.kernel_launches += 2;
                     stats.flux_more_launches++;
                     done_iter += 1;
@@ -1119,7 +1148,10 @@ template <typename T> struct Engine : EngineBase {
                 CK(cudaMemcpyAsync(d_stars.p, h_stars.data(), (size_t)ns * kStarStride * sizeof(T), cudaMemcpyHostToDevice, stream));
                 continue;
             }
-            for (int s = g0; s < g1; s++) stats.survivors += h_int[s * SI_COUNT + SI_NSURV];
+            for (int s = g0; s < g1; s++) {
+                stats.survivors += h_int[s * SI_COUNT + SI_NSURV];
+                if (h_int[s * SI_COUNT + SI_NFLUX] >= max_flux && max_flux > 2) stats.unconverged++;   // stopped by the cap
+            }
             *nrec = n;
         }
         *fits = true;
@@ -1144,6 +1176,10 @@ template <typename T> struct Engine : EngineBase {
             prep_star(flux + (size_t)s * nfilt, errv + (size_t)s * nfilt, mask + (size_t)s * nfilt, nfilt,
                       par ? par[s] : NAN, perr ? perr[s] : NAN, apply_clip, slack, sp);
             for (int k = 0; k < kStarStride; k++) h_stars[(size_t)s * kStarStride + k] = (T)sp.row[k];
+            if (sp.ndim < 4) {   // Ndim - 3 degrees of freedom (brutus/fitting.py:815); BruteForce refuses such objects (:1413-1420)
+                err = "fewer than 4 bands of acceptable photometry: the fit is degenerate (brutus/fitting.py:1413-1420)";
+                return BF_E_INVALID;
+            }
             int* si = &h_int[s * SI_COUNT];
             for (int k = 0; k < SI_COUNT; k++) si[k] = 0;
             si[SI_NDIM] = sp.ndim;
@@ -1178,7 +1214,8 @@ template <typename T> struct Engine : EngineBase {
         nlabel = 0;  // loglike itself applies no label priors
         int32_t nd;
         // slack = +inf: every model is a candidate, so the pool holds a record of every model
-        fill_rows(1, flux, errv, mask, &par, &perr, nullptr, nullptr, 0, INFINITY, max_iter, &nd, mask_out);
+        rc = fill_rows(1, flux, errv, mask, &par, &perr, nullptr, nullptr, 0, INFINITY, max_iter, &nd, mask_out);
+        if (rc) { nlabel = saved_labels; return rc; }
         rc = upload_stars(1);
         int nm = 0;
         std::vector<char> exact(1, 0);
@@ -1270,11 +1307,12 @@ template <typename T> struct Engine : EngineBase {
         const int bstep = std::max(1, std::min(batch_cap, batch_limit));
         for (int64_t s0 = 0; s0 < nstar; s0 += bstep) {
             const int ns = (int)std::min<int64_t>(bstep, nstar - s0);
-            fill_rows(ns, flux + (size_t)s0 * nfilt, errv + (size_t)s0 * nfilt, mask + (size_t)s0 * nfilt,
-                      par ? par + s0 : nullptr, perr ? perr + s0 : nullptr,
-                      ext_mean ? ext_mean + (size_t)s0 * nlabel : nullptr,
-                      ext_std ? ext_std + (size_t)s0 * nlabel : nullptr, opt->apply_parallax_clip, slack, max_iter,
-                      ndim ? ndim + s0 : nullptr, nullptr);
+            rc = fill_rows(ns, flux + (size_t)s0 * nfilt, errv + (size_t)s0 * nfilt, mask + (size_t)s0 * nfilt,
+                           par ? par + s0 : nullptr, perr ? perr + s0 : nullptr,
+                           ext_mean ? ext_mean + (size_t)s0 * nlabel : nullptr,
+                           ext_std ? ext_std + (size_t)s0 * nlabel : nullptr, opt->apply_parallax_clip, slack, max_iter,
+                           ndim ? ndim + s0 : nullptr, nullptr);
+            if (rc) return rc;
             rc = upload_stars(ns);
             if (rc) return rc;
             CK(cudaEventRecord(ev0, stream));
@@ -1526,18 +1564,25 @@ template <typename T> struct Engine : EngineBase {
         CK(cudaSetDevice(device));
         if (!kt) { err = "bf_fit_batch: no grid (call bf_set_grid)"; return BF_E_NOGRID; }
         if (nstar < 0 || (nstar > 0 && (!flux || !errv || !mask)) || !opt || !po || !out || !levid || !chi2min) { err = "bf_fit_batch: null argument"; return BF_E_INVALID; }
-        // library-owned pinned arena for the draws: [idx int32 | 8 double arrays | cov 9 doubles] x nstar*ndraws
-        const size_t ntot = (size_t)std::max<int64_t>(nstar, 1) * po->ndraws;
-        if (ntot > draw_cap) {
-            if (draw_arena) cudaFreeHost(draw_arena);
-            draw_arena = nullptr; draw_cap = 0;
-            CK(cudaHostAlloc((void**)&draw_arena, ntot * (17 * sizeof(double) + sizeof(int32_t)) + 64, cudaHostAllocPortable));
-            draw_cap = ntot;
-        }
-        double* const hd = (double*)draw_arena;                     // 8 arrays, then cov
-        int32_t* const hidx = (int32_t*)(draw_arena + ntot * 17 * sizeof(double));
         if (po->nmc_prior < 1 || po->ndraws < 1) { err = "bf_fit_batch: nmc_prior and ndraws must be >= 1"; return BF_E_INVALID; }
         if (po->use_gal_prior && !coords) { err = "`coord` must be provided if using the default Galactic model prior."; return BF_E_INVALID; }
+        // pinned arena for the draws: [8 double arrays | cov 9 doubles | idx int32] x ntot draws; owned by this
+        // engine, or the shared arena of a multi-device handle (this engine then fills its stars' slice)
+        size_t ntot = (size_t)std::max<int64_t>(nstar, 1) * po->ndraws, aoff = 0;
+        char* abase = nullptr;
+        if (ext_arena) {
+            abase = ext_arena; ntot = ext_ntot; aoff = ext_off;
+        } else {
+            if (ntot > draw_cap) {
+                if (draw_arena) cudaFreeHost(draw_arena);
+                draw_arena = nullptr; draw_cap = 0;
+                CK(cudaHostAlloc((void**)&draw_arena, ntot * (17 * sizeof(double) + sizeof(int32_t)) + 64, cudaHostAllocPortable));
+                draw_cap = ntot;
+            }
+            abase = draw_arena;
+        }
+        double* const hd = (double*)abase;                     // 8 arrays, then cov
+        int32_t* const hidx = (int32_t*)(abase + ntot * 17 * sizeof(double));
         stats = bf_stats{};
         const int nd = po->ndraws, nmc = po->nmc_prior;
         const GalDev<T> G = make_gal(po);
@@ -1681,7 +1726,7 @@ template <typename T> struct Engine : EngineBase {
             CK(cudaGetLastError());
             CK(cudaEventRecord(evP1, stream));
             // ---- ndraws samples per star back to the caller's arrays ----
-            const size_t off = (size_t)g.g0 * nd, cnt = (size_t)ng * nd, dst = (size_t)(g.s0 + g.g0) * nd;
+            const size_t off = (size_t)g.g0 * nd, cnt = (size_t)ng * nd, dst = (aoff + (size_t)(g.s0 + g.g0)) * nd;   // aoff: first star of this engine in the arena
             CK(cudaMemcpyAsync(hidx + dst, pp.o_idx + off, cnt * sizeof(int), cudaMemcpyDeviceToHost, stream));
             double* hdst[8];
             for (int k = 0; k < 8; k++) hdst[k] = hd + (size_t)k * ntot;   // scale, av, rv, lnprob, dist, red, dred, logwt
@@ -1717,9 +1762,107 @@ template <typename T> struct Engine : EngineBase {
 // =================================================================================================
 // C ABI
 // =================================================================================================
-struct bf_handle {
-    bf::EngineBase* eng;
+// ---- NCCL, resolved at run time --------------------------------------------------------------------------
+// The library does not link NCCL: single-GPU use must work where NCCL is absent, and a process that also
+// imports PyTorch already has a libnccl.so.2 loaded (dlopen by soname then returns that same copy instead of
+// mixing two versions).  Only the multi-device entry points need it.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <thread>
+
+namespace bf {
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*GetVersion)(int*) = nullptr;
 };
+
+static NcclApi* nccl_api(std::string& err) {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.lib) break; }
+        if (api.lib) {
+#define BF_SYM(field, name) *(void**)(&api.field) = dlsym(api.lib, name)
+            BF_SYM(GetUniqueId, "ncclGetUniqueId"); BF_SYM(CommInitRank, "ncclCommInitRank");
+            BF_SYM(CommInitAll, "ncclCommInitAll"); BF_SYM(CommDestroy, "ncclCommDestroy");
+            BF_SYM(Broadcast, "ncclBroadcast"); BF_SYM(AllReduce, "ncclAllReduce");
+            BF_SYM(GroupStart, "ncclGroupStart"); BF_SYM(GroupEnd, "ncclGroupEnd");
+            BF_SYM(GetErrorString, "ncclGetErrorString"); BF_SYM(GetVersion, "ncclGetVersion");
+#undef BF_SYM
+            if (!api.GetUniqueId || !api.CommInitRank || !api.CommInitAll || !api.CommDestroy || !api.Broadcast ||
+                !api.AllReduce || !api.GroupStart || !api.GroupEnd) { dlclose(api.lib); api.lib = nullptr; }
+        }
+    }
+    if (!api.lib) { err = "NCCL (libnccl.so.2) could not be loaded: multi-GPU entry points are unavailable"; return nullptr; }
+    return &api;
+}
+}  // namespace bf
+
+// One handle = one engine per device.  bf_create: one device.  bf_create_multi: several devices of this
+// process, an NCCL communicator per device (ncclCommInitAll), one host thread per device in the batch calls.
+struct bf_handle {
+    std::vector<bf::EngineBase*> eng;
+    std::vector<ncclComm_t> comms;      // in-process group (bf_create_multi), or the one rank of a process group
+    int rank = 0, world = 1;            // process group (bf_nccl_init); in-process handles keep (0, 1)
+    std::string err;
+    bf_stats stats{};
+    // combined results of the multi-device batch calls (pinned, owned by the handle)
+    char* draw_arena = nullptr; size_t draw_cap = 0;
+    char* rec_arena = nullptr; int64_t rec_cap = 0;
+    std::vector<int64_t> last_split;    // stars [last_split[d], last_split[d+1]) went to device d in the last call
+    bf::EngineBase* e0() const { return eng[0]; }
+};
+
+#define HCK(h, call)                                                                           \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            char b_[512];                                                                      \
+            snprintf(b_, sizeof b_, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            (h)->err = b_;                                                                     \
+            return BF_E_CUDA;                                                                  \
+        }                                                                                      \
+    } while (0)
+#define HNCCL(h, api, call)                                                                    \
+    do {                                                                                       \
+        ncclResult_t r_ = (call);                                                              \
+        if (r_ != ncclSuccess) {                                                               \
+            (h)->err = std::string("NCCL: ") + #call + ": " + ((api)->GetErrorString ? (api)->GetErrorString(r_) : "error"); \
+            return BF_E_CUDA;                                                                  \
+        }                                                                                      \
+    } while (0)
+
+static bf::EngineBase* make_engine(int device, int precision, std::string& err, int* rc_out) {
+    bf::EngineBase* eng = nullptr;
+    if (precision == BF_PRECISION_F32) eng = new bf::Engine<float>();
+    else if (precision == BF_PRECISION_F64) eng = new bf::Engine<double>();
+    else { err = "bf_create: unknown precision"; *rc_out = BF_E_INVALID; return nullptr; }
+    eng->device = device;
+    eng->precision = precision;
+    int rc = precision == BF_PRECISION_F32 ? static_cast<bf::Engine<float>*>(eng)->init()
+                                           : static_cast<bf::Engine<double>*>(eng)->init();
+    if (rc) { err = eng->err; delete eng; *rc_out = rc; return nullptr; }
+    *rc_out = BF_OK;
+    return eng;
+}
+
+// contiguous star ranges, sizes differing by at most one
+static void split_stars(int64_t nstar, int nd, std::vector<int64_t>& b) {
+    b.assign(nd + 1, 0);
+    const int64_t base = nstar / nd, extra = nstar % nd;
+    for (int d = 0; d < nd; d++) b[d + 1] = b[d] + base + (d < extra ? 1 : 0);
+}
 
 extern "C" {
 
@@ -1740,61 +1883,242 @@ int bf_device_count(void) {
     return n;
 }
 
-const char* bf_version(void) { return "brutus_b200 0.1.0 (sm_100a)"; }
+const char* bf_version(void) { return "brutus_b200 0.2.0 (sm_100a)"; }
 
-int bf_create(int device, int precision, bf_handle** out) {
+int bf_create_multi(const int* devices, int ndev, int precision, bf_handle** out) {
     if (!out) { bf::g_create_error = "bf_create: null out pointer"; return BF_E_INVALID; }
     *out = nullptr;
+    if (!devices || ndev < 1) { bf::g_create_error = "bf_create_multi: need at least one device"; return BF_E_INVALID; }
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) {
         bf::g_create_error = std::string("bf_create: no CUDA device available (") + cudaGetErrorString(e) + "); there is no CPU fallback";
         return BF_E_CUDA;
     }
-    if (device < 0 || device >= n) { bf::g_create_error = "bf_create: device ordinal out of range"; return BF_E_INVALID; }
-    bf::EngineBase* eng = nullptr;
-    if (precision == BF_PRECISION_F32) eng = new bf::Engine<float>();
-    else if (precision == BF_PRECISION_F64) eng = new bf::Engine<double>();
-    else { bf::g_create_error = "bf_create: unknown precision"; return BF_E_INVALID; }
-    eng->device = device;
-    eng->precision = precision;
-    int rc = precision == BF_PRECISION_F32 ? static_cast<bf::Engine<float>*>(eng)->init()
-                                           : static_cast<bf::Engine<double>*>(eng)->init();
-    if (rc) { bf::g_create_error = eng->err; delete eng; return rc; }
-    *out = new bf_handle{eng};
+    for (int d = 0; d < ndev; d++) {
+        if (devices[d] < 0 || devices[d] >= n) { bf::g_create_error = "bf_create: device ordinal out of range"; return BF_E_INVALID; }
+        for (int k = 0; k < d; k++)
+            if (devices[k] == devices[d]) { bf::g_create_error = "bf_create_multi: duplicate device"; return BF_E_INVALID; }
+    }
+    bf_handle* h = new bf_handle();
+    for (int d = 0; d < ndev; d++) {
+        int rc = BF_OK;
+        bf::EngineBase* eng = make_engine(devices[d], precision, bf::g_create_error, &rc);
+        if (!eng) { for (auto* x : h->eng) delete x; delete h; return rc; }
+        h->eng.push_back(eng);
+    }
+    if (ndev > 1) {   // the communicators the grid broadcast runs on
+        bf::NcclApi* api = bf::nccl_api(bf::g_create_error);
+        ncclResult_t r = ncclSuccess;
+        if (api) {
+            h->comms.resize(ndev);
+            r = api->CommInitAll(h->comms.data(), ndev, devices);
+        }
+        if (!api || r != ncclSuccess) {
+            if (api) bf::g_create_error = std::string("ncclCommInitAll: ") + (api->GetErrorString ? api->GetErrorString(r) : "error");
+            for (auto* x : h->eng) delete x;
+            delete h;
+            return BF_E_CUDA;
+        }
+    }
+    *out = h;
     return BF_OK;
 }
 
+int bf_create(int device, int precision, bf_handle** out) { return bf_create_multi(&device, 1, precision, out); }
+
+int bf_num_devices(const bf_handle* h) { return h ? (int)h->eng.size() : 0; }
+
 int bf_destroy(bf_handle* h) {
     if (!h) return BF_OK;
-    delete h->eng;
+    if (!h->comms.empty()) {
+        std::string e;
+        if (bf::NcclApi* api = bf::nccl_api(e))
+            for (ncclComm_t c : h->comms) if (c) api->CommDestroy(c);
+    }
+    for (auto* x : h->eng) delete x;
+    if (h->draw_arena) cudaFreeHost(h->draw_arena);
+    if (h->rec_arena) cudaFreeHost(h->rec_arena);
     delete h;
     return BF_OK;
 }
 
-const char* bf_last_error(const bf_handle* h) { return h ? h->eng->err.c_str() : bf::g_create_error.c_str(); }
+const char* bf_last_error(const bf_handle* h) {
+    if (!h) return bf::g_create_error.c_str();
+    if (!h->err.empty()) return h->err.c_str();
+    for (auto* x : h->eng) if (!x->err.empty()) return x->err.c_str();
+    return "";
+}
+
+// ---- process groups: one process per GPU (torchrun), NCCL inside the library -------------------------------
+int bf_nccl_unique_id(void* out128) {
+    if (!out128) return BF_E_INVALID;
+    bf::NcclApi* api = bf::nccl_api(bf::g_create_error);
+    if (!api) return BF_E_CUDA;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    if (api->GetUniqueId(&id) != ncclSuccess) { bf::g_create_error = "ncclGetUniqueId failed"; return BF_E_CUDA; }
+    std::memcpy(out128, &id, sizeof id);
+    return BF_OK;
+}
+
+int bf_nccl_init(bf_handle* h, const void* id128, int rank, int world) {
+    if (!h || !id128 || world < 1 || rank < 0 || rank >= world) return BF_E_INVALID;
+    if (h->eng.size() != 1) { h->err = "bf_nccl_init: a process-group handle drives exactly one device"; return BF_E_INVALID; }
+    h->err.clear();
+    bf::NcclApi* api = bf::nccl_api(h->err);
+    if (!api) return BF_E_CUDA;
+    HCK(h, cudaSetDevice(h->e0()->device));
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof id);
+    h->comms.assign(1, nullptr);
+    HNCCL(h, api, api->CommInitRank(&h->comms[0], world, id, rank));
+    h->rank = rank; h->world = world;
+    return BF_OK;
+}
+
+// host buffer of `bytes` bytes: on return every rank holds rank `root`'s content (staged through the device)
+int bf_bcast_host(bf_handle* h, void* buf, int64_t bytes, int root) {
+    if (!h || bytes < 0 || (bytes > 0 && !buf)) return BF_E_INVALID;
+    if (h->world == 1 || bytes == 0) return BF_OK;
+    h->err.clear();
+    bf::NcclApi* api = bf::nccl_api(h->err);
+    if (!api) return BF_E_CUDA;
+    HCK(h, cudaSetDevice(h->e0()->device));
+    void* d = nullptr;
+    HCK(h, cudaMalloc(&d, (size_t)bytes));
+    if (h->rank == root) HCK(h, cudaMemcpy(d, buf, (size_t)bytes, cudaMemcpyHostToDevice));
+    ncclResult_t r = api->Broadcast(d, d, (size_t)bytes, ncclChar, root, h->comms[0], 0);
+    cudaError_t e = cudaStreamSynchronize(0);
+    if (r == ncclSuccess && e == cudaSuccess && h->rank != root) e = cudaMemcpy(buf, d, (size_t)bytes, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (r != ncclSuccess) { h->err = std::string("ncclBroadcast: ") + (api->GetErrorString ? api->GetErrorString(r) : "error"); return BF_E_CUDA; }
+    HCK(h, e);
+    return BF_OK;
+}
+
+// element-wise maximum over the ranks of n doubles, in place (also a barrier): device-timed results of a
+// sharded run are reported as the maximum over ranks
+int bf_allreduce_max(bf_handle* h, double* vals, int32_t n) {
+    if (!h || n < 0 || (n > 0 && !vals)) return BF_E_INVALID;
+    if (h->world == 1 || n == 0) return BF_OK;
+    h->err.clear();
+    bf::NcclApi* api = bf::nccl_api(h->err);
+    if (!api) return BF_E_CUDA;
+    HCK(h, cudaSetDevice(h->e0()->device));
+    double* d = nullptr;
+    HCK(h, cudaMalloc((void**)&d, (size_t)n * sizeof(double)));
+    HCK(h, cudaMemcpy(d, vals, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    ncclResult_t r = api->AllReduce(d, d, (size_t)n, ncclDouble, ncclMax, h->comms[0], 0);
+    cudaError_t e = cudaStreamSynchronize(0);
+    if (r == ncclSuccess && e == cudaSuccess) e = cudaMemcpy(vals, d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (r != ncclSuccess) { h->err = std::string("ncclAllReduce: ") + (api->GetErrorString ? api->GetErrorString(r) : "error"); return BF_E_CUDA; }
+    HCK(h, e);
+    return BF_OK;
+}
+
+// The grid goes host -> device once (first device of the handle / rank `root` of the process group), then ONE
+// ncclBroadcast replicates it GPU to GPU over NVLink; every device re-tiles its copy.
+static int set_grid_everywhere(bf_handle* h, const float* coeffs, int64_t nmodel, int32_t nfilt, int32_t layout, int root) {
+    h->err.clear();
+    const int nd = (int)h->eng.size();
+    if (nd == 1 && h->world == 1) return h->e0()->set_grid(coeffs, nmodel, nfilt, layout, false);
+    if (nmodel <= 0 || nfilt <= 0 || nfilt > BF_MAX_FILT) { h->err = "bf_set_grid: bad shape"; return BF_E_INVALID; }
+    bf::NcclApi* api = bf::nccl_api(h->err);
+    if (!api) return BF_E_CUDA;
+    const size_t nval = (size_t)nmodel * nfilt * 3;
+    const bool have_src = nd > 1 || h->rank == root;
+    if (have_src && !coeffs) { h->err = "bf_set_grid: null grid on the root"; return BF_E_INVALID; }
+    std::vector<float*> buf(nd, nullptr);
+    std::vector<cudaStream_t> st(nd, nullptr);
+    int rc = BF_OK;
+    auto cleanup = [&]() {
+        for (int d = 0; d < nd; d++) {
+            cudaSetDevice(h->eng[d]->device);
+            if (st[d]) cudaStreamDestroy(st[d]);
+            if (buf[d]) cudaFree(buf[d]);
+        }
+    };
+    for (int d = 0; d < nd && rc == BF_OK; d++) {
+        if (cudaSetDevice(h->eng[d]->device) != cudaSuccess || cudaMalloc((void**)&buf[d], nval * sizeof(float)) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&st[d], cudaStreamNonBlocking) != cudaSuccess) { h->err = "bf_set_grid: device allocation failed"; rc = BF_E_NOMEM; }
+    }
+    if (rc == BF_OK && have_src) {
+        cudaSetDevice(h->eng[0]->device);
+        if (cudaMemcpyAsync(buf[0], coeffs, nval * sizeof(float), cudaMemcpyHostToDevice, st[0]) != cudaSuccess) { h->err = "bf_set_grid: H2D copy failed"; rc = BF_E_CUDA; }
+    }
+    if (rc == BF_OK) {
+        ncclResult_t r = api->GroupStart();
+        for (int d = 0; d < nd && r == ncclSuccess; d++) {
+            cudaSetDevice(h->eng[d]->device);
+            r = api->Broadcast(buf[d], buf[d], nval, ncclFloat, nd > 1 ? 0 : root, h->comms[nd > 1 ? d : 0], st[d]);
+        }
+        ncclResult_t r2 = api->GroupEnd();
+        if (r == ncclSuccess) r = r2;
+        if (r != ncclSuccess) { h->err = std::string("ncclBroadcast: ") + (api->GetErrorString ? api->GetErrorString(r) : "error"); rc = BF_E_CUDA; }
+    }
+    for (int d = 0; d < nd && rc == BF_OK; d++) {
+        cudaSetDevice(h->eng[d]->device);
+        if (cudaStreamSynchronize(st[d]) != cudaSuccess) { h->err = "bf_set_grid: broadcast failed"; rc = BF_E_CUDA; break; }
+        rc = h->eng[d]->set_grid(buf[d], nmodel, nfilt, layout, true);
+    }
+    cleanup();
+    return rc;
+}
 
 int bf_set_grid(bf_handle* h, const float* coeffs, int64_t nmodel, int32_t nfilt, int32_t layout) {
     if (!h) return BF_E_INVALID;
-    return h->eng->set_grid(coeffs, nmodel, nfilt, layout, false);
+    if (h->world > 1) { h->err = "bf_set_grid: this handle belongs to a process group, use bf_set_grid_bcast"; return BF_E_INVALID; }
+    return set_grid_everywhere(h, coeffs, nmodel, nfilt, layout, 0);
+}
+
+int bf_set_grid_bcast(bf_handle* h, const float* coeffs, int64_t nmodel, int32_t nfilt, int32_t layout, int32_t root) {
+    if (!h) return BF_E_INVALID;
+    return set_grid_everywhere(h, coeffs, nmodel, nfilt, layout, root);
 }
 
 int bf_set_grid_device(bf_handle* h, const void* d_coeffs, int64_t nmodel, int32_t nfilt, int32_t layout) {
     if (!h) return BF_E_INVALID;
-    return h->eng->set_grid((const float*)d_coeffs, nmodel, nfilt, layout, true);
+    if (h->eng.size() != 1) { h->err = "bf_set_grid_device: single-device handles only"; return BF_E_INVALID; }
+    h->err.clear();
+    return h->e0()->set_grid((const float*)d_coeffs, nmodel, nfilt, layout, true);
 }
 
 int bf_set_labels(bf_handle* h, const double* labels, int32_t nlabel) {
     if (!h) return BF_E_INVALID;
-    return h->eng->set_labels(labels, nlabel);
+    h->err.clear();
+    for (auto* e : h->eng) { int rc = e->set_labels(labels, nlabel); if (rc) return rc; }
+    return BF_OK;
 }
 
 int bf_loglike_full(bf_handle* h, const double* flux, const double* err, const uint8_t* mask, double parallax,
                     double parallax_err, const bf_options* opt, double* lnl, double* chi2, double* scale,
                     double* av, double* rv, double* icov, uint8_t* mask_clean_out, int64_t* diag) {
     if (!h) return BF_E_INVALID;
-    return h->eng->loglike_full(flux, err, mask, parallax, parallax_err, opt, lnl, chi2, scale, av, rv, icov,
-                                mask_clean_out, diag);
+    h->err.clear();
+    int rc = h->e0()->loglike_full(flux, err, mask, parallax, parallax_err, opt, lnl, chi2, scale, av, rv, icov,
+                                   mask_clean_out, diag);
+    h->stats = h->e0()->stats;
+    return rc;
+}
+
+// statistics of a multi-device call: counts add up, device times are the slowest device's
+static void merge_stats(bf_handle* h) {
+    bf_stats t = h->eng[0]->stats;
+    for (size_t d = 1; d < h->eng.size(); d++) {
+        const bf_stats& s = h->eng[d]->stats;
+        t.ms_device = std::max(t.ms_device, s.ms_device); t.ms_magfit = std::max(t.ms_magfit, s.ms_magfit);
+        t.ms_flux = std::max(t.ms_flux, s.ms_flux); t.ms_select = std::max(t.ms_select, s.ms_select);
+        t.ms_post = std::max(t.ms_post, s.ms_post);
+        t.kernel_launches += s.kernel_launches; t.magfit_launches += s.magfit_launches;
+        t.magfit_star_passes += s.magfit_star_passes; t.resweeps += s.resweeps; t.candidates += s.candidates;
+        t.fallbacks += s.fallbacks; t.survivors += s.survivors; t.selected += s.selected;
+        t.h2d_bytes += s.h2d_bytes; t.d2h_bytes += s.d2h_bytes; t.selected2 += s.selected2; t.clipped += s.clipped;
+        t.fixups += s.fixups; t.flux_more_launches += s.flux_more_launches; t.regroups += s.regroups;
+        t.unconverged += s.unconverged;
+    }
+    h->stats = t;
 }
 
 int bf_sweep_batch(bf_handle* h, int64_t nstar, const double* flux, const double* err, const uint8_t* mask,
@@ -1802,8 +2126,74 @@ int bf_sweep_batch(bf_handle* h, int64_t nstar, const double* flux, const double
                    const double* ext_std, const bf_options* opt, int32_t record_rows, int32_t* ndim,
                    int32_t* n_iter, int64_t* n_surv, double* max_lnprob, int64_t* offsets, bf_records* out) {
     if (!h) return BF_E_INVALID;
-    return h->eng->sweep_batch(nstar, flux, err, mask, parallax, parallax_err, ext_mean, ext_std, opt,
-                               record_rows, ndim, n_iter, n_surv, max_lnprob, offsets, out);
+    h->err.clear();
+    const int nd = (int)h->eng.size();
+    if (nd == 1 || nstar < nd) {
+        int rc = h->e0()->sweep_batch(nstar, flux, err, mask, parallax, parallax_err, ext_mean, ext_std, opt,
+                                      record_rows, ndim, n_iter, n_surv, max_lnprob, offsets, out);
+        h->stats = h->e0()->stats;
+        split_stars(nstar, 1, h->last_split);
+        return rc;
+    }
+    if (!flux || !err || !mask || !opt || !offsets || !out) { h->err = "bf_sweep_batch: null argument"; return BF_E_INVALID; }
+    // stars sharded contiguously over the devices, one host thread each, no collective
+    const int nfilt = h->e0()->nfilt_(), nlabel = h->e0()->nlabel_();
+    split_stars(nstar, nd, h->last_split);
+    const std::vector<int64_t>& b = h->last_split;
+    std::vector<int> rcs(nd, BF_OK);
+    std::vector<bf_records> recs(nd);
+    std::vector<std::vector<int64_t>> offs(nd);
+    std::vector<std::thread> th;
+    for (int d = 0; d < nd; d++) {
+        offs[d].assign((size_t)(b[d + 1] - b[d]) + 1, 0);
+        th.emplace_back([&, d]() {
+            const int64_t lo = b[d], n = b[d + 1] - b[d];
+            rcs[d] = h->eng[d]->sweep_batch(n, flux + lo * nfilt, err + lo * nfilt, mask + lo * nfilt,
+                                            parallax ? parallax + lo : nullptr, parallax_err ? parallax_err + lo : nullptr,
+                                            ext_mean ? ext_mean + lo * nlabel : nullptr, ext_std ? ext_std + lo * nlabel : nullptr,
+                                            opt, record_rows, ndim ? ndim + lo : nullptr, n_iter ? n_iter + 2 * lo : nullptr,
+                                            n_surv ? n_surv + lo : nullptr, max_lnprob ? max_lnprob + lo : nullptr,
+                                            offs[d].data(), &recs[d]);
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int d = 0; d < nd; d++) if (rcs[d]) return rcs[d];
+    merge_stats(h);
+    // gather: one CSR over the whole catalogue, records concatenated in star order in the handle's arena
+    int64_t total = 0;
+    offsets[0] = 0;
+    for (int d = 0; d < nd; d++) {
+        for (int64_t s = 0; s < b[d + 1] - b[d]; s++) offsets[b[d] + s + 1] = total + offs[d][s + 1];
+        total += recs[d].n;
+    }
+    const size_t es = (size_t)recs[0].elem_size;
+    if (total > h->rec_cap) {
+        if (h->rec_arena) cudaFreeHost(h->rec_arena);
+        h->rec_arena = nullptr; h->rec_cap = 0;
+        HCK(h, cudaHostAlloc((void**)&h->rec_arena, (size_t)total * (sizeof(int) + 11 * es) + 64, cudaHostAllocPortable));
+        h->rec_cap = total;
+    }
+    const int64_t cap = std::max<int64_t>(h->rec_cap, 1);
+    if (total > 0) {
+        th.clear();
+        int64_t at = 0;
+        for (int d = 0; d < nd; d++) {
+            const int64_t n = recs[d].n, dst = at;
+            at += n;
+            if (n == 0) continue;
+            th.emplace_back([&, d, n, dst]() {
+                std::memcpy(h->rec_arena + (size_t)11 * cap * es + (size_t)dst * sizeof(int), recs[d].model_idx, (size_t)n * sizeof(int));
+                for (int r = 0; r < record_rows; r++)
+                    std::memcpy(h->rec_arena + ((size_t)r * cap + (size_t)dst) * es,
+                                (const char*)recs[d].rows + (size_t)r * recs[d].stride * es, (size_t)n * es);
+            });
+        }
+        for (auto& t : th) t.join();
+    }
+    out->n = total; out->stride = cap; out->elem_size = (int32_t)es; out->nrows = record_rows;
+    out->model_idx = h->rec_arena ? (const int32_t*)(h->rec_arena + (size_t)11 * cap * es) : nullptr;
+    out->rows = h->rec_arena;
+    return BF_OK;
 }
 
 void bf_default_gal_params(bf_gal_params* g) {   /* defaults of gal_lnprior, brutus/pdf.py:476-486 */
@@ -1828,7 +2218,9 @@ void bf_default_post_options(bf_post_options* o) {
 
 int bf_set_model_priors(bf_handle* h, const double* lnprior, const double* feh, const double* loga) {
     if (!h) return BF_E_INVALID;
-    return h->eng->set_model_priors(lnprior, feh, loga);
+    h->err.clear();
+    for (auto* e : h->eng) { int rc = e->set_model_priors(lnprior, feh, loga); if (rc) return rc; }
+    return BF_OK;
 }
 
 int bf_fit_batch(bf_handle* h, int64_t nstar, const double* flux, const double* err, const uint8_t* mask,
@@ -1837,26 +2229,73 @@ int bf_fit_batch(bf_handle* h, int64_t nstar, const double* flux, const double* 
                  const bf_post_options* post, int32_t* ndim, int32_t* n_iter, int64_t* nsel,
                  double* levid, double* chi2min, bf_draws* out) {
     if (!h) return BF_E_INVALID;
-    return h->eng->fit_batch(nstar, flux, err, mask, parallax, parallax_err, coords, ext_mean, ext_std, opt, post,
-                             ndim, n_iter, nsel, levid, chi2min, out);
+    h->err.clear();
+    const int nd = (int)h->eng.size();
+    if (nd == 1 || nstar < nd) {
+        h->e0()->set_ext_arena(nullptr, 0, 0);
+        int rc = h->e0()->fit_batch(nstar, flux, err, mask, parallax, parallax_err, coords, ext_mean, ext_std, opt, post,
+                                    ndim, n_iter, nsel, levid, chi2min, out);
+        h->stats = h->e0()->stats;
+        split_stars(nstar, 1, h->last_split);
+        return rc;
+    }
+    if (!flux || !err || !mask || !opt || !post || !out || !levid || !chi2min) { h->err = "bf_fit_batch: null argument"; return BF_E_INVALID; }
+    if (post->ndraws < 1 || post->nmc_prior < 1) { h->err = "bf_fit_batch: nmc_prior and ndraws must be >= 1"; return BF_E_INVALID; }
+    if (post->u_override) { h->err = "bf_fit_batch: u_override is a single-device test hook"; return BF_E_INVALID; }
+    // one shared pinned arena: every device writes the draws of its stars straight into its slice
+    const size_t ntot = (size_t)nstar * post->ndraws;
+    if (ntot > h->draw_cap) {
+        if (h->draw_arena) cudaFreeHost(h->draw_arena);
+        h->draw_arena = nullptr; h->draw_cap = 0;
+        HCK(h, cudaHostAlloc((void**)&h->draw_arena, ntot * (17 * sizeof(double) + sizeof(int32_t)) + 64, cudaHostAllocPortable));
+        h->draw_cap = ntot;
+    }
+    const int nfilt = h->e0()->nfilt_(), nlabel = h->e0()->nlabel_();
+    split_stars(nstar, nd, h->last_split);
+    const std::vector<int64_t>& b = h->last_split;
+    std::vector<int> rcs(nd, BF_OK);
+    std::vector<bf_draws> dr(nd);
+    std::vector<std::thread> th;
+    for (int d = 0; d < nd; d++) {
+        th.emplace_back([&, d]() {
+            const int64_t lo = b[d], n = b[d + 1] - b[d];
+            bf_post_options po = *post;
+            po.star_base = post->star_base + lo;   // the generator is keyed by the catalogue index: results do not depend on the sharding
+            h->eng[d]->set_ext_arena(h->draw_arena, ntot, (size_t)lo);
+            rcs[d] = h->eng[d]->fit_batch(n, flux + lo * nfilt, err + lo * nfilt, mask + lo * nfilt,
+                                          parallax ? parallax + lo : nullptr, parallax_err ? parallax_err + lo : nullptr,
+                                          coords ? coords + 2 * lo : nullptr,
+                                          ext_mean ? ext_mean + lo * nlabel : nullptr, ext_std ? ext_std + lo * nlabel : nullptr,
+                                          opt, &po, ndim ? ndim + lo : nullptr, n_iter ? n_iter + 2 * lo : nullptr,
+                                          nsel ? nsel + lo : nullptr, levid + lo, chi2min + lo, &dr[d]);
+            h->eng[d]->set_ext_arena(nullptr, 0, 0);
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int d = 0; d < nd; d++) if (rcs[d]) return rcs[d];
+    merge_stats(h);
+    *out = dr[0];   // every engine reports the same arena pointers
+    return BF_OK;
 }
 
 int bf_get_seds(bf_handle* h, int64_t n, const int32_t* idx, const double* av, const double* rv, int32_t return_flux,
                 double* seds, double* rvecs, double* drvecs) {
     if (!h) return BF_E_INVALID;
-    return h->eng->get_seds(n, idx, av, rv, return_flux, seds, rvecs, drvecs);
+    h->err.clear();
+    return h->e0()->get_seds(n, idx, av, rv, return_flux, seds, rvecs, drvecs);
 }
 
 int bf_flush_l2(bf_handle* h) {
     if (!h) return BF_E_INVALID;
-    return h->eng->flush_l2();
+    for (auto* e : h->eng) { int rc = e->flush_l2(); if (rc) return rc; }
+    return BF_OK;
 }
 
-const char* bf_get_trace(bf_handle* h) { return h ? h->eng->get_trace() : ""; }
+const char* bf_get_trace(bf_handle* h) { return h ? h->e0()->get_trace() : ""; }
 
 int bf_get_stats(const bf_handle* h, bf_stats* out) {
     if (!h || !out) return BF_E_INVALID;
-    *out = h->eng->stats;
+    *out = h->stats;
     return BF_OK;
 }
 

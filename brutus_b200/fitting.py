@@ -5,7 +5,7 @@ and :class:`BruteForce` (:1110) with ``fit`` / ``_fit``.  All O(Nmodel) arithmet
 ``libbrutus_b200.so``; this module only validates arguments, raises the reference's
 ``ValueError``s, and post-processes the (small) selected subsets.  No CPU fallback exists.
 """
-import weakref
+import os
 
 import numpy as np
 
@@ -16,22 +16,31 @@ __all__ = ["loglike", "get_handle", "release_handles"]
 _handles = {}
 
 
-def get_handle(mag_coeffs, precision="f32", device=0):
-    """Return a sweep handle with ``mag_coeffs`` staged in HBM, uploading only when the array
-    object changes (the reference re-reads the host array on every call, brutus/fitting.py:714)."""
-    key = (precision, int(device))
+def _fingerprint(a):
+    """Cheap content fingerprint of a grid: identity, layout, and a strided sample of its bytes (at most ~64k
+    values), so that an in-place edit of the same array object is noticed and the grid re-staged."""
+    a = np.asarray(a)
+    flat = a.reshape(-1) if a.flags.c_contiguous or a.flags.f_contiguous else np.ascontiguousarray(a).reshape(-1)
+    step = max(1, flat.size // 65536)
+    sample = np.ascontiguousarray(flat[::step])
+    return (a.__array_interface__["data"][0], a.shape, a.strides, a.dtype.str, hash(sample.tobytes()),
+            float(sample.astype(np.float64).sum()))
+
+
+def get_handle(mag_coeffs, precision="f32", device=0, restage=False):
+    """Return a sweep handle with ``mag_coeffs`` staged in HBM.  The reference re-reads the host array on every call
+    (brutus/fitting.py:714); here the upload is skipped while a content fingerprint of the array (address, layout
+    and a strided checksum) is unchanged.  An edit confined to entries the checksum does not sample can go
+    unnoticed: pass ``restage=True`` (or call :func:`release_handles`) after modifying a grid in place."""
+    key = (precision, tuple(device) if isinstance(device, (list, tuple)) else int(device))
     ent = _handles.get(key)
     if ent is None:
-        ent = {"h": _lib.Handle(device, precision), "ref": None, "shape": None}
+        ent = {"h": _lib.Handle(device, precision), "fp": None}
         _handles[key] = ent
-    ref = ent["ref"]() if ent["ref"] is not None else None
-    if ref is not mag_coeffs or ent["shape"] != mag_coeffs.shape:
+    fp = _fingerprint(mag_coeffs)
+    if restage or ent["fp"] != fp:
         ent["h"].set_grid(mag_coeffs)
-        try:
-            ent["ref"] = weakref.ref(mag_coeffs)
-        except TypeError:
-            ent["ref"] = None
-        ent["shape"] = mag_coeffs.shape
+        ent["fp"] = fp
     return ent["h"]
 
 
@@ -52,12 +61,11 @@ def loglike(data, data_err, data_mask, mag_coeffs,
     return tuple ``(lnl, Ndim, chi2[, scale, av, rv, icov_sar])`` (float64 arrays of length
     Nmodel), same in-place clean-up of ``data_mask`` (:709) and the same ``ValueError`` (:691-693).
 
-    ``av_init``/``rv_init`` other than the defaults (the prior means, :700-703) are not supported
-    by the kernels.  ``precision`` selects float32 (throughput) or float64 (verification) math.
+    ``init_thresh=None`` keeps every model in the flux-space refinement (:769-775).  ``av_init``/``rv_init`` other
+    than the defaults (the prior means, :700-703) are not supported by the kernels.  ``precision`` selects float32
+    (throughput) or float64 (verification) math.
     """
-    if init_thresh is None:
-        raise NotImplementedError("init_thresh=None (no cull) is not supported")
-    if init_thresh > ltol_subthresh:
+    if init_thresh is not None and init_thresh > ltol_subthresh:
         raise ValueError("The initial threshold must be smaller than or equal "
                          "to the final threshold applied to be useful!")
     if av_init is not None or rv_init is not None:
@@ -65,7 +73,7 @@ def loglike(data, data_err, data_mask, mag_coeffs,
     h = get_handle(mag_coeffs, precision=precision, device=device)
     opts = _lib.make_options(avlim=avlim, av_gauss=av_gauss, rvlim=rvlim, rv_gauss=rv_gauss,
                              dim_prior=dim_prior, ltol=ltol, ltol_subthresh=ltol_subthresh,
-                             init_thresh=init_thresh)
+                             init_thresh=0. if init_thresh is None else init_thresh)
     par = np.nan if parallax is None or parallax_err is None else float(parallax)
     perr = np.nan if parallax is None or parallax_err is None else float(parallax_err)
     lnl, chi2, sc, av, rv, icov, mclean, diag = h.loglike_full(
@@ -97,36 +105,8 @@ __all__ += ["lnpost_selected", "BruteForce", "imf_lnprior", "parallax_lnprior",
             "scale_parallax_lnprior"]
 
 
-def imf_lnprior(mgrid, alpha_low=1.3, alpha_high=2.3, mass_break=0.5):
-    """Kroupa-like broken power-law IMF prior over initial mass (brutus/pdf.py:38-108, single
-    stars)."""
-    mgrid = np.asarray(mgrid, dtype=float)
-    out = np.full_like(mgrid, -np.inf)
-    lo = (mgrid > 0.08) & (mgrid <= mass_break)
-    hi = mgrid > mass_break
-    out[lo] = -alpha_low * np.log(mgrid[lo])
-    out[hi] = -alpha_high * np.log(mgrid[hi]) + (alpha_high - alpha_low) * np.log(mass_break)
-    n_lo = mass_break ** (1. - alpha_low) / (alpha_high - 1.)
-    n_hi = (0.08 ** (1. - alpha_low) - mass_break ** (1. - alpha_low)) / (alpha_low - 1.)
-    return out - np.log(n_lo + n_hi)
-
-
-def parallax_lnprior(parallaxes, p_meas, p_err):
-    """Gaussian parallax likelihood, flat if there is no measurement (brutus/pdf.py:144-175)."""
-    if np.isfinite(p_meas) and np.isfinite(p_err):
-        return -0.5 * ((parallaxes - p_meas) ** 2 / p_err ** 2 + np.log(2. * np.pi * p_err ** 2))
-    return np.zeros_like(parallaxes)
-
-
-def scale_parallax_lnprior(scales, scale_errs, p_meas, p_err, snr_lim=4.):
-    """Parallax prior mapped to scale = parallax**2 (brutus/pdf.py:178-260)."""
-    if np.isfinite(p_meas) and np.isfinite(p_err) and p_meas / p_err > snr_lim:
-        pm = max(0., p_meas)
-        s_mean = pm ** 2 + p_err ** 2
-        s_var = 2 * p_err ** 4 + 4 * pm ** 2 * p_err ** 2
-        vtot = s_var + scale_errs ** 2
-        return -0.5 * ((scales - s_mean) ** 2 / vtot + np.log(2. * np.pi * vtot))
-    return np.zeros_like(scales)
+from .pdf import (imf_lnprior, ps1_MrLF_lnprior, parallax_lnprior, scale_parallax_lnprior,  # noqa: E402,F401
+                  gal_lnprior, dust_lnprior)
 
 
 def _inv3(mats):
@@ -159,21 +139,32 @@ def _unpack_icov(icov6):
     return out
 
 
+def _cdf_select(lnp, cdf_thresh):
+    """The reference's CDF thresholding (brutus/fitting.py:992-997, :1017-1022): models in ascending order of
+    probability, kept while the cumulative probability stays <= 1 - cdf_thresh.  Returned in that order, as the
+    reference does (the order feeds the random-number stream)."""
+    idx_sort = np.argsort(lnp)
+    prob = np.exp(lnp - logsumexp(lnp))
+    cdf = np.cumsum(prob[idx_sort])
+    return idx_sort[cdf <= (1. - cdf_thresh)]
+
+
 def lnpost_selected(sel, lnlike, scales, avs, rvs, icovs_sar, parallax=None, parallax_err=None,
-                    coord=None, Nmc_prior=100, lnprior=None, wt_thresh=1e-3, lngalprior=None,
+                    coord=None, Nmc_prior=100, lnprior=None, wt_thresh=1e-3, cdf_thresh=2e-3, lngalprior=None,
                     lndustprior=None, dustfile=None, dlabels=None, avlim=(0., 20.), rvlim=(1., 8.),
                     mem_lim=8000., rstate=None, apply_av_prior=True):
     """The part of the reference's ``lnpost`` (brutus/fitting.py:999-1107) that follows the first
     selection, which ``bf_sweep_batch`` already performed on the GPU (:976-991).  Inputs are the
-    compacted records of the first selection ``sel`` (model indices, ascending).  Returns the
-    reference's tuple ``(sel, cov_sar, lnp, dist_mc, a_mc, r_mc, lnp_mc)``."""
+    compacted records of the first selection ``sel`` (model indices, ascending).  With ``wt_thresh=None`` (CDF
+    thresholding, :992-997) the device ships every model and the first selection is taken here as well.
+    Returns ``(sel, keep, cov_sar, lnp, dist_mc, a_mc, r_mc, lnp_mc)``: the reference's tuple plus ``keep``, the
+    positions of the final selection within the input records."""
     if rstate is None:
         rstate = np.random
     if lngalprior is None:
-        raise NotImplementedError("the default Galactic prior (brutus/pdf.py:476-749, astropy) is outside "
-                                  "this build's scope; pass `lngalprior`")
+        lngalprior = gal_lnprior
     if lndustprior is None and apply_av_prior:
-        raise NotImplementedError("the default 3-D dust prior needs the Bayestar map; pass `lndustprior`")
+        lndustprior = dust_lnprior
     if coord is None:
         coord = np.zeros(2)
     if lnprior is None:
@@ -186,15 +177,25 @@ def lnpost_selected(sel, lnlike, scales, avs, rvs, icovs_sar, parallax=None, par
     avs = np.asarray(avs, dtype=np.float64)
     rvs = np.asarray(rvs, dtype=np.float64)
     first = np.arange(len(sel))
-    # MLE-based prior evaluation and second threshold (:1000-1016)
+    if wt_thresh is None:   # first selection by CDF over lnprob = lnlike + rough parallax prior (:976-997)
+        lnprob = lnlike
+        if have_par:
+            ds2 = np.asarray(icovs_sar)[:, 0, 0]
+            lnprob = lnlike + scale_parallax_lnprior(scales, 1. / np.sqrt(np.abs(ds2)), parallax, parallax_err)
+        lnprob = np.where(np.isfinite(lnprob), lnprob, -1e300)
+        first = _cdf_select(lnprob, cdf_thresh)
+    # MLE-based prior evaluation and second threshold (:1000-1022)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        lnp = lnlike + lnprior_sel
-        dist = 1. / np.sqrt(scales)
-        lnp = lnp + lngalprior(dist, coord, labels=None if dlabels is None else dlabels[sel])
+        lnp = lnlike[first] + lnprior_sel[first]
+        dist = 1. / np.sqrt(scales[first])
+        lnp = lnp + lngalprior(dist, coord, labels=None if dlabels is None else dlabels[np.asarray(sel)[first]])
         if apply_av_prior:
-            lnp = lnp + lndustprior(dist, coord, avs, dustfile=dustfile)
-    keep = first[lnp > np.log(wt_thresh) + np.max(lnp)]
+            lnp = lnp + lndustprior(dist, coord, avs[first], dustfile=dustfile)
+    if wt_thresh is not None:
+        keep = first[lnp > np.log(wt_thresh) + np.max(lnp)]
+    else:
+        keep = first[_cdf_select(lnp, cdf_thresh)]
     lnp = lnlike[keep] + lnprior_sel[keep]
     if len(keep) > nsel_max:  # :1029-1036
         order = np.argsort(lnp)[::-1][:nsel_max]
@@ -269,6 +270,8 @@ class BruteForce(object):
     to ``<save_file>.npz`` with the same dataset names otherwise."""
 
     def __init__(self, models, models_labels, labels_mask, precision="f32", device=0):
+        """``device``: a CUDA ordinal, or a sequence of ordinals to shard every batch of stars over several GPUs of
+        this process (grid replicated by one NCCL broadcast inside the library)."""
         self.NMODEL, self.NDIM, self.NCOEF = models.shape
         self.models = models
         self.models_labels = models_labels
@@ -313,14 +316,11 @@ class BruteForce(object):
         data_err = np.array(data_err, dtype=np.float64)
         data_mask = np.array(data_mask, dtype=bool)
         ndata, nfilt = data.shape
-        if logl_initthresh > ltol_subthresh:
+        if logl_initthresh is not None and logl_initthresh > ltol_subthresh:
             raise ValueError("The initial threshold must be smaller than or equal to the "
                              "convergence threshold in order to be useful!")
         if wt_thresh is None and cdf_thresh is None:
             wt_thresh = -np.inf
-        if wt_thresh is None:
-            raise NotImplementedError("CDF-based thresholding (wt_thresh=None) is not supported; "
-                                      "the GPU selection uses wt_thresh (brutus/fitting.py:988-991)")
         if rstate is None:
             rstate = np.random
         if parallax is not None and parallax_err is None:
@@ -331,9 +331,8 @@ class BruteForce(object):
             names = self.models_labels.dtype.names or ()
             if "mini" in names:
                 lnprior = imf_lnprior(self.models_labels["mini"])
-            else:
-                raise NotImplementedError("default prior without a 'mini' label needs the PS1 luminosity "
-                                          "function table (brutus/pdf.py:111-141); pass `lnprior`")
+            else:   # PS1 r-band luminosity function (brutus/fitting.py:1339-1341)
+                lnprior = ps1_MrLF_lnprior(self.models_labels["Mr"])
         lnprior = np.array(lnprior, dtype=np.float64)
         names = self.models_labels.dtype.names or ()
         if apply_agewt and "agewt" in names:
@@ -392,11 +391,9 @@ class BruteForce(object):
         parallax = np.asarray(parallax, dtype=np.float64)
         parallax_err = np.asarray(parallax_err, dtype=np.float64)
         dlabels = self.models_labels if apply_dlabels else None
-        device_posterior = lngalprior is None
-        if device_posterior and lndustprior is not None:
-            raise NotImplementedError("a user `lndustprior` needs a user `lngalprior` too (host posterior path)")
-        if device_posterior and Nmc_prior < 1:
-            raise NotImplementedError("Nmc_prior = 0 is only supported on the host posterior path")
+        # the device posterior covers the reference's defaults; anything it does not implement (a user prior
+        # callable, CDF thresholding, Nmc_prior = 0) takes the host path with the same priors
+        device_posterior = lngalprior is None and lndustprior is None and wt_thresh is not None and Nmc_prior >= 1
         ext_keys = []
         if lnprior_ext is not None:   # validated before any device work, like every other argument error
             ext_keys = list(lnprior_ext.keys())
@@ -411,13 +408,22 @@ class BruteForce(object):
             h.set_labels(np.zeros((0, self.NMODEL)))
         opts = _lib.make_options(avlim=avlim, av_gauss=av_gauss, rvlim=rvlim, rv_gauss=rv_gauss,
                                  dim_prior=logl_dim_prior, ltol=ltol, ltol_subthresh=ltol_subthresh,
-                                 init_thresh=logl_initthresh, wt_thresh=wt_thresh)
+                                 init_thresh=0. if logl_initthresh is None else logl_initthresh,
+                                 wt_thresh=0. if wt_thresh is None else wt_thresh)   # 0: every model is shipped
         if device_posterior:
             names = (dlabels.dtype.names or ()) if dlabels is not None else ()
             h.set_model_priors(lnprior=lnprior if np.ndim(lnprior) else np.full(self.NMODEL, float(lnprior)),
                                feh=dlabels["feh"] if "feh" in names else None,
                                loga=dlabels["loga"] if "loga" in names else None)
-            seed = int(rstate.randint(0, 2 ** 31 - 1)) if hasattr(rstate, "randint") else 0
+            # the device draws from a counter-based generator keyed by (seed, catalogue index, model, draw): one
+            # seed is taken from the caller's generator, whose stream is otherwise untouched on this path
+            # (distributional, not draw-for-draw, equivalence with the reference)
+            if hasattr(rstate, "randint"):          # numpy.random / RandomState
+                seed = int(rstate.randint(0, 2 ** 31 - 1))
+            elif hasattr(rstate, "integers"):       # numpy.random.Generator
+                seed = int(rstate.integers(0, 2 ** 63 - 1))
+            else:
+                raise TypeError("`rstate` must be a numpy RandomState or Generator, got %r" % type(rstate))
         for b0 in range(0, ndata, batch):
             b1 = min(ndata, b0 + batch)
             em = es = None
@@ -456,7 +462,8 @@ class BruteForce(object):
                 sel2, keep, cov_sar, lnprob, dists, reds, dreds, logwts = lnpost_selected(
                     sel, res["lnl"][lo:hi], scales, avs, rvs, _unpack_icov(res["icov6"][:, lo:hi]),
                     parallax=parallax[i], parallax_err=parallax_err[i], coord=data_coords[i],
-                    Nmc_prior=Nmc_prior, lnprior=lnprior, wt_thresh=wt_thresh, lngalprior=lngalprior,
+                    Nmc_prior=Nmc_prior, lnprior=lnprior, wt_thresh=wt_thresh, cdf_thresh=cdf_thresh,
+                    lngalprior=lngalprior,
                     lndustprior=lndustprior, dustfile=dustfile, dlabels=dlabels, avlim=avlim,
                     rvlim=rvlim, mem_lim=mem_lim, rstate=rstate, apply_av_prior=apply_av_prior)
                 # parallax enters chi2 and Ndim (:2025-2030)
@@ -503,20 +510,12 @@ class BruteForce(object):
             data_coords=data_coords, ltol_subthresh=ltol_subthresh, logl_initthresh=logl_initthresh,
             mag_max=mag_max, merr_max=merr_max, rstate=rstate)
         ndata = data.shape[0]
-        out = {"model_idx": np.full((ndata, Ndraws), -99, dtype="int32"),
-               "ml_scale": np.ones((ndata, Ndraws), dtype="float32"),
-               "ml_av": np.zeros((ndata, Ndraws), dtype="float32"),
-               "ml_rv": np.zeros((ndata, Ndraws), dtype="float32"),
-               "ml_cov_sar": np.zeros((ndata, Ndraws, 3, 3), dtype="float32"),
-               "obj_log_post": np.zeros((ndata, Ndraws), dtype="float32"),
-               "obj_log_evid": np.zeros(ndata, dtype="float32"),
-               "obj_chi2min": np.zeros(ndata, dtype="float32"),
-               "obj_Nbands": np.zeros(ndata, dtype="int16")}
-        if save_dar_draws:
-            for k in ("samps_dist", "samps_red", "samps_dred", "samps_logp"):
-                out[k] = np.ones((ndata, Ndraws), dtype="float32")
+        # the output file is created BEFORE any fitting (exclusively, like the reference's "w-", :1632): an existing
+        # file or an unwritable path fails now, not after the catalogue has been fitted
+        store = _ResultStore(save_file, data_labels, ndata, Ndraws, save_dar_draws, running_io)
+        out = store.arrays
         t0 = time.time()
-        device_posterior = lngalprior is None
+        device_posterior = (lngalprior is None and lndustprior is None and wt_thresh is not None and Nmc_prior >= 1)
         gen = self._fit(data, data_err, data_mask, parallax=parallax, parallax_err=parallax_err,
                         avlim=avlim, rvlim=rvlim, av_gauss=av_gauss,
                         rv_gauss=rv_gauss, Nmc_prior=Nmc_prior, lnprior=lnprior, lnprior_ext=lnprior_ext,
@@ -526,44 +525,119 @@ class BruteForce(object):
                         return_distreds=save_dar_draws, ltol_subthresh=ltol_subthresh,
                         logl_dim_prior=logl_dim_prior, logl_initthresh=logl_initthresh, ltol=ltol,
                         mem_lim=mem_lim, _device_arrays=device_posterior)
-        if device_posterior:   # the device returns (Nbatch, Ndraws) arrays: assign them wholesale
-            for b0, b1, r in gen:
-                out["model_idx"][b0:b1], out["ml_scale"][b0:b1] = r["sidxs"], r["scales"]
-                out["ml_av"][b0:b1], out["ml_rv"][b0:b1], out["ml_cov_sar"][b0:b1] = r["avs"], r["rvs"], r["cov_sar"]
-                out["obj_Nbands"][b0:b1], out["obj_log_post"][b0:b1] = r["ndim"], r["lnprob"]
-                out["obj_log_evid"][b0:b1], out["obj_chi2min"][b0:b1] = r["levid"], r["chi2min"]
-                if save_dar_draws:
-                    out["samps_dist"][b0:b1], out["samps_red"][b0:b1] = r["dists"], r["reds"]
-                    out["samps_dred"][b0:b1], out["samps_logp"][b0:b1] = r["dreds"], r["logwts"]
-                if verbose:
-                    sys.stderr.write("\rFitted objects {:d}/{:d} (mean time: {:2.6f} s/obj)    ".format(
-                        b1, ndata, (time.time() - t0) / b1))
-                    sys.stderr.flush()
-            gen = ()
-        for i, r in enumerate(gen):
-            out["model_idx"][i], out["ml_scale"][i], out["ml_av"][i], out["ml_rv"][i] = r[0], r[1], r[2], r[3]
-            out["ml_cov_sar"][i], out["obj_Nbands"][i], out["obj_log_post"][i] = r[4], r[5], r[6]
-            out["obj_log_evid"][i], out["obj_chi2min"][i] = r[7], r[8]
-            if save_dar_draws:
-                out["samps_dist"][i], out["samps_red"][i] = r[9], r[10]
-                out["samps_dred"][i], out["samps_logp"][i] = r[11], r[12]
+        try:
+            if device_posterior:   # the device returns (Nbatch, Ndraws) arrays: rows land batch by batch
+                for b0, b1, r in gen:
+                    rows = {"model_idx": r["sidxs"], "ml_scale": r["scales"], "ml_av": r["avs"], "ml_rv": r["rvs"],
+                            "ml_cov_sar": r["cov_sar"], "obj_Nbands": r["ndim"], "obj_log_post": r["lnprob"],
+                            "obj_log_evid": r["levid"], "obj_chi2min": r["chi2min"]}
+                    if save_dar_draws:
+                        rows.update(samps_dist=r["dists"], samps_red=r["reds"], samps_dred=r["dreds"],
+                                    samps_logp=r["logwts"])
+                    store.write(b0, b1, rows)
+                    if verbose:
+                        sys.stderr.write("\rFitted objects {:d}/{:d} (mean time: {:2.6f} s/obj)    ".format(
+                            b1, ndata, (time.time() - t0) / b1))
+                        sys.stderr.flush()
+            else:
+                names = ("model_idx", "ml_scale", "ml_av", "ml_rv", "ml_cov_sar", "obj_Nbands", "obj_log_post",
+                         "obj_log_evid", "obj_chi2min", "samps_dist", "samps_red", "samps_dred", "samps_logp")
+                for i, r in enumerate(gen):
+                    store.write(i, i + 1, {k: np.asarray(v)[None] for k, v in zip(names, r)})
+                    if verbose:
+                        t_avg = (time.time() - t0) / (i + 1)
+                        sys.stderr.write("\rFitting object {:d}/{:d} [chi2/n: {:2.1f}/{:d}] (mean time: {:2.3f} s/obj, "
+                                         "est. remaining: {:10.3f} s)    ".format(i + 1, ndata, r[8], r[5], t_avg,
+                                                                                  t_avg * (ndata - i - 1)))
+                        sys.stderr.flush()
             if verbose:
-                t_avg = (time.time() - t0) / (i + 1)
-                sys.stderr.write("\rFitting object {:d}/{:d} [chi2/n: {:2.1f}/{:d}] (mean time: {:2.3f} s/obj, "
-                                 "est. remaining: {:10.3f} s)    ".format(i + 1, ndata, r[8], r[5], t_avg,
-                                                                          t_avg * (ndata - i - 1)))
-                sys.stderr.flush()
-        if verbose:
-            sys.stderr.write("\n")
+                sys.stderr.write("\n")
+        finally:
+            store.close()
+        return out
+
+
+class _ResultStore(object):
+    """Output file of ``fit`` with the reference's dataset names and dtypes (brutus/fitting.py:1632-1662).
+
+    ``<save_file>.h5`` through h5py when it is importable, opened ``"w-"`` like the reference.  Without h5py (this
+    image) the same datasets go to ``<save_file>.npz``; with ``running_io`` the rows are first written, batch by
+    batch, into memory-mapped ``.npy`` files under ``<save_file>.partial/`` and flushed, so that a crash keeps what
+    was fitted so far (the reference's reason for ``running_io``, :1594-1601), and the directory is folded into the
+    ``.npz`` when the fit completes.  Either way an existing output makes the constructor raise before any fitting."""
+
+    def __init__(self, save_file, data_labels, ndata, ndraws, save_dar_draws, running_io):
+        spec = {"model_idx": ((ndata, ndraws), "int32", -99), "ml_scale": ((ndata, ndraws), "float32", 1.),
+                "ml_av": ((ndata, ndraws), "float32", 0.), "ml_rv": ((ndata, ndraws), "float32", 0.),
+                "ml_cov_sar": ((ndata, ndraws, 3, 3), "float32", 0.),
+                "obj_log_post": ((ndata, ndraws), "float32", 0.), "obj_log_evid": ((ndata,), "float32", 0.),
+                "obj_chi2min": ((ndata,), "float32", 0.), "obj_Nbands": ((ndata,), "int16", 0)}
+        if save_dar_draws:
+            for k in ("samps_dist", "samps_red", "samps_dred", "samps_logp"):
+                spec[k] = ((ndata, ndraws), "float32", 1.)
+        self.running_io = bool(running_io)
+        self.labels = np.asarray(data_labels)
+        self.h5 = None
+        self.partial = None
         try:
             import h5py
+            if not isinstance(getattr(h5py, "__file__", None), str):   # an inert stand-in module, not the real thing
+                h5py = None
         except ImportError:
             h5py = None
         if h5py is not None:
-            with h5py.File("{0}.h5".format(save_file), "w-") as f:
-                f.create_dataset("labels", data=data_labels)
-                for k, v in out.items():
-                    f.create_dataset(k, data=v)
+            self.h5 = h5py.File("{0}.h5".format(save_file), "w-")
+            self.h5.create_dataset("labels", data=self.labels)
+            self.arrays = {k: np.full(sh, fill, dtype=dt) for k, (sh, dt, fill) in spec.items()}
+            if self.running_io:
+                for k, a in self.arrays.items():
+                    self.h5.create_dataset(k, data=a)
+            return
+        self.target = "{0}.npz".format(save_file)
+        if os.path.exists(self.target):
+            raise FileExistsError("Unable to create file (file exists): %r" % self.target)
+        with open(self.target, "xb"):      # claims the name; fails on an unwritable path
+            pass
+        if self.running_io:
+            self.partial = "{0}.partial".format(save_file)
+            os.makedirs(self.partial, exist_ok=False)
+            np.save(os.path.join(self.partial, "labels.npy"), self.labels)
+            self.arrays = {}
+            for k, (sh, dt, fill) in spec.items():
+                m = np.lib.format.open_memmap(os.path.join(self.partial, k + ".npy"), mode="w+", dtype=dt, shape=sh)
+                m[...] = fill
+                self.arrays[k] = m
         else:
-            np.savez("{0}.npz".format(save_file), labels=np.asarray(data_labels), **out)
-        return out
+            self.arrays = {k: np.full(sh, fill, dtype=dt) for k, (sh, dt, fill) in spec.items()}
+
+    def write(self, b0, b1, rows):
+        for k, v in rows.items():
+            if k not in self.arrays:
+                continue
+            self.arrays[k][b0:b1] = v
+            if self.h5 is not None and self.running_io:
+                self.h5[k][b0:b1] = self.arrays[k][b0:b1]
+        if self.h5 is not None and self.running_io:
+            self.h5.flush()
+        elif self.partial is not None:
+            for m in self.arrays.values():
+                m.flush()
+
+    def close(self):
+        if self.h5 is not None:
+            if not self.running_io:
+                for k, a in self.arrays.items():
+                    self.h5.create_dataset(k, data=a)
+            self.h5.close()
+            self.h5 = None
+            return
+        if getattr(self, "target", None) is None:
+            return
+        np.savez(self.target, labels=self.labels, **{k: np.asarray(v) for k, v in self.arrays.items()})
+        if self.partial is not None:
+            for k in list(self.arrays):                                        # detach from the memmaps (in place:
+                self.arrays[k] = np.array(self.arrays[k])                       # fit() returns this dictionary)
+            import shutil
+            shutil.rmtree(self.partial, ignore_errors=True)
+            self.partial = None
+        self.target = None

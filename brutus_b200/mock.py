@@ -7,13 +7,16 @@ format: float32 ``(Nmodel, Nfilt, 3)`` holding ``(mag0 @ 1 kpc, R0, dR/dRv)`` pe
 """
 import numpy as np
 
-__all__ = ["make_grid", "make_stars", "CONFIGS"]
+__all__ = ["make_grid", "make_grid_lattice", "make_stars", "load_ngc2682", "CONFIGS"]
 
 # BASELINE.json configs (index -> workload shape)
 CONFIGS = {
     1: dict(nmodel=10_000, nfilt=5, nstar=1, avlim=(0., 20.), av_max=2.0, dropout=0.0),
     2: dict(nmodel=1_000_000, nfilt=8, nstar=1_000, avlim=(0., 20.), av_max=2.0, dropout=0.0),
     3: dict(nmodel=3_000_000, nfilt=12, nstar=100_000, avlim=(0., 6.), av_max=6.0, dropout=0.1),
+    # NGC 2682 demo catalogue against a Bayestar-shaped (Mr, [Fe/H]) lattice: 568 x 72 = 40 896 models, PS grizy +
+    # 2MASS JHKs (demos/Overview 1 cell 39, brutus/filters.py:9-10); 3.9 MB grid: L2-resident, launch/latency-bound
+    4: dict(nmodel=40_896, nfilt=8, nstar=1_585, avlim=(0., 20.), av_max=2.0, dropout=0.0, lattice=(568, 72)),
     5: dict(nmodel=3_000_000, nfilt=8, nstar=1_000_000, avlim=(0., 20.), av_max=2.0, dropout=0.0),
 }
 
@@ -65,6 +68,51 @@ def make_grid_locus(nmodel, nfilt, seed=1000):
     labels["Mr"] = grid[:, min(1, nfilt - 1), 0]
     labels["loga"] = np.clip(10.0 - 2.5 * np.log10(mini) + 0.3 * (u2 - 0.5), 6.5, 10.13)   # <= 13.5 Gyr
     return grid, labels
+
+
+def make_grid_lattice(n_mr=568, n_feh=72, nfilt=8, dist_mod=10.):
+    """Bayestar-shaped mock grid (BASELINE.json configs[3]): a regular (Mr, [Fe/H]) lattice, Mr fastest -- the real
+    ``grid_bayestar_v5.h5`` has 40 896 models on such a lattice and cannot be fetched offline.  A main sequence
+    below Mr = 3.5 and a giant branch above it; blackbody colours + blanketing as in :func:`make_grid_locus`;
+    magnitudes at 1 kpc (``dist_mod`` = 10, brutus/seds.py:720), so that scale = parallax^2 holds for real
+    parallaxes.  Labels 'Mr', 'feh' only: no 'mini', so the default prior is the PS1 luminosity function
+    (brutus/fitting.py:1335-1341)."""
+    lam = _WAVE[:nfilt]
+    mr = np.repeat(np.linspace(-1., 18., n_mr)[None, :], n_feh, axis=0).ravel()
+    feh = np.repeat(np.linspace(-2.5, 0.5, n_feh)[:, None], n_mr, axis=1).ravel()
+    nmodel = mr.size
+    mini = np.clip(10. ** ((4.81 - mr) / 8.75), 0.08, 10.)
+    teff = np.clip(5772. * mini ** 0.57, 2800., 15000.)
+    giant = mr < 3.5
+    teff = np.where(giant, 5200. - 1500. * (3.5 - mr) / 4.5, teff) * 10. ** (-0.02 * feh)
+    hck = 14387.77
+    r0 = (0.55 / lam) ** 1.6
+    dr = 0.06 * (1. - (0.55 / lam) ** 0.8)
+    t = teff[:, None]
+    bb = -2.5 * np.log10(lam[None, :] ** -5 / np.expm1(hck / (lam[None, :] * t)))
+    bbr = -2.5 * np.log10(lam[1] ** -5 / np.expm1(hck / (lam[1] * t)))
+    blanket = -0.12 * feh[:, None] * (0.55 / lam[None, :]) ** 2 * (lam[None, :] < 0.7)
+    grid = np.empty((nmodel, nfilt, 3), dtype=np.float32)
+    grid[:, :, 0] = mr[:, None] + (bb - bbr) + (blanket - blanket[:, 1:2]) + dist_mod   # band 1 (PS r) carries Mr
+    grid[:, :, 1] = (r0 - 3.3 * dr)[None, :]
+    grid[:, :, 2] = dr[None, :]
+    labels = np.zeros(nmodel, dtype=[("Mr", "f8"), ("feh", "f8")])
+    labels["Mr"], labels["feh"] = mr, feh
+    return grid, labels
+
+
+def load_ngc2682(path=None):
+    """The NGC 2682 (M67) demo catalogue of the reference (demos/NGC_2682.fits, 1 585 objects) restricted to the 8
+    bands a Bayestar-type grid covers, as assembled by tests/gen_golden.py::gen_ngc2682 (SURVEY.md Appendix E) and
+    kept in tests/golden/ngc2682.npz.  Returns the ``make_stars`` dictionary for the objects with >= 4 usable bands
+    (``BruteForce`` refuses the others, brutus/fitting.py:1413-1420) plus ``index`` into the catalogue."""
+    import os
+    if path is None:
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "ngc2682.npz")
+    d = np.load(path)
+    ok = np.where(d["mask"].sum(axis=1) >= 4)[0]
+    return dict(flux=d["phot"][ok], err=d["err"][ok], mask=d["mask"][ok], parallax=d["parallax"][ok],
+                parallax_err=d["parallax_err"][ok], coords=d["coords"][ok], index=ok)
 
 
 def make_grid(nmodel, nfilt, seed=1000, kind="tilt"):

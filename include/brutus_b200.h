@@ -7,9 +7,11 @@
  * tree).  Plain pointers and sizes only; no exceptions cross the boundary; every call returns
  * an int status (0 = OK, negative = error, see BF_E_*), and bf_last_error() gives the message.
  *
- * Threading: a handle is bound to one CUDA device and one stream and is NOT re-entrant; distinct
- * handles are independent (one handle per GPU, one process per GPU under torchrun).
- * Inputs are never modified.  All host buffers are caller-owned.
+ * Threading: a handle is NOT re-entrant (calls on one handle must be serialised); distinct handles are
+ * independent.  A handle drives one CUDA device (bf_create) or several devices of this process
+ * (bf_create_multi: stars are sharded over them inside the batch calls, one host thread and stream per
+ * device); with one process per GPU (torchrun) each process holds a one-device handle that joins an NCCL
+ * process group (bf_nccl_init).  Inputs are never modified.  All host buffers are caller-owned.
  */
 #ifndef BRUTUS_B200_H
 #define BRUTUS_B200_H
@@ -57,7 +59,8 @@ typedef struct bf_options {
                                more than select_slack below the provisional one the star is redone with every
                                model as a candidate (bf_stats.fallbacks) */
     int32_t dim_prior;      /* default 1            */
-    int32_t max_iter;       /* cap on mag/flux loop iterations (reference: unbounded); 0 = 64 */
+    int32_t max_iter;       /* cap on mag / flux loop iterations (reference: unbounded); 0 = 64 mag, 1000 flux;
+                               stars stopped by it are counted in bf_stats.unconverged */
     int32_t apply_parallax_clip; /* 1: lnpost's rough parallax prior (fitting.py:976-980) is applied
                                     before thresholding; 0 mimics lnpost(parallax=None) */
     int32_t skip_d2h;       /* bf_sweep_batch: leave the records on the device (device-only timing) */
@@ -84,6 +87,7 @@ typedef struct bf_stats {
     int64_t fixups;         /* records refined as likely survivors that the exact cull rejected (redone)   */
     int64_t flux_more_launches; /* flux iterations beyond the ones the sweep runs itself (whole-pool passes) */
     int64_t regroups;       /* star groups split because their candidate records overflowed the pool      */
+    int64_t unconverged;    /* stars whose mag or flux loop was stopped by the iteration cap (max_iter)     */
 } bf_stats;
 
 void bf_default_options(bf_options* opt);
@@ -91,6 +95,32 @@ void bf_default_options(bf_options* opt);
 /* Lifetime.  device = CUDA ordinal; precision = BF_PRECISION_*. */
 int bf_create(int device, int precision, bf_handle** out);
 int bf_destroy(bf_handle* h);
+
+/* ---- several GPUs -----------------------------------------------------
+ * The reference fits objects strictly one after another (`for i in range(Ndata)`, brutus/fitting.py:1980) and no
+ * object depends on another, so the catalogue is sharded into contiguous star ranges, the grid is replicated,
+ * and nothing is exchanged in the hot loop.
+ *
+ * One process, n devices: bf_create_multi builds one engine per device and an NCCL communicator over them
+ * (ncclCommInitAll).  bf_set_grid then copies the grid to the first device once and replicates it with ONE
+ * ncclBroadcast; bf_sweep_batch / bf_fit_batch give device d the stars [d*N/n, (d+1)*N/n) and return one result
+ * in catalogue order.  The posterior's random numbers are keyed by the catalogue index of a star, so results do
+ * not depend on n.  bf_loglike_full and bf_get_seds run on the first device.  NCCL is loaded at run time
+ * (dlopen "libnccl.so.2"): single-device handles do not need it. */
+int bf_create_multi(const int* devices, int ndev, int precision, bf_handle** out);
+int bf_num_devices(const bf_handle* h);
+
+/* One process per GPU: rank 0 calls bf_nccl_unique_id and hands the 128 bytes to every rank (any channel: the
+ * Python side uses a TCP socket on MASTER_ADDR); every rank then calls bf_nccl_init on its one-device handle
+ * (ncclCommInitRank).  bf_set_grid_bcast: `coeffs` is read on rank `root` only (NULL elsewhere); one
+ * ncclBroadcast, every rank re-tiles its copy.  bf_bcast_host replicates a small host buffer (labels, priors)
+ * and bf_allreduce_max reduces n doubles in place (device timings are reported as the maximum over ranks; it is
+ * also a barrier).  With a single rank these are no-ops. */
+int bf_nccl_unique_id(void* out128);
+int bf_nccl_init(bf_handle* h, const void* id128, int rank, int world);
+int bf_set_grid_bcast(bf_handle* h, const float* coeffs, int64_t nmodel, int32_t nfilt, int32_t layout, int32_t root);
+int bf_bcast_host(bf_handle* h, void* buf, int64_t bytes, int root);
+int bf_allreduce_max(bf_handle* h, double* vals, int32_t n);
 const char* bf_last_error(const bf_handle* h); /* h may be NULL: last error of a failed bf_create */
 
 /* Stage the SED grid in HBM once.  Replaces BruteForce.__init__'s self.models (brutus/fitting.py:1139)

@@ -220,6 +220,29 @@ def gen_lnpost(fit):
     print("wrote lnpost")
 
 
+def gen_lnpost_cdf(fit):
+    """`lnpost` with CDF thresholding (wt_thresh=None, cdf_thresh=2e-3: brutus/fitting.py:992-997, :1017-1022) on the
+    first two stars of the lnpost case; the selection comes back in ascending order of probability."""
+    c = LNPOST_CASE
+    grid, labels, st, kw = build_case(c["name"])
+    gF = np.array(grid, order="F")
+    lnprior = -0.1 * (labels["Mr"] - 5.) ** 2
+    out = {}
+    for i in range(2):
+        m = st["mask"][i].copy()
+        res = fit.loglike(st["flux"][i], st["err"][i], m, gF, return_vals=True, parallax=st["parallax"][i],
+                          parallax_err=st["parallax_err"][i], **kw)
+        r = fit.lnpost(tuple(np.array(x) if np.ndim(x) else x for x in res), parallax=st["parallax"][i],
+                       parallax_err=st["parallax_err"][i], coord=np.zeros(2), Nmc_prior=4,
+                       lnprior=lnprior, wt_thresh=None, cdf_thresh=2e-3, lngalprior=toy_galprior, apply_av_prior=False,
+                       dlabels=labels, avlim=(0., 20.), rvlim=(1., 8.), mem_lim=20.,
+                       rstate=np.random.RandomState(c["rseed"]))
+        for key, val in zip(("sel", "cov_sar", "lnp", "dists", "reds", "dreds", "logwts"), r):
+            out["%s_%d" % (key, i)] = np.asarray(val)
+    np.savez_compressed(os.path.join(GOLD, "lnpost_cdf.npz"), **out)
+    print("wrote lnpost_cdf", [len(out["sel_%d" % i]) for i in range(2)])
+
+
 NGC2682_FITS = os.path.join(ref_import.REFERENCE_ROOT, "demos", "NGC_2682.fits")
 NGC2682_GRID = dict(nmodel=4_000, nfilt=8, seed=1050, kind="locus")
 
@@ -310,10 +333,29 @@ def gen_ngc2682(fit):
     print("wrote ngc2682: %d objects, bands-per-object %s, picks %s" % (n, np.bincount(nb).tolist(), picks))
 
 
+def gen_priors():
+    """Static priors of the fit path (brutus/pdf.py:38-260) on seeded inputs."""
+    ref_import.import_reference()
+    from brutus import pdf as rpdf
+    rs = np.random.RandomState(41)
+    out = dict(mini=10. ** rs.uniform(-1.3, 1., 400), mini2=10. ** rs.uniform(-1.3, 1., 400),
+               Mr=rs.uniform(-3., 24., 400), parallaxes=rs.uniform(0.01, 5., 300),
+               scales=10. ** rs.uniform(-3, 1, 300), scale_errs=10. ** rs.uniform(-4, 0, 300),
+               par_cases=np.array([[1.3, 0.1], [0.2, 0.1], [np.nan, 0.1], [-0.1, 0.3], [2.0, np.nan]]))
+    out["imf"] = rpdf.imf_lnprior(out["mini"])
+    out["imf_binary"] = rpdf.imf_lnprior(out["mini"], mgrid2=out["mini2"])
+    out["ps1"] = rpdf.ps1_MrLF_lnprior(out["Mr"])
+    for k, (pm, pe) in enumerate(out["par_cases"]):
+        out["parallax_lnprior_%d" % k] = rpdf.parallax_lnprior(out["parallaxes"], pm, pe)
+        out["scale_parallax_lnprior_%d" % k] = rpdf.scale_parallax_lnprior(out["scales"], out["scale_errs"], pm, pe)
+    np.savez_compressed(os.path.join(GOLD, "priors.npz"), **out)
+    print("wrote priors")
+
+
 if __name__ == "__main__":
     fit = ref_import.import_reference()
     os.makedirs(GOLD, exist_ok=True)
-    only = [a for a in sys.argv[1:] if a in LOGLIKE_CASES or a in ("galprior", "offsets", "ngc2682", "lnpost")]
+    only = [a for a in sys.argv[1:] if a in LOGLIKE_CASES or a in ("galprior", "offsets", "ngc2682", "lnpost", "lnpost_cdf", "priors", "fitopts")]
     gen_loglike(fit, only=only)
     if not only:
         gen_fit(fit)
@@ -325,3 +367,7 @@ if __name__ == "__main__":
         gen_lnpost(fit)
     if (not only or "ngc2682" in sys.argv[1:]) and os.path.exists(NGC2682_FITS):
         gen_ngc2682(fit)
+    if not only or "priors" in sys.argv[1:]:
+        gen_priors()
+    if not only or "lnpost_cdf" in sys.argv[1:]:
+        gen_lnpost_cdf(fit)

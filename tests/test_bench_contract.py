@@ -43,6 +43,9 @@ def test_b200_arm_line():
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
     r = d["roofline"]
     assert r["bound"] in ("hbm", "tensor") and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["limiter"] == "fp32-issue" and 0 < r["step_frac"] <= r["frac"] <= r["frac_per_pass"]
+    assert d["config"] == _run(["--impl", "reference", "--config", "1", "--steps", "1", "--warmup", "0"])["config"]
+    assert d["e2e_fit_api"]["value"] > 0 and d["cpu_baseline"]["one_core"]["cores"] == 1
     c = d["cpu_baseline"]
     assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])

@@ -93,3 +93,55 @@ def test_small_priors_match_the_live_reference():
         s, se = p ** 2, rs.uniform(0.01, 0.5, 200)
         assert np.allclose(fitting.scale_parallax_lnprior(s, se, pm, pe), rpdf.scale_parallax_lnprior(s, se, pm, pe),
                            rtol=1e-12)
+
+
+def test_result_store_is_exclusive_and_incremental(tmp_path):
+    """fit()'s writer (brutus/fitting.py:1632-1662, :1734-1748): refuses an existing output BEFORE fitting ("w-"), and
+    with running_io the rows fitted so far are on disk after every batch."""
+    target = str(tmp_path / "out")
+    st = fitting._ResultStore(target, np.arange(5), 5, 3, True, True)
+    assert set(st.arrays) >= {"model_idx", "ml_scale", "ml_av", "ml_rv", "ml_cov_sar", "obj_log_post", "obj_log_evid",
+                              "obj_chi2min", "obj_Nbands", "samps_dist", "samps_red", "samps_dred", "samps_logp"}
+    assert st.arrays["model_idx"].dtype == np.int32 and st.arrays["obj_Nbands"].dtype == np.int16
+    assert st.arrays["ml_cov_sar"].shape == (5, 3, 3, 3) and np.all(st.arrays["model_idx"] == -99)
+    with pytest.raises((FileExistsError, OSError)):
+        fitting._ResultStore(target, np.arange(5), 5, 3, True, True)
+    st.write(0, 2, {"model_idx": np.full((2, 3), 7), "obj_log_evid": np.array([1.5, 2.5])})
+    if st.h5 is None:    # no h5py in this image: the rows are already in the memory-mapped partial files
+        part = np.load(str(tmp_path / "out.partial" / "model_idx.npy"))
+        assert np.all(part[:2] == 7) and np.all(part[2:] == -99)
+    st.close()
+    if st.h5 is None and not (tmp_path / "out.h5").exists():
+        d = np.load(target + ".npz")
+        assert np.all(d["model_idx"][:2] == 7) and d["obj_log_evid"][1] == 2.5 and np.array_equal(d["labels"], np.arange(5))
+        assert not (tmp_path / "out.partial").exists()
+    with pytest.raises((FileExistsError, OSError)):        # still exclusive after completion
+        fitting._ResultStore(target, np.arange(5), 5, 3, True, False)
+
+
+def test_grid_fingerprint_sees_in_place_edits():
+    """The handle cache re-stages a grid that was modified in place (the reference re-reads the array every call)."""
+    grid, _ = mock.make_grid(20_000, 6, seed=9)
+    fp = fitting._fingerprint(grid)
+    assert fitting._fingerprint(grid) == fp
+    grid[:, :, 0] += 0.25
+    assert fitting._fingerprint(grid) != fp
+    gF = np.asfortranarray(grid)
+    assert fitting._fingerprint(gF) != fitting._fingerprint(grid)
+
+
+def test_cdf_select_is_the_reference_rule():
+    rs = np.random.RandomState(1)
+    lnp = rs.normal(0, 3, 500)
+    sel = fitting._cdf_select(lnp, 2e-3)
+    order = np.argsort(lnp)
+    p = np.exp(lnp - np.logaddexp.reduce(lnp))
+    assert np.array_equal(sel, order[np.cumsum(p[order]) <= 1 - 2e-3])
+
+
+def test_default_prior_is_ps1_lf_without_mini(bf_case):            # brutus/fitting.py:1335-1341
+    bf, st = bf_case
+    out = bf._setup(st["flux"], st["err"], st["mask"], parallax=st["parallax"], parallax_err=st["parallax_err"],
+                    lngalprior=gc.toy_galprior, data_coords=np.zeros((4, 2)), apply_agewt=False, apply_grad=False)
+    from brutus_b200 import pdf
+    assert np.allclose(out[5], pdf.ps1_MrLF_lnprior(bf.models_labels["Mr"]))

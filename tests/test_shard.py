@@ -1,7 +1,8 @@
-"""CPU-only, world size 2 over gloo: the multi-GPU host logic (brutus_b200/shard.py) -- contiguous star
-shards, one grid broadcast, no collective in the hot loop, catalogue-ordered gather.  The per-shard
-compute is stood in for by the CPU oracle (test infrastructure), packaged exactly like
-``Handle.sweep_batch`` packages its records; the GPU tests check the kernels themselves."""
+"""CPU-only, world size 2: the multi-GPU host logic (brutus_b200/shard.py) -- contiguous star shards, no
+collective in the hot loop, catalogue-ordered gather -- once over the product's own TCP communicator
+(SocketComm, no PyTorch) and once over torch.distributed/gloo through a small adapter (test helper).  The
+per-shard compute is stood in for by the CPU oracle (test infrastructure), packaged exactly like
+``Handle.sweep_batch`` packages its records; the GPU tests check the kernels and the in-library NCCL broadcast."""
 import os
 import socket
 import sys
@@ -68,29 +69,54 @@ class _FakeFitHandle(object):
                     ndim=np.asarray(mask).sum(axis=1).astype(np.int32))
 
 
-def _worker(rank, world, port, q):
+class GlooComm(object):
+    """Adapter: torch.distributed (gloo) behind the interface shard.py expects of a communicator."""
+
+    def __init__(self, dist):
+        self.dist = dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+
+    def gather_object(self, obj, dst=0):
+        out = [None] * self.world if self.rank == dst else None
+        self.dist.gather_object(obj, out, dst=dst)
+        return out
+
+    def bcast_object(self, obj, src=0):
+        box = [obj]
+        self.dist.broadcast_object_list(box, src=src)
+        return box[0]
+
+
+def _worker(rank, world, port, q, backend):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, HERE)
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    import torch.distributed as dist
     from brutus_b200 import mock
-    from brutus_b200.shard import broadcast_grid, gather_catalogue, shard_bounds
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from brutus_b200.shard import SocketComm, gather_catalogue, shard_bounds
+    dist = None
+    if backend == "gloo":
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        import torch.distributed as dist
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        comm = GlooComm(dist)
+    else:
+        assert "torch" not in sys.modules, "the product's communicator must not need PyTorch"
+        comm = SocketComm(rank, world, "127.0.0.1", port)
     try:
         nmodel, nfilt, ndata = 3000, 6, 9
-        grid = mock.make_grid(nmodel, nfilt, seed=1600)[0] if rank == 0 else None
-        grid = broadcast_grid(grid, (nmodel, nfilt, 3), dist=dist)            # the ONE collective
+        # rank 0 owns the grid; the others receive it (on GPUs this is the library's ncclBroadcast, here the
+        # communicator's object broadcast stands in for it)
+        grid = comm.bcast_object(mock.make_grid(nmodel, nfilt, seed=1600)[0] if rank == 0 else None)
         st = mock.make_stars(mock.make_grid(nmodel, nfilt, seed=1600)[0], ndata, seed=2600, dropout=0.1)
         lo, hi = shard_bounds(ndata, world, rank)
         local = oracle_sweep(grid, st, lo, hi)                                 # hot loop: no communication
-        merged = gather_catalogue(local, ndata, dist=dist)
+        merged = gather_catalogue(local, ndata, comm=comm)
         # the fit-level call: shards carry their first catalogue index (star_base), results gather in order
         from brutus_b200.shard import fit_shard, gather_draws
         flo, fhi, fres = fit_shard(_FakeFitHandle(), st["flux"], st["err"], st["mask"], st["parallax"],
                                    st["parallax_err"], coords=st["coords"], world=world, rank=rank, ndraws=4)
         assert (flo, fhi) == (lo, hi)
-        draws = gather_draws(fres, ndata, dist=dist)
+        draws = gather_draws(fres, ndata, comm=comm)
         if rank == 0:
             whole = oracle_sweep(grid, st, 0, ndata)
             ok = all(np.array_equal(merged[k], whole[k]) for k in whole)
@@ -104,17 +130,21 @@ def _worker(rank, world, port, q):
         q.put(("error", repr(e), rank))
         raise
     finally:
-        dist.destroy_process_group()
+        if dist is not None:
+            dist.destroy_process_group()
+        else:
+            comm.close()
 
 
-def test_two_rank_shards_equal_single_process():
-    import torch.multiprocessing as mp
+@pytest.mark.parametrize("backend", ["socket", "gloo"])
+def test_two_rank_shards_equal_single_process(backend):
+    import multiprocessing as mp
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, backend)) for r in range(2)]
     for p in procs:
         p.start()
     tag, ok, n = q.get(timeout=240)
@@ -122,3 +152,8 @@ def test_two_rank_shards_equal_single_process():
         p.join(timeout=120)
     assert tag == "ok" and ok and n > 0, (tag, ok, n)
     assert all(p.exitcode == 0 for p in procs)
+
+
+def test_product_shard_module_is_torch_free():
+    src = open(os.path.join(ROOT, "brutus_b200", "shard.py")).read()
+    assert "import torch" not in src
