@@ -239,6 +239,35 @@ template <typename T> __global__ void __launch_bounds__(kTile) k_cull(const Pass
     agg.flush(p.red, which, p.star_int + SI_NSURV, SI_COUNT);
 }
 
+// Survivors of the stars whose flux loop continues (SI_ACTIVE after the first k_flux_ctl): their pool indices, for
+// k_flux_more.  A light walk over the record tags; one atomic per warp.
+template <typename T> __global__ void __launch_bounds__(kTile) k_flux_list(const PassParams<T> p, int* list, int* nlist) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = (int64_t)blockIdx.x * kPassStep; base < p.n; base += (int64_t)gridDim.x * kPassStep) {
+        int tag[kPassU];
+#pragma unroll
+        for (int u = 0; u < kPassU; u++) {
+            const int64_t q = base + u * kTile + threadIdx.x;
+            tag[u] = q < p.n ? p.pool.sflag[q] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < kPassU; u++) {
+            bool act = false;
+            if (tag_flags(tag[u]) & kFlagSurv) {
+                const int* si = p.star_int + tag_slot(tag[u]) * SI_COUNT;
+                act = tag_epoch(tag[u]) == (si[SI_EPOCH] & 0xff) && si[SI_ACTIVE] != 0;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, act);
+            if (bal) {
+                int at = 0;
+                if (lane == 0) at = atomicAdd(nlist, __popc(bal));
+                at = __shfl_sync(0xffffffffu, at, 0);
+                if (act) list[at + __popc(bal & ((1u << lane) - 1u))] = (int)(base + u * kTile + threadIdx.x);
+            }
+        }
+    }
+}
+
 // Convergence control of the flux loops, on the device (one CTA): "lerr > ltol" (:781, :798-799) restated
 // on the two max-reductions of the `nit` iterations that just ran (first: the ones inside the sweep).
 // *any_out = 1 if some star of the group needs another iteration.
@@ -1093,17 +1122,14 @@ template <typename T> struct Engine : EngineBase {
             // extra iteration walks the whole pool and lists the active stars' survivors (in the memory of the
             // fix-up list, consumed by now); later ones visit that list only. ----
             int done_iter = nit_first;
-            bool have_list = false;
-            rp.n = n;
+            rp.n = n; rp.list = fixlist(); rp.nlist = d_ctr.p + CTR_NLIST;
+            if (any && done_iter < max_flux) {
+                { TRACE("k_flux_list"); k_flux_list<T><<<pass_ctas(n), kTile, 0, stream>>>(pp, fixlist(), d_ctr.p + CTR_NLIST); }
+                stats.kernel_launches++;
+            }
             while (any && done_iter < max_flux) {
                 int any_slot = CTR_ANY;
                 for (int r = 0; r < 3 && done_iter < max_flux; r++) {
-                    if (!have_list) {
-                        rp.list = nullptr; rp.nlist = nullptr; rp.list_out = fixlist(); rp.nlist_out = d_ctr.p + CTR_NLIST;
-                        have_list = true;
-                    } else {
-                        rp.list = fixlist(); rp.nlist = d_ctr.p + CTR_NLIST; rp.list_out = nullptr; rp.nlist_out = nullptr;
-                    }
                     { TRACE("k_flux_more"); kt->flux_more(rp, stream); }
                     any_slot = CTR_ANY + 1 + r;
                     { TRACE("k_flux_ctl"); k_flux_ctl<T><<<1, 1024, 0, stream>>>(d_star_int.p, d_red.p, d_list.p, ng, 0, 1, max_flux, o.ln_sub, d_ctr.p + any_slot); }

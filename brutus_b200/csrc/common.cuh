@@ -447,10 +447,8 @@ template <typename T> struct RecParams {
     DevOpts<T> o;
     PoolArrays<T> pool;
     int64_t n;                // records of the pool (k_flux_more) / entries of `list` (k_fixup)
-    const int* list;          // k_fixup: pool indices to redo; k_flux_more: the active survivors, or null = whole pool
-    const int* nlist;         // k_flux_more with a list: its length (device)
-    int* list_out;            // k_flux_more over the whole pool: receives the active survivors' indices
-    int* nlist_out;
+    const int* list;          // k_fixup: pool indices to redo; k_flux_more: the survivors of the active stars
+    const int* nlist;         // k_flux_more: length of the list (device)
     typename Enc<T>::U* red;
 };
 

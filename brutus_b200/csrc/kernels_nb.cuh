@@ -447,50 +447,72 @@ __device__ __forceinline__ void store_fit(const PoolArrays<T>& pl, int64_t q, T 
 // used to be four passes of latency-bound gathers over the candidates (re-fit, flux loop, scatter, records)
 // is arithmetic on data already on the SM.
 // =================================================================================================
-constexpr int kQueue = 64;   // ring-buffer entries per warp (a flush is triggered at 32; at most 31 + 32 queued)
+#ifndef BF_FLUSH_STARS
+#define BF_FLUSH_STARS 4
+#endif
+constexpr int kFlushStars = BF_FLUSH_STARS;        // the CTA meets (one barrier) every kFlushStars stars to drain its queue
+constexpr int kQueue = kTile * (kFlushStars + 1);  // ring-buffer entries per CTA: < kTile left over + kTile per star pushed
 
 template <typename T, int NB> struct SweepSmem {
     static constexpr int RS = tile_stride(NB);
     static constexpr size_t off_star = 0;
     static constexpr size_t off_tile = off_star + sizeof(T) * kStarChunk * kStarSmem;
     static constexpr size_t off_qav = off_tile + sizeof(float) * kTile * RS;
-    static constexpr size_t off_qrv = off_qav + sizeof(T) * (kTile / 32) * kQueue;
-    static constexpr size_t off_qlp = off_qrv + sizeof(T) * (kTile / 32) * kQueue;
-    static constexpr size_t off_qkey = off_qlp + sizeof(T) * (kTile / 32) * kQueue;
-    static constexpr size_t off_red = off_qkey + sizeof(uint32_t) * (kTile / 32) * kQueue;   // [warp][star][kSweepRed] of T
+    static constexpr size_t off_qrv = off_qav + sizeof(T) * kQueue;
+    static constexpr size_t off_qlp = off_qrv + sizeof(T) * kQueue;
+    static constexpr size_t off_qkey = off_qlp + sizeof(T) * kQueue;
+    static constexpr size_t off_red = off_qkey + sizeof(uint32_t) * kQueue;   // [warp][star][kSweepRed] of T
     static constexpr size_t off_snap = off_red + sizeof(T) * (kTile / 32) * kStarChunk * kSweepRed;
     static constexpr size_t off_int = off_snap + sizeof(T) * kStarChunk * 2;
-    static constexpr size_t bytes = off_int + sizeof(int) * kStarChunk * 3;
+    static constexpr size_t bytes = off_int + sizeof(int) * (kStarChunk * 3 + 4 + 2 * (kTile / 32));   // + queue tail, head, warp counts
 };
 
-// The dense phase for entries [head, head + n) of the warp's ring buffer (n <= 32; lanes >= n idle).
+// The dense phase for entries [head, head + n) of the CTA's ring buffer (n <= kTile): one entry per thread, the
+// records appended to the pool as one contiguous block.  All threads of the CTA must call it (it contains
+// barriers); warps whose 32 threads are all beyond n only keep the barriers company.
 template <typename T, int NB>
 __device__ __forceinline__ void dense_flush(const SweepParams<T>& p, const DevOpts<T>& o, const T* __restrict__ s_star,
-                                            const float* __restrict__ tile_w, const int* __restrict__ s_tag,
+                                            const float* __restrict__ s_tile, const int* __restrict__ s_tag,
                                             const T* __restrict__ q_av, const T* __restrict__ q_rv,
-                                            const T* __restrict__ q_lp, const uint32_t* __restrict__ q_key, int head,
-                                            int n, int64_t model0, int lane) {
+                                            const T* __restrict__ q_lp, const uint32_t* __restrict__ q_key, int* s_head,
+                                            int n, unsigned long long* s_base) {
     constexpr int NP = (NB + 1) / 2;
     constexpr int RS = tile_stride(NB);
-    const bool act = lane < n;
-    const int qi = (head + (act ? lane : 0)) & (kQueue - 1);   // idle lanes shadow entry 0 (results discarded)
+    const bool act = (int)threadIdx.x < n;
+    const int head = *s_head;                                   // ring position of the first entry (< kQueue)
+    int qi = head + (act ? (int)threadIdx.x : 0);               // idle threads shadow entry 0 (results discarded)
+    if (qi >= kQueue) qi -= kQueue;
     const uint32_t key = q_key[qi];
     T A = q_av[qi], rho = q_rv[qi];
     // the cull statistic exactly as the main loop computed it: the exact cull test (k_cull) compares it with the
     // per-star maximum of the same quantity, so survival never hinges on the rounding of a second evaluation
     const T lp = q_lp[qi];
-    __syncwarp();   // the ring entries may be overwritten once every lane has read its own
-    const int s = key & 31, ml = (key >> 5) & 31;
-    const bool fluxed = ((key >> 10) & 1u) != 0u && p.nit_first > 0;
+    if (threadIdx.x == 0) *s_base = atomicAdd(p.pool_count, (unsigned long long)n);   // one atomic per flush
+    __syncthreads();   // every thread has read the head and its entry (the ring slots may be overwritten); s_base is visible
+    if (threadIdx.x == 0) {
+        const int h = head + n;
+        *s_head = h >= kQueue ? h - kQueue : h;
+    }
+    if ((int)(threadIdx.x & ~31u) < n) {
+    const int64_t q = (int64_t)*s_base + threadIdx.x;
+    const int s = key & 31, ml = (key >> 5) & 255;
+    const bool fluxed = ((key >> 13) & 1u) != 0u && p.nit_first > 0;
+    const PoolArrays<T>& pl = p.pool;
+    const bool wr = act && q < p.pool_cap;
+    if (wr) {   // what is known already goes out first (coalesced stores of the warp's records): fewer live registers below
+        pl.model[q] = (int)(blockIdx.x * kTile + ml);
+        pl.sflag[q] = s_tag[s] | (fluxed ? kFlagFluxed << 24 : 0);
+        pl.lp[q] = lp;
+        pl.lnl[q] = A; pl.lnprob[q] = rho;   // the magnitude fit, kept for k_fixup until k_final overwrites it
+    }
     const T* __restrict__ srow = s_star + s * kStarSmem;
     ModelRegs<T, NB> m;
-    load_model_row<T, NB>(tile_w + ml * RS, o, m);
+    load_model_row<T, NB>(s_tile + ml * RS, o, m);
     const T c = srow[SR_SC + SC_MBAR] - m.bbar;
     P2<T> e[NP], r[NP];
     Mle<T, NB> r4;
     resid_at<T, NB>(m, o, srow, A, rho, e, r);
     mle_from_resid<T, NB>(e, c, srow, r4);
-    const T Am = A, rhom = rho;
     T eta = T(1), lold = Num<T>::kNegBig, lprev = Num<T>::kNegBig;   // stepsize 1, lnl_old = -1e300 (:778-779)
     if (fluxed) {
         for (int it = 0; it < p.nit_first; it++) {
@@ -502,20 +524,12 @@ __device__ __forceinline__ void dense_flush(const SweepParams<T>& p, const DevOp
     }
     T ic[5];
     icov_terms<T, NB>(m, o, srow, A, r, r4, ic);
-    // append: one atomic per flush, coalesced stores
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(p.pool_count, (unsigned long long)n);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    const int64_t q = (int64_t)base + lane;
-    if (act && q < p.pool_cap) {
-        const PoolArrays<T>& pl = p.pool;
-        pl.model[q] = (int)(model0 + ml);
-        pl.sflag[q] = s_tag[s] | (fluxed ? kFlagFluxed << 24 : 0);
+    if (wr) {
         store_fit<T>(pl, q, A, rho, r4.chi2, r4.s, r4.den * r4.E * r4.E, ic);
-        pl.lp[q] = lp;
         pl.eta[q] = eta; pl.lold[q] = lold; pl.lprev[q] = lprev;
-        pl.lnl[q] = Am; pl.lnprob[q] = rhom;   // the magnitude fit, kept for k_fixup until k_final overwrites it
     }
+    }
+    __syncthreads();   // s_base may be rewritten by the next flush; the new head is visible
 }
 
 // up to 8 bands: capped at 80 registers (3 CTAs = 24 warps per SM); left to itself ptxas takes more and the
@@ -533,7 +547,7 @@ __global__ void __launch_bounds__(kTile, (sweep_min_ctas<T, NB>())) k_sweep(cons
     extern __shared__ __align__(16) unsigned char smem[];
     T* s_star = reinterpret_cast<T*>(smem + SM::off_star);                 // [32][kStarSmem]
     float* s_tile = reinterpret_cast<float*>(smem + SM::off_tile);         // [256][RS]
-    T* s_qav = reinterpret_cast<T*>(smem + SM::off_qav);                   // [8][kQueue]
+    T* s_qav = reinterpret_cast<T*>(smem + SM::off_qav);                   // [kQueue]: the CTA's candidate queue
     T* s_qrv = reinterpret_cast<T*>(smem + SM::off_qrv);
     T* s_qlp = reinterpret_cast<T*>(smem + SM::off_qlp);
     uint32_t* s_qkey = reinterpret_cast<uint32_t*>(smem + SM::off_qkey);
@@ -542,6 +556,10 @@ __global__ void __launch_bounds__(kTile, (sweep_min_ctas<T, NB>())) k_sweep(cons
     int* s_slot = reinterpret_cast<int*>(smem + SM::off_int);              // [32]
     int* s_kspec = s_slot + kStarChunk;
     int* s_tag = s_kspec + kStarChunk;
+    int* s_qtot = s_tag + kStarChunk;                                      // entries pushed so far
+    int* s_head = s_qtot + 1;                                              // ring position of the oldest queued entry
+    unsigned long long* s_base = reinterpret_cast<unsigned long long*>(s_qtot + 2);   // pool position of the flush
+    int* s_wc = s_qtot + 4;                                                // [2][8]: candidates per warp since the last meeting
 
     const int first = blockIdx.y * kStarChunk;
     const int nst = min(kStarChunk, p.nlist - first);
@@ -549,6 +567,8 @@ __global__ void __launch_bounds__(kTile, (sweep_min_ctas<T, NB>())) k_sweep(cons
         int s = t / kStarStride, k = t - s * kStarStride;
         s_star[s * kStarSmem + k] = p.stars[(int64_t)p.list[first + s] * kStarStride + k];
     }
+    if (threadIdx.x == 0) { *s_qtot = 0; *s_head = 0; }
+    if (threadIdx.x < 2 * (kTile / 32)) s_wc[threadIdx.x] = 0;
     for (int t = threadIdx.x; t < nst; t += kTile) {
         int slot = p.list[first + t];
         s_slot[t] = slot;
@@ -576,16 +596,10 @@ __global__ void __launch_bounds__(kTile, (sweep_min_ctas<T, NB>())) k_sweep(cons
     ModelRegs<T, NB> m;
     load_model_row<T, NB>(tile_w + lane * RS, o, m);
     const int64_t word = i >> 5;
-    const int64_t model0 = i - lane;
     const T ninf = Num<T>::neg_inf();
     const T ln_init_c = o.ln_init - T(kCandMargin);
     T* w_red = s_red + wrp * kStarChunk * kSweepRed;               // lane s stores the warp's maxima for star s
-    T* q_av = s_qav + wrp * kQueue;
-    T* q_rv = s_qrv + wrp * kQueue;
-    T* q_lp = s_qlp + wrp * kQueue;
-    uint32_t* q_key = s_qkey + wrp * kQueue;
-    int qh = 0, qn = 0;                                             // ring buffer head / fill (warp-uniform)
-    const unsigned lt_mask = (1u << lane) - 1u;
+    int pend = 0;                                                   // queued entries not yet processed (CTA-uniform)
 
     for (int s = 0; s < nst; s++) {
         const T* __restrict__ srow = s_star + s * kStarSmem;
@@ -619,26 +633,50 @@ __global__ void __launch_bounds__(kTile, (sweep_min_ctas<T, NB>())) k_sweep(cons
         const bool cand = valid && (likely || lq > thr2);
         const unsigned bal = __ballot_sync(0xffffffffu, cand);
         if (lane == 0) p.cand[(int64_t)slot * p.nwords + word] = bal;
-        if (bal) {
-            if (cand) {
-                const int pos = (qh + qn + __popc(bal & lt_mask)) & (kQueue - 1);
-                q_av[pos] = A; q_rv[pos] = rho; q_lp[pos] = lp;
-                q_key[pos] = (uint32_t)s | (uint32_t)lane << 5 | (likely ? 1u << 10 : 0u);
+        const int par = (s / kFlushStars) & 1;                      // parity of the warp-count buffer in use
+        if (bal) {   // push the warp's candidates of this star into the CTA's queue: one shared-memory atomic per warp
+            int base = 0;
+            if (lane == 0) {   // inline PTX: the compiler would wrap a one-lane atomicAdd in its own warp aggregation
+                const int n = __popc(bal);
+                const uint32_t a_tot = (uint32_t)__cvta_generic_to_shared(s_qtot);
+                asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(base) : "r"(a_tot), "r"(n) : "memory");
+                if (base < kQueue && base + n >= kQueue)                      // the push that wraps the ring
+                    asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(a_tot), "r"(-kQueue) : "memory");
+                if (kFlushStars == 1) s_wc[par * (kTile / 32) + wrp] = n;
+                else asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(a_tot + 16u + 4u * (par * (kTile / 32) + wrp)), "r"(n) : "memory");
             }
-            qn += __popc(bal);
-            if (qn >= 32) {
-                __syncwarp();
-                dense_flush<T, NB>(p, o, s_star, tile_w, s_tag, q_av, q_rv, q_lp, q_key, qh, 32, model0, lane);
-                qh = (qh + 32) & (kQueue - 1);
-                qn -= 32;
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (cand) {
+                unsigned lt_mask;
+                asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
+                int pos = base + __popc(bal & lt_mask);
+                if (pos >= kQueue) pos -= kQueue;
+                s_qav[pos] = A; s_qrv[pos] = rho; s_qlp[pos] = lp;
+                s_qkey[pos] = (uint32_t)s | (uint32_t)threadIdx.x << 5 | (likely ? 1u << 13 : 0u);
+            }
+        } else if (kFlushStars == 1 && lane == 0) s_wc[par * (kTile / 32) + wrp] = 0;
+        // The CTA meets every kFlushStars stars: the warps' candidates of those stars are then adjacent in the queue
+        // (and later in the pool: runs of a star's records several times longer than a warp alone would give, which is
+        // what the pool passes and the ordered gather want), and every full kTile of queued entries is run through the
+        // dense phase by all 256 threads, one entry each.  The queue fill is derived from per-warp counts (double
+        // buffered), so every thread sees the same value whatever the faster warps push next.
+        if (((s + 1) & (kFlushStars - 1)) == 0 || s == nst - 1) {
+            __syncthreads();
+            const int4 c0 = *reinterpret_cast<const int4*>(s_wc + par * (kTile / 32));
+            const int4 c1 = *reinterpret_cast<const int4*>(s_wc + par * (kTile / 32) + 4);
+            pend += c0.x + c0.y + c0.z + c0.w + c1.x + c1.y + c1.z + c1.w;
+            // the other buffer was read by everybody before this barrier: clear this warp's slot for its next use
+            if (kFlushStars > 1 && lane == 0) s_wc[(par ^ 1) * (kTile / 32) + wrp] = 0;
+            if (pend >= kTile) {
+                do {
+                    dense_flush<T, NB>(p, o, s_star, s_tile, s_tag, s_qav, s_qrv, s_qlp, s_qkey, s_head, kTile, s_base);
+                    pend -= kTile;
+                } while (pend >= kTile);
                 load_model_row<T, NB>(tile_w + lane * RS, o, m);   // this thread's own model again
             }
         }
     }
-    if (qn > 0) {
-        __syncwarp();
-        dense_flush<T, NB>(p, o, s_star, tile_w, s_tag, q_av, q_rv, q_lp, q_key, qh, qn, model0, lane);
-    }
+    if (pend > 0) dense_flush<T, NB>(p, o, s_star, s_tile, s_tag, s_qav, s_qrv, s_qlp, s_qkey, s_head, pend, s_base);
     __syncthreads();
     // combine the warps' maxima and publish them; NaN maxima (every lane NaN) must not poison the
     // unsigned-encoded atomics
@@ -692,8 +730,7 @@ __global__ void __launch_bounds__(kTile) k_fixup(const RecParams<T> p) {
 // the iterations the sweep ran (SI_ACTIVE, decided on the device by k_flux_ctl), with the convergence
 // reductions of that iteration:
 //   "lerr <= ltol"  <=>  max{lnl_new_i : |lnl_new_i - lnl_old_i| > ltol} <= max lnl_new + ln(ltol_subthresh)
-// The first launch of a group walks every record of the pool and writes the indices of the active stars'
-// survivors to `list_out`; further iterations only visit that list (`list`, `nlist`).
+// It visits the list of those survivors that k_flux_list (api.cu) extracted from the pool.
 // =================================================================================================
 template <typename T, int NB>
 __global__ void __launch_bounds__(kTile) k_flux_more(const RecParams<T> p) {
@@ -703,64 +740,42 @@ __global__ void __launch_bounds__(kTile) k_flux_more(const RecParams<T> p) {
     agg.init();
     __syncthreads();
     const PoolArrays<T>& pl = p.pool;
-    const int64_t n = p.list ? (int64_t)*p.nlist : p.n;
-    int64_t lo, hi;
-    pass_range(n, lo, hi);
-    const int lane = threadIdx.x & 31;
-    for (int64_t base = lo; base < hi; base += kPassStep) {
-        int64_t q[kPassU];
-        int tag[kPassU];
-#pragma unroll
-        for (int u = 0; u < kPassU; u++) {
-            const int64_t t = base + u * kTile + threadIdx.x;
-            q[u] = t < hi ? (p.list ? (int64_t)p.list[t] : t) : -1;
+    const int64_t n = (int64_t)*p.nlist;
+    for (int64_t base = (int64_t)blockIdx.x * kTile; base < n; base += (int64_t)gridDim.x * kTile) {
+        const int64_t t = base + threadIdx.x;
+        int64_t q = -1;
+        int slot = -1;
+        bool act = false;
+        if (t < n) {
+            q = p.list[t];
+            const int tag = pl.sflag[q];
+            const int sl = tag_slot(tag);
+            if (p.star_int[sl * SI_COUNT + SI_ACTIVE] != 0) { act = true; slot = sl; }
         }
-#pragma unroll
-        for (int u = 0; u < kPassU; u++) tag[u] = q[u] >= 0 ? pl.sflag[q[u]] : 0;
-#pragma unroll
-        for (int u = 0; u < kPassU; u++) {
-            int slot = -1;
-            bool act = false;
-            if (q[u] >= 0 && (tag_flags(tag[u]) & kFlagSurv)) {
-                const int sl = tag_slot(tag[u]);
-                const int* si = p.star_int + sl * SI_COUNT;
-                if (tag_epoch(tag[u]) == (si[SI_EPOCH] & 0xff) && si[SI_ACTIVE] != 0) { act = true; slot = sl; }
-            }
-            if (p.list_out) {   // remember the active survivors: one atomic per warp
-                const unsigned bal = __ballot_sync(0xffffffffu, act);
-                if (bal) {
-                    int at = 0;
-                    if (lane == 0) at = atomicAdd(p.nlist_out, __popc(bal));
-                    at = __shfl_sync(0xffffffffu, at, 0);
-                    if (act) p.list_out[at + __popc(bal & ((1u << lane) - 1u))] = (int)q[u];
-                }
-            }
-            T v[2] = {Num<T>::neg_inf(), Num<T>::neg_inf()};
-            if (act) {
-                const int64_t qq = q[u];
-                const DevOpts<T> o = p.o;
-                const T* __restrict__ srow = p.stars + (int64_t)slot * kStarStride;
-                ModelRegs<T, NB> m;
-                load_model_row<T, NB>(p.rows + (int64_t)pl.model[qq] * row_stride(NB), o, m);
-                const T c = srow[SR_SC + SC_MBAR] - m.bbar;
-                T A = pl.av[qq], rho = pl.rv[qq], eta = pl.eta[qq], lold = pl.lold[qq];
-                P2<T> e[NP], r[NP];
-                Mle<T, NB> r4;
-                resid_at<T, NB>(m, o, srow, A, rho, e, r);
-                mle_from_resid<T, NB>(e, c, srow, r4);
-                const T lnew = flux_step<T, NB>(m, o, srow, c, eta, A, rho, e, r, r4);
-                v[0] = (lnew == lnew) ? lnew : Num<T>::neg_inf();
-                v[1] = (tabs(lnew - lold) > o.ltol) ? v[0] : Num<T>::neg_inf();
-                pl.lprev[qq] = lold;
-                if (lnew < lold) eta = eta / T(1.2);            // :802
-                pl.eta[qq] = eta;
-                pl.lold[qq] = lnew;                              // :803
-                T ic[5];
-                icov_terms<T, NB>(m, o, srow, A, r, r4, ic);
-                store_fit<T>(pl, qq, A, rho, r4.chi2, r4.s, r4.den * r4.E * r4.E, ic);
-            }
-            if (__any_sync(0xffffffffu, act)) agg.add(p.red, which, nullptr, 0, slot, act, v, false);
+        T v[2] = {Num<T>::neg_inf(), Num<T>::neg_inf()};
+        if (act) {
+            const DevOpts<T> o = p.o;
+            const T* __restrict__ srow = p.stars + (int64_t)slot * kStarStride;
+            ModelRegs<T, NB> m;
+            load_model_row<T, NB>(p.rows + (int64_t)pl.model[q] * row_stride(NB), o, m);
+            const T c = srow[SR_SC + SC_MBAR] - m.bbar;
+            T A = pl.av[q], rho = pl.rv[q], eta = pl.eta[q], lold = pl.lold[q];
+            P2<T> e[NP], r[NP];
+            Mle<T, NB> r4;
+            resid_at<T, NB>(m, o, srow, A, rho, e, r);
+            mle_from_resid<T, NB>(e, c, srow, r4);
+            const T lnew = flux_step<T, NB>(m, o, srow, c, eta, A, rho, e, r, r4);
+            v[0] = (lnew == lnew) ? lnew : Num<T>::neg_inf();
+            v[1] = (tabs(lnew - lold) > o.ltol) ? v[0] : Num<T>::neg_inf();
+            pl.lprev[q] = lold;
+            if (lnew < lold) eta = eta / T(1.2);            // :802
+            pl.eta[q] = eta;
+            pl.lold[q] = lnew;                              // :803
+            T ic[5];
+            icov_terms<T, NB>(m, o, srow, A, r, r4, ic);
+            store_fit<T>(pl, q, A, rho, r4.chi2, r4.s, r4.den * r4.E * r4.E, ic);
         }
+        if (__any_sync(0xffffffffu, act)) agg.add(p.red, which, nullptr, 0, slot, act, v, false);
     }
     agg.flush(p.red, which, nullptr, 0);
 }
@@ -791,7 +806,7 @@ template <typename T, int NB> void launch_fixup(const RecParams<T>& p, cudaStrea
 }
 template <typename T, int NB> void launch_flux_more(const RecParams<T>& p, cudaStream_t st) {
     if (p.n <= 0) return;
-    const int64_t ctas = (p.n + kPassStep - 1) / kPassStep;   // with a list: p.n is an upper bound, the kernel reads *nlist
+    const int64_t ctas = (p.n + kTile - 1) / kTile;   // p.n: upper bound of the list length, the kernel reads *nlist
     k_flux_more<T, NB><<<(unsigned)(ctas < kPassCtas ? ctas : kPassCtas), kTile, 0, st>>>(p);
 }
 

