@@ -22,6 +22,11 @@ namespace bf {
 // ---- Philox4x32 (Salmon et al. 2011) ------------------------------------------------------------------
 // R = 10 rounds is the standard generator (resampling uniforms); R = 7, the fewest rounds that pass
 // BigCrush in the paper, feeds the Monte Carlo normals, whose loop is bound by instruction issue.
+#ifndef BF_MC_POLY_ANGLES
+#define BF_MC_POLY_ANGLES 2
+#endif
+constexpr int kMcPolyAngles = BF_MC_POLY_ANGLES;   // Box-Muller angles (of 3 per block) evaluated by polynomial
+
 template <int R>
 __device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                            uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
@@ -74,18 +79,55 @@ BF_PAIR_FN(abs2, tabs)
 #undef BF_PAIR_FN
 constexpr double kLog2e = 1.4426950408889634, kLn2 = 0.6931471805599453;
 
-// three standard normals for (star, model, draw j): Box-Muller on one Philox block
+// sine and cosine of an angle uniform on the circle, from 16 random bits, WITHOUT the transcendental unit: the
+// low 14 bits place theta in [-pi/4, pi/4), the top 2 bits rotate by a multiple of pi/2 (swap + signs).  Both
+// series are evaluated together with packed FMAs (|error| < 4e-6).  The Monte Carlo loop is bound by the
+// transcendental unit, not by the FMA pipe.
+__device__ __forceinline__ void sincos_bits(uint32_t h, float& sn, float& cs) {
+    // [1, 2) from 14 mantissa bits, then theta = (pi/2) (f - 1.5)
+    const float f = __uint_as_float(0x3f800000u | ((h & 0x3fffu) << 9));
+    const float th = fmaf(f, 1.5707963267948966f, -2.356194490192345f);
+    const float t = th * th;
+    // sin(th) / th = 1 - t/6 + t^2/120 - t^3/5040 ;  cos(th) = 1 - t/2 + t^2/24 - t^3/720
+    const P2<float> tt = bc2(t);
+    P2<float> pq = fma2(tt, mk2(-1.98412698e-4f, -1.38888889e-3f), mk2(8.33333333e-3f, 4.16666667e-2f));
+    pq = fma2(pq, tt, mk2(-1.66666667e-1f, -0.5f));
+    pq = fma2(pq, tt, bc2(1.f));
+    const float s0 = lo2(pq) * th, c0 = hi2(pq);
+    const uint32_t q = h >> 14;                                   // 0..3: rotate by q pi/2
+    const bool sw = (q & 1u) != 0u;
+    const float s1 = sw ? c0 : s0, c1 = sw ? s0 : c0;             // q odd: (sin, cos) <- (cos, -sin)
+    sn = __uint_as_float(__float_as_uint(s1) ^ ((q >> 1) << 31));
+    cs = __uint_as_float(__float_as_uint(c1) ^ (((q ^ (q >> 1)) & 1u) << 31));
+}
+
+// six standard normals for draws (2k, 2k + 1) of (star, model): ONE Philox block.  Each 32-bit word feeds one
+// Box-Muller pair: its high half is the radius uniform, (h + 1/2) / 2^16 (the normals reach 4.7 sigma), its low
+// half the angle.  The fourth word is not used.  The generator, not the prior, was the largest single item of
+// the Monte Carlo loop when every draw had a block of its own.  Two of the three angles go through the packed
+// polynomial, one through MUFU.SIN/COS: that balances the transcendental unit against instruction issue.
 template <typename T>
-__device__ __forceinline__ void normals3(uint64_t seed, uint64_t star, uint32_t model, uint32_t j, T (&z)[3]) {
+__device__ __forceinline__ void normals6(uint64_t seed, uint64_t star, uint32_t model, uint32_t k, T (&za)[3], T (&zb)[3]) {
     uint32_t r[4];
-    philox4x32<7>(model, j, (uint32_t)star, (uint32_t)(star >> 32) ^ 0x4D435A31u, (uint32_t)seed,
+    philox4x32<7>(model, k, (uint32_t)star, (uint32_t)(star >> 32) ^ 0x4D435A31u, (uint32_t)seed,
                   (uint32_t)(seed >> 32), r);
-    const float r0 = psqrt(-2.f * __logf(u01(r[0]))), r1 = psqrt(-2.f * __logf(u01(r[2])));
-    float s0, c0, s1, c1;
-    __sincosf(6.2831853f * u01(r[1]), &s0, &c0);
-    __sincosf(6.2831853f * u01(r[3]), &s1, &c1);
-    z[0] = (T)(r0 * c0); z[1] = (T)(r0 * s0); z[2] = (T)(r1 * c1);
-    (void)s1;
+    float n[6];
+#pragma unroll
+    for (int w = 0; w < 3; w++) {
+        // [1, 2) from the mantissa bits, minus (1 - 2^-17): exact, no int->float conversion
+        const float u = __uint_as_float(0x3f800000u | ((r[w] >> 16) << 7)) - 0.99999237060546875f;
+        const float rad = psqrt(-1.3862943611198906f * plg2(u));          // sqrt(-2 ln u)
+        float sn, cs;
+        if (w < kMcPolyAngles) {
+            sincos_bits(r[w] & 0xffffu, sn, cs);
+        } else {
+            const float v = __uint_as_float(0x3f800000u | ((r[w] & 0xffffu) << 7)) - 1.f;
+            __sincosf(6.2831853f * v, &sn, &cs);
+        }
+        n[2 * w] = rad * cs; n[2 * w + 1] = rad * sn;
+    }
+    za[0] = (T)n[0]; za[1] = (T)n[1]; za[2] = (T)n[2];
+    zb[0] = (T)n[3]; zb[1] = (T)n[4]; zb[2] = (T)n[5];
 }
 
 // ---- the Galactic prior (brutus/pdf.py:476-749) --------------------------------------------------------
@@ -338,42 +380,21 @@ template <typename T> struct McCtx {
     ModelW<T> w;
     GalStar<T> gs;
     T par, pivar, lnorm_par;   // parallax prior (brutus/pdf.py:144-175); pivar = 0: none
+    T par_c2, par_k2;          // the same in log2 units: lg2 prior += par_c2 (p - par)^2 + par_k2
     uint32_t model;
     uint64_t star;
 };
 
-template <typename T, bool ZOV>
-__device__ __forceinline__ void mc_draw(const PostParams<T>& p, const McCtx<T>& c, int j, T& s, T& a, T& r, T& lp, bool& inb) {
-    T z[3];
-    if (ZOV) {
-        const double* zz = p.zov + (size_t)c.model * 3 * p.nmc + j;
-        z[0] = (T)zz[0]; z[1] = (T)zz[p.nmc]; z[2] = (T)zz[2 * p.nmc];
-    } else {
-        normals3<T>(p.seed, c.star, c.model, (uint32_t)j, z);
-    }
-    s = c.scale * (T(1) + c.L[0] * z[0]);
-    a = c.av + c.L[1] * z[0] + c.L[2] * z[1];
-    r = c.rv + c.L[3] * z[0] + c.L[4] * z[1] + c.L[5] * z[2];
-    inb = s >= T(1e-20) && a >= p.avmin && a <= p.avmax && r >= p.rvmin && r <= p.rvmax;   // (:1090-1092)
-    lp = Num<T>::kNegBig;
-    if (inb) {
-        const T dist = prsqrt(s), par = s * dist;
-        lp = gal_lnprior<T>(p.G, c.gs, c.w, s, dist);
-        if (c.pivar > T(0)) {
-            const T d = par - c.par;
-            lp += T(-0.5) * (d * d * c.pivar + c.lnorm_par);
-        }
-        if (lp != lp) lp = Num<T>::neg_inf();
-    }
-}
-
 // ---- two Monte Carlo draws at a time ---------------------------------------------------------------------
 // k_post_mc is bound by instruction issue (ncu: 184 instructions and 17 MUFU per draw, issue 78 %, XU 71 %), so
 // the floating-point work of draws (j, j+1) is done with packed FP32 (FFMA2 / FMUL2 / FADD2: one issue slot
-// for both draws); the transcendentals stay scalar.  Same formula as gal_lnprior above, evaluated in base 2.
+// for both draws); the transcendentals stay scalar.  Same formula as gal_lnprior above, evaluated in base 2 and returned in two
+// parts, prior = arg * 2^lg2h: the accumulation over draws needs 2^(lg2 prior - reference) = arg * 2^(lg2h - reference),
+// one exponential and no logarithm.
 // T = double runs the same code on plain pairs.
 template <typename T>
-__device__ __forceinline__ P2<T> gal_lnprior2(const GalDev<T>& G, const GalStar<T>& gs, const ModelW<T>& w, P2<T> s, P2<T> d) {
+__device__ __forceinline__ void gal_prior2(const GalDev<T>& G, const GalStar<T>& gs, const ModelW<T>& w, P2<T> s, P2<T> d,
+                                           P2<T>& lg2h, P2<T>& arg) {
     const P2<T> x = fma2(d, bc2(gs.ax), bc2(gs.x0)), y = mul2(d, bc2(gs.ay)), z = fma2(d, bc2(gs.az), bc2(gs.z0));
     const P2<T> R2 = fma2(x, x, mul2(y, y));
     const P2<T> dz = sub2(abs2(z), bc2(G.aZ_solar));
@@ -393,15 +414,22 @@ __device__ __forceinline__ P2<T> gal_lnprior2(const GalDev<T>& G, const GalStar<
     const P2<T> s0 = add2(add2(nt, nk), bc2(T(1)));
     const P2<T> s1 = fma2(nt, bc2(w.f[0]), fma2(nk, bc2(w.f[1]), bc2(w.f[2])));
     const P2<T> s2 = fma2(nt, bc2(w.g[0]), fma2(nk, bc2(w.g[1]), bc2(w.g[2])));
-    const P2<T> arg = mul2(mul2(s1, s2), rcp2(mul2(s0, s)));
-    return mul2(add2(lh, lg22(arg)), bc2(T(kLn2)));
+    arg = mul2(mul2(s1, s2), rcp2(mul2(s0, s)));
+    lg2h = lh;
 }
 
 // draws j and j + 1 of a selected model: (s, Av, Rv), in-bounds flags and log-priors (:1070-1095).  The second
 // lane is computed even when j + 1 == nmc (the caller ignores it).
 template <typename T> struct McPair {
-    P2<T> s, a, r, lp;
+    P2<T> s, a, r;
+    P2<T> lg2h, arg; // the prior at the two draws = arg * 2^lg2h (meaningless for a lane that is out of bounds)
     bool inb[2];
+    // the log-prior of lane k the way the reference holds it: -1e300 out of bounds (:1093), -inf for NaN (:1095 nan_to_num
+    // of exp) -- only the resampling kernel and the exact fallback of the accumulation need this form
+    __device__ T lnp(int k) const {
+        const T l = (k ? hi2(lg2h) + plg2(hi2(arg)) : lo2(lg2h) + plg2(lo2(arg))) * T(kLn2);
+        return !inb[k] ? Num<T>::kNegBig : (l != l ? Num<T>::neg_inf() : l);
+    }
 };
 
 template <typename T, bool ZOV>
@@ -413,8 +441,7 @@ __device__ __forceinline__ void mc_pair(const PostParams<T>& p, const McCtx<T>& 
 #pragma unroll
         for (int k = 0; k < 3; k++) { za[k] = (T)zz[k * p.nmc + j]; zb[k] = (T)zz[k * p.nmc + jb]; }
     } else {
-        normals3<T>(p.seed, c.star, c.model, (uint32_t)j, za);
-        normals3<T>(p.seed, c.star, c.model, (uint32_t)(j + 1), zb);
+        normals6<T>(p.seed, c.star, c.model, (uint32_t)(j >> 1), za, zb);
     }
     const P2<T> z0 = mk2(za[0], zb[0]), z1 = mk2(za[1], zb[1]), z2 = mk2(za[2], zb[2]);
     o.s = mul2(bc2(c.scale), fma2(bc2(c.L[0]), z0, bc2(T(1))));
@@ -427,15 +454,14 @@ __device__ __forceinline__ void mc_pair(const PostParams<T>& p, const McCtx<T>& 
     // out-of-bounds lanes may carry a negative scale: give them a harmless one, their result is discarded
     const P2<T> sc = mk2(o.inb[0] ? sv[0] : c.scale, o.inb[1] ? sv[1] : c.scale);
     const P2<T> dist = rsqrt2(sc), par = mul2(sc, dist);
-    P2<T> lp = p.G.use ? gal_lnprior2<T>(p.G, c.gs, c.w, sc, dist) : bc2(T(0));
+    P2<T> lp = bc2(T(0));
+    o.arg = bc2(T(1));
+    if (p.G.use) gal_prior2<T>(p.G, c.gs, c.w, sc, dist, lp, o.arg);
     if (c.pivar > T(0)) {
         const P2<T> d = sub2(par, bc2(c.par));
-        lp = fma2(mul2(d, d), bc2(T(-0.5) * c.pivar), add2(lp, bc2(T(-0.5) * c.lnorm_par)));
+        lp = fma2(mul2(d, d), bc2(c.par_c2), add2(lp, bc2(c.par_k2)));
     }
-    T l0 = lo2(lp), l1 = hi2(lp);
-    l0 = !o.inb[0] ? Num<T>::kNegBig : (l0 != l0 ? Num<T>::neg_inf() : l0);
-    l1 = !o.inb[1] ? Num<T>::kNegBig : (l1 != l1 ? Num<T>::neg_inf() : l1);
-    o.lp = mk2(l0, l1);
+    o.lg2h = lp;
 }
 
 template <typename T>
@@ -454,6 +480,8 @@ __device__ __forceinline__ void mc_setup(const PostParams<T>& p, int64_t t, int 
     c.par = srow[SR_SC + SC_PAR];
     c.pivar = srow[SR_SC + SC_PIVAR];
     c.lnorm_par = c.pivar > T(0) ? T(1.8378770664093453) - plog(c.pivar) : T(0);
+    c.par_c2 = T(-0.5 * kLog2e) * c.pivar;
+    c.par_k2 = T(-0.5 * kLog2e) * c.lnorm_par;
     c.model = (uint32_t)i;
     c.star = (uint64_t)(p.star_base + slot);
 }
@@ -483,22 +511,51 @@ template <typename T, bool ZOV> __global__ void __launch_bounds__(kTile, 4) k_po
         McCtx<T> c;
         Cov3 cv;
         mc_setup<T>(p, t, slot, c, cv);
-        Lse<T> acc;
+        // logsumexp over the draws against a FIXED reference, the prior at the MLE itself: one ex2 and one add per
+        // draw, no running maximum.  The prior moves by far less than the 2^+-126 range of float32 over draws a few
+        // sigma from the MLE; if the sum nevertheless leaves the range the model is redone the careful way.
+        T ref2;
+        {
+            const P2<T> s0 = bc2(c.scale), d0 = rsqrt2(s0);
+            P2<T> l0 = bc2(T(0)), a0 = bc2(T(1));
+            if (p.G.use) gal_prior2<T>(p.G, c.gs, c.w, s0, d0, l0, a0);
+            if (c.pivar > T(0)) {
+                const P2<T> d = sub2(mul2(s0, d0), bc2(c.par));
+                l0 = fma2(mul2(d, d), bc2(c.par_c2), add2(l0, bc2(c.par_k2)));
+            }
+            ref2 = lo2(l0) + plg2(lo2(a0));
+            if (!Num<T>::finite(ref2)) ref2 = T(0);
+        }
+        T sum0 = T(0), sum1 = T(0);
         int neff = 0;
         for (int j = 0; j < p.nmc; j += 2) {
             McPair<T> m;
             mc_pair<T, ZOV>(p, c, j, m);
-            acc.add(lo2(m.lp));
-            neff += m.inb[0] ? 1 : 0;
-            if (j + 1 < p.nmc) {
-                acc.add(hi2(m.lp));
-                neff += m.inb[1] ? 1 : 0;
+            const P2<T> e = mul2(m.arg, ex22(sub2(m.lg2h, bc2(ref2))));
+            const bool in1 = m.inb[1] && j + 1 < p.nmc;
+            // max(NaN, 0) = 0: a NaN prior counts as exp(-inf) like in the reference (:1095)
+            sum0 += m.inb[0] ? Num<T>::max(lo2(e), T(0)) : T(0);
+            sum1 += in1 ? Num<T>::max(hi2(e), T(0)) : T(0);
+            neff += (m.inb[0] ? 1 : 0) + (in1 ? 1 : 0);
+        }
+        const T sum = sum0 + sum1;
+        T lse;
+        if (sum > T(0) && Num<T>::finite(sum)) {
+            lse = (ref2 + plg2(sum)) * T(kLn2);
+        } else {   // every term underflowed (or none is finite): running-maximum accumulation, as the reference's logsumexp
+            Lse<T> acc;
+            for (int j = 0; j < p.nmc; j += 2) {
+                McPair<T> m;
+                mc_pair<T, ZOV>(p, c, j, m);
+                acc.add(m.lnp(0));
+                if (j + 1 < p.nmc) acc.add(m.lnp(1));
             }
+            lse = acc.value();
         }
         const int64_t q = p.ord[t];
         const int64_t i = p.pool.model[q];
         lnp = p.pool.lnl[q] + (p.lnprior ? p.lnprior[i] : T(0));             // lnlike + lnprior (:1024)
-        lnp = neff > 0 ? lnp + acc.value() - plog((T)neff) : Num<T>::kNegBig;  // (:1098-1100; Neff = 0 -> +inf -> -1e300)
+        lnp = neff > 0 ? lnp + lse - plog((T)neff) : Num<T>::kNegBig;  // (:1098-1100; Neff = 0 -> +inf -> -1e300)
         if (!Num<T>::finite(lnp) || lnp < Num<T>::kNegBig) lnp = Num<T>::kNegBig;   // (:1103-1105)
         p.lnp2[u] = lnp;
         // chi2 with the parallax term (:2025-2030), for chi2min
@@ -606,8 +663,8 @@ template <typename T, bool ZOV> __global__ void __launch_bounds__(kTile) k_post_
     for (int j = 0; j < p.nmc; j += 2) {   // the same paired evaluation as k_post_mc: identical log-priors
         McPair<T> m;
         mc_pair<T, ZOV>(p, c, j, m);
-        acc.add(lo2(m.lp));
-        if (j + 1 < p.nmc) acc.add(hi2(m.lp));
+        acc.add(m.lnp(0));
+        if (j + 1 < p.nmc) acc.add(m.lnp(1));
     }
     const T m = acc.m;
     const double W = (double)acc.s;
@@ -618,7 +675,7 @@ template <typename T, bool ZOV> __global__ void __launch_bounds__(kTile) k_post_
         McPair<T> mp;
         mc_pair<T, ZOV>(p, c, j0, mp);
         const T sv[2] = {lo2(mp.s), hi2(mp.s)}, av[2] = {lo2(mp.a), hi2(mp.a)}, rv[2] = {lo2(mp.r), hi2(mp.r)};
-        const T lv[2] = {lo2(mp.lp), hi2(mp.lp)};
+        const T lv[2] = {mp.lnp(0), mp.lnp(1)};
 #pragma unroll
         for (int k = 0; k < 2; k++) {
             const int j = j0 + k;

@@ -280,6 +280,8 @@ class BruteForce(object):
         self.precision = precision
         self.device = device
         self._handle = None
+        self._prior_cache = {}       # (apply_agewt, apply_grad) -> the default per-model prior (labels are fixed)
+        self._staged_priors = None   # what set_model_priors last put on the device
 
     # -- device handle, created on first use so that constructing the object needs no GPU --
     def _get_handle(self):
@@ -305,6 +307,7 @@ class BruteForce(object):
         if self._handle is not None:
             self._handle.close()
             self._handle = None
+        self._staged_priors = None
 
     def _setup(self, data, data_err, data_mask, data_labels=None, phot_offsets=None, parallax=None,
                parallax_err=None, av_gauss=None, lnprior=None, wt_thresh=1e-3, cdf_thresh=2e-3,
@@ -327,22 +330,29 @@ class BruteForce(object):
             raise ValueError("Must provide both `parallax` and `parallax_err`.")
         if phot_offsets is None:
             phot_offsets = np.ones(nfilt)
-        if lnprior is None:
+        # the static per-model prior depends on the model labels only: computed once per (flags), reused by every call
+        key = (bool(apply_agewt), bool(apply_grad)) if lnprior is None else None
+        if key is not None and key in self._prior_cache:
+            lnprior = self._prior_cache[key]
+        else:
             names = self.models_labels.dtype.names or ()
-            if "mini" in names:
-                lnprior = imf_lnprior(self.models_labels["mini"])
-            else:   # PS1 r-band luminosity function (brutus/fitting.py:1339-1341)
-                lnprior = ps1_MrLF_lnprior(self.models_labels["Mr"])
-        lnprior = np.array(lnprior, dtype=np.float64)
-        names = self.models_labels.dtype.names or ()
-        if apply_agewt and "agewt" in names:
-            lnprior = lnprior + np.log(np.abs(self.models_labels["agewt"]))
-        if apply_grad:
-            for l in names:
-                if self.labels_mask[l][0]:
-                    ul = np.unique(self.models_labels[l])
-                    if len(ul) > 1:
-                        lnprior = lnprior + np.interp(self.models_labels[l], ul, np.log(np.gradient(ul)))
+            if lnprior is None:
+                if "mini" in names:
+                    lnprior = imf_lnprior(self.models_labels["mini"])
+                else:   # PS1 r-band luminosity function (brutus/fitting.py:1339-1341)
+                    lnprior = ps1_MrLF_lnprior(self.models_labels["Mr"])
+            lnprior = np.array(lnprior, dtype=np.float64)
+            if apply_agewt and "agewt" in names:
+                lnprior = lnprior + np.log(np.abs(self.models_labels["agewt"]))
+            if apply_grad:
+                for l in names:
+                    if self.labels_mask[l][0]:
+                        ul = np.unique(self.models_labels[l])
+                        if len(ul) > 1:
+                            lnprior = lnprior + np.interp(self.models_labels[l], ul, np.log(np.gradient(ul)))
+            if key is not None:
+                lnprior.setflags(write=False)
+                self._prior_cache[key] = lnprior
         if lngalprior is None and data_coords is None:   # brutus/fitting.py:1362-1365
             raise ValueError("`data_coords` must be provided if using the default Galactic model prior.")
         if lndustprior is None and dustfile is not None:
@@ -371,18 +381,19 @@ class BruteForce(object):
              lnprior_ext=None, wt_thresh=1e-3, cdf_thresh=2e-3, Ndraws=250, lngalprior=None,
              lndustprior=None, dustfile=None, apply_dlabels=True, data_coords=None,
              return_distreds=True, logl_dim_prior=True, ltol=3e-2, ltol_subthresh=1e-2,
-             logl_initthresh=5e-3, mem_lim=8000., rstate=None, batch=1024, _device_arrays=False):
+             logl_initthresh=5e-3, mem_lim=8000., rstate=None, batch=1024, _device_arrays=False, _prepared=False):
         """Generator with the reference's contract (brutus/fitting.py:1803-2061): yields, per object,
         ``(sidxs, scales, avs, rvs, cov_sar, Ndim, lnprob, levid, chi2min[, dists, reds, dreds,
         logwts])``.  Stars go to the GPU ``batch`` at a time; the prior integration and resampling
         run on the host in catalogue order with the caller's ``rstate``."""
-        (data, data_err, data_mask, _, data_coords, lnprior, lngalprior, lndustprior, av_gauss,
-         wt_thresh, rstate) = self._setup(
-            data, data_err, data_mask, parallax=parallax, parallax_err=parallax_err,
-            av_gauss=av_gauss, lnprior=lnprior, wt_thresh=wt_thresh, cdf_thresh=cdf_thresh,
-            apply_agewt=False, apply_grad=False, lngalprior=lngalprior, lndustprior=lndustprior,
-            dustfile=dustfile, data_coords=data_coords, ltol_subthresh=ltol_subthresh,
-            logl_initthresh=logl_initthresh, mag_max=np.inf, merr_max=np.inf, rstate=rstate)
+        if not _prepared:   # fit() has been through _setup already
+            (data, data_err, data_mask, _, data_coords, lnprior, lngalprior, lndustprior, av_gauss,
+             wt_thresh, rstate) = self._setup(
+                data, data_err, data_mask, parallax=parallax, parallax_err=parallax_err,
+                av_gauss=av_gauss, lnprior=lnprior, wt_thresh=wt_thresh, cdf_thresh=cdf_thresh,
+                apply_agewt=False, apply_grad=False, lngalprior=lngalprior, lndustprior=lndustprior,
+                dustfile=dustfile, data_coords=data_coords, ltol_subthresh=ltol_subthresh,
+                logl_initthresh=logl_initthresh, mag_max=np.inf, merr_max=np.inf, rstate=rstate)
         apply_av_prior = av_gauss is None  # brutus/fitting.py:1965
         ndata = data.shape[0]
         if parallax is None:  # the reference indexes parallax[i] unconditionally (:1989)
@@ -412,9 +423,15 @@ class BruteForce(object):
                                  wt_thresh=0. if wt_thresh is None else wt_thresh)   # 0: every model is shipped
         if device_posterior:
             names = (dlabels.dtype.names or ()) if dlabels is not None else ()
-            h.set_model_priors(lnprior=lnprior if np.ndim(lnprior) else np.full(self.NMODEL, float(lnprior)),
-                               feh=dlabels["feh"] if "feh" in names else None,
-                               loga=dlabels["loga"] if "loga" in names else None)
+            feh = dlabels["feh"] if "feh" in names else None
+            loga = dlabels["loga"] if "loga" in names else None
+            # staged once: the cached default prior is the same (read-only) array from call to call
+            staged = (id(h), id(lnprior) if np.ndim(lnprior) and not lnprior.flags.writeable else None,
+                      "feh" in names, "loga" in names)
+            if staged[1] is None or staged != self._staged_priors:
+                h.set_model_priors(lnprior=lnprior if np.ndim(lnprior) else np.full(self.NMODEL, float(lnprior)),
+                                   feh=feh, loga=loga)
+                self._staged_priors = staged if staged[1] is not None else None
             # the device draws from a counter-based generator keyed by (seed, catalogue index, model, draw): one
             # seed is taken from the caller's generator, whose stream is otherwise untouched on this path
             # (distributional, not draw-for-draw, equivalence with the reference)
@@ -524,7 +541,7 @@ class BruteForce(object):
                         apply_dlabels=apply_dlabels, data_coords=data_coords,
                         return_distreds=save_dar_draws, ltol_subthresh=ltol_subthresh,
                         logl_dim_prior=logl_dim_prior, logl_initthresh=logl_initthresh, ltol=ltol,
-                        mem_lim=mem_lim, _device_arrays=device_posterior)
+                        mem_lim=mem_lim, _device_arrays=device_posterior, _prepared=True)
         try:
             if device_posterior:   # the device returns (Nbatch, Ndraws) arrays: rows land batch by batch
                 for b0, b1, r in gen:
