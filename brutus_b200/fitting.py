@@ -578,10 +578,11 @@ class _ResultStore(object):
     """Output file of ``fit`` with the reference's dataset names and dtypes (brutus/fitting.py:1632-1662).
 
     ``<save_file>.h5`` through h5py when it is importable, opened ``"w-"`` like the reference.  Without h5py (this
-    image) the same datasets go to ``<save_file>.npz``; with ``running_io`` the rows are first written, batch by
-    batch, into memory-mapped ``.npy`` files under ``<save_file>.partial/`` and flushed, so that a crash keeps what
-    was fitted so far (the reference's reason for ``running_io``, :1594-1601), and the directory is folded into the
-    ``.npz`` when the fit completes.  Either way an existing output makes the constructor raise before any fitting."""
+    image) the same datasets go to ``<save_file>.npz``.  With ``running_io`` that archive is laid out before the first
+    object is fitted and the rows are written into it in place, batch by batch, through a memory map (npzstore.py):
+    a crash keeps what was fitted so far (the reference's reason for ``running_io``, :1594-1601; ``row_done`` marks
+    the rows written, ``npzstore.read_partial`` reads an unfinished file), and completing the fit only patches the
+    members' checksums.  Either way an existing output makes the constructor raise before any fitting."""
 
     def __init__(self, save_file, data_labels, ndata, ndraws, save_dar_draws, running_io):
         spec = {"model_idx": ((ndata, ndraws), "int32", -99), "ml_scale": ((ndata, ndraws), "float32", 1.),
@@ -595,7 +596,7 @@ class _ResultStore(object):
         self.running_io = bool(running_io)
         self.labels = np.asarray(data_labels)
         self.h5 = None
-        self.partial = None
+        self.npz = None
         try:
             import h5py
             if not isinstance(getattr(h5py, "__file__", None), str):   # an inert stand-in module, not the real thing
@@ -613,18 +614,14 @@ class _ResultStore(object):
         self.target = "{0}.npz".format(save_file)
         if os.path.exists(self.target):
             raise FileExistsError("Unable to create file (file exists): %r" % self.target)
-        with open(self.target, "xb"):      # claims the name; fails on an unwritable path
-            pass
         if self.running_io:
-            self.partial = "{0}.partial".format(save_file)
-            os.makedirs(self.partial, exist_ok=False)
-            np.save(os.path.join(self.partial, "labels.npy"), self.labels)
-            self.arrays = {}
-            for k, (sh, dt, fill) in spec.items():
-                m = np.lib.format.open_memmap(os.path.join(self.partial, k + ".npy"), mode="w+", dtype=dt, shape=sh)
-                m[...] = fill
-                self.arrays[k] = m
+            from .npzstore import NpzInPlace
+            spec["row_done"] = ((ndata,), "uint8", 0)
+            self.npz = NpzInPlace(self.target, spec, {"labels": self.labels})
+            self.arrays = self.npz.arrays
         else:
+            with open(self.target, "xb"):      # claims the name; fails on an unwritable path
+                pass
             self.arrays = {k: np.full(sh, fill, dtype=dt) for k, (sh, dt, fill) in spec.items()}
 
     def write(self, b0, b1, rows):
@@ -636,9 +633,9 @@ class _ResultStore(object):
                 self.h5[k][b0:b1] = self.arrays[k][b0:b1]
         if self.h5 is not None and self.running_io:
             self.h5.flush()
-        elif self.partial is not None:
-            for m in self.arrays.values():
-                m.flush()
+        elif self.npz is not None:
+            self.arrays["row_done"][b0:b1] = 1
+            self.npz.flush()
 
     def close(self):
         if self.h5 is not None:
@@ -650,11 +647,9 @@ class _ResultStore(object):
             return
         if getattr(self, "target", None) is None:
             return
-        np.savez(self.target, labels=self.labels, **{k: np.asarray(v) for k, v in self.arrays.items()})
-        if self.partial is not None:
-            for k in list(self.arrays):                                        # detach from the memmaps (in place:
-                self.arrays[k] = np.array(self.arrays[k])                       # fit() returns this dictionary)
-            import shutil
-            shutil.rmtree(self.partial, ignore_errors=True)
-            self.partial = None
+        if self.npz is not None:
+            self.npz.close()
+            self.npz = None
+        else:
+            np.savez(self.target, labels=self.labels, **{k: np.asarray(v) for k, v in self.arrays.items()})
         self.target = None

@@ -107,14 +107,17 @@ def test_result_store_is_exclusive_and_incremental(tmp_path):
     with pytest.raises((FileExistsError, OSError)):
         fitting._ResultStore(target, np.arange(5), 5, 3, True, True)
     st.write(0, 2, {"model_idx": np.full((2, 3), 7), "obj_log_evid": np.array([1.5, 2.5])})
-    if st.h5 is None:    # no h5py in this image: the rows are already in the memory-mapped partial files
-        part = np.load(str(tmp_path / "out.partial" / "model_idx.npy"))
-        assert np.all(part[:2] == 7) and np.all(part[2:] == -99)
+    if st.h5 is None:    # no h5py in this image: the rows are already in the archive, written in place
+        from brutus_b200 import npzstore
+        part = npzstore.read_partial(target + ".npz")
+        assert np.all(part["model_idx"][:2] == 7) and np.all(part["model_idx"][2:] == -99)
+        assert list(part["row_done"]) == [1, 1, 0, 0, 0]
     st.close()
     if st.h5 is None and not (tmp_path / "out.h5").exists():
         d = np.load(target + ".npz")
         assert np.all(d["model_idx"][:2] == 7) and d["obj_log_evid"][1] == 2.5 and np.array_equal(d["labels"], np.arange(5))
-        assert not (tmp_path / "out.partial").exists()
+        import zipfile
+        assert zipfile.ZipFile(target + ".npz").testzip() is None      # checksums patched on completion
     with pytest.raises((FileExistsError, OSError)):        # still exclusive after completion
         fitting._ResultStore(target, np.arange(5), 5, 3, True, False)
 
