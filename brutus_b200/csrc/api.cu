@@ -949,7 +949,16 @@ template <typename T> struct Engine : EngineBase {
         return BF_OK;
     }
 
-    static unsigned pass_ctas(int64_t n) { return (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + kPassStep - 1) / kPassStep, kPassCtas)); }
+    // CTAs of a pass over the pool: exactly one wave -- what the device keeps resident of this kernel -- each CTA taking
+    // a contiguous range of records (1.6 waves of a fixed 148 x 8 grid left the second wave's SMs idle for 20 % of the pass)
+    template <typename K> unsigned pass_ctas(int64_t n, K kernel) {
+        int per_sm = 0, sms = 0, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTile, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+        const int64_t wave = std::min<int64_t>((int64_t)sms * per_sm, kPassCtas);
+        return (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + kPassStep - 1) / kPassStep, wave));
+    }
 
     void phase_begin() { cudaEventRecord(evA, stream); }
     double phase_end() {  // synchronises the stream
@@ -1098,7 +1107,7 @@ template <typename T> struct Engine : EngineBase {
             // ---- 2. exact cull, flux-loop control ----
             phase_begin();
             { TRACE("k_reset_red"); k_reset_red<T><<<(ng * kNumRed + 255) / 256, 256, 0, stream>>>(d_red.p, d_list.p, ng, (1u << RED_FL) | (1u << RED_FB) | (1u << RED_LNP)); }
-            if (n > 0) { TRACE("k_cull"); k_cull<T><<<pass_ctas(n), kTile, 0, stream>>>(pp); }
+            if (n > 0) { TRACE("k_cull"); k_cull<T><<<pass_ctas(n, k_cull<T>), kTile, 0, stream>>>(pp); }
             { TRACE("k_flux_ctl"); k_flux_ctl<T><<<1, 1024, 0, stream>>>(d_star_int.p, d_red.p, d_list.p, ng, 1, nit_first, max_flux, o.ln_sub, d_ctr.p + CTR_ANY); }
             stats.kernel_launches += 3;
             CK(cudaGetLastError());
@@ -1124,7 +1133,7 @@ template <typename T> struct Engine : EngineBase {
             int done_iter = nit_first;
             rp.n = n; rp.list = fixlist(); rp.nlist = d_ctr.p + CTR_NLIST;
             if (any && done_iter < max_flux) {
-                { TRACE("k_flux_list"); k_flux_list<T><<<pass_ctas(n), kTile, 0, stream>>>(pp, fixlist(), d_ctr.p + CTR_NLIST); }
+                { TRACE("k_flux_list"); k_flux_list<T><<<pass_ctas(n, k_flux_list<T>), kTile, 0, stream>>>(pp, fixlist(), d_ctr.p + CTR_NLIST); }
                 stats.kernel_launches++;
             }
             while (any && done_iter < max_flux) {
@@ -1144,7 +1153,7 @@ template <typename T> struct Engine : EngineBase {
             }
             // ---- 3. lnlike / lnprob, per-star maximum, first selection, selection map scan ----
             if (n > 0) {
-                { TRACE("k_final"); k_final<T><<<pass_ctas(n), kTile, 0, stream>>>(pp); }
+                { TRACE("k_final"); k_final<T><<<pass_ctas(n, k_final<T>), kTile, 0, stream>>>(pp); }
                 { TRACE("k_sel"); k_sel<T><<<(unsigned)((n + kPassStep - 1) / kPassStep), kTile, 0, stream>>>(pp); }
                 stats.kernel_launches += 2;
             }
