@@ -466,7 +466,9 @@ def run_b200(args):
         "counts_per_step": {"candidates": agg["candidates"] / args.steps, "survivors": agg["survivors"] / args.steps,
                             "selected": agg["selected"] / args.steps, "resweeps": agg["resweeps"] / args.steps,
                             "fixups": agg["fixups"] / args.steps, "fallbacks": agg["fallbacks"] / args.steps,
-                            "regroups": agg["regroups"] / args.steps},
+                            "regroups": agg["regroups"] / args.steps,
+                            "host_syncs": agg.get("host_syncs", 0) / args.steps,
+                            "host_syncs_fit_call": agg_f.get("host_syncs", 0) / args.steps},
         "clocks": clocks,
         "region_wall_s": t_region,
     }

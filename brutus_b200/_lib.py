@@ -55,7 +55,7 @@ class Stats(C.Structure):
                 ("selected", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("ms_post", C.c_double), ("selected2", C.c_int64), ("clipped", C.c_int64),
                 ("fixups", C.c_int64), ("flux_more_launches", C.c_int64), ("regroups", C.c_int64),
-                ("unconverged", C.c_int64)]
+                ("unconverged", C.c_int64), ("host_syncs", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -961,7 +961,9 @@ template <typename T> struct Engine : EngineBase {
     }
 
     void phase_begin() { cudaEventRecord(evA, stream); }
+    cudaError_t sync() { stats.host_syncs++; return cudaStreamSynchronize(stream); }
     double phase_end() {  // synchronises the stream
+        stats.host_syncs++;
         cudaEventRecord(evB, stream);
         cudaEventSynchronize(evB);
         float ms = 0.f;
@@ -1050,7 +1052,7 @@ template <typename T> struct Engine : EngineBase {
                 stats.kernel_launches++; stats.magfit_launches++; stats.magfit_star_passes += nl;
                 publish(h_red.data(), d_red.p, (size_t)ns * kNumRed * sizeof(U));
                 publish(h_ctr.data(), d_ctr.p, CTR_COUNT * sizeof(int));
-                CK(cudaStreamSynchronize(stream));
+                CK(sync());
                 {
                     float ms = 0.f;
                     CK(cudaEventElapsedTime(&ms, evA, evB));
@@ -1093,7 +1095,7 @@ template <typename T> struct Engine : EngineBase {
                 stats.kernel_launches++;
                 CK(cudaGetLastError());
                 publish(h_ncand.data() + g0, d_ncand.p + g0, (size_t)ng * sizeof(int64_t));
-                CK(cudaStreamSynchronize(stream));
+                CK(sync());
                 *fits = false;
                 return BF_OK;
             }
@@ -1148,7 +1150,7 @@ template <typename T> struct Engine : EngineBase {
                 }
                 CK(cudaGetLastError());
                 publish(h_ctr.data(), d_ctr.p, CTR_COUNT * sizeof(int));
-                CK(cudaStreamSynchronize(stream));
+                CK(sync());
                 any = h_ctr[any_slot];
             }
             // ---- 3. lnlike / lnprob, per-star maximum, first selection, selection map scan ----
@@ -1527,7 +1529,7 @@ template <typename T> struct Engine : EngineBase {
         CK(cudaMemcpyAsync(seds, o_s, (size_t)tot * sizeof(double), cudaMemcpyDeviceToHost, stream));
         if (rvecs) CK(cudaMemcpyAsync(rvecs, o_r, (size_t)tot * sizeof(double), cudaMemcpyDeviceToHost, stream));
         if (drvecs) CK(cudaMemcpyAsync(drvecs, o_d, (size_t)tot * sizeof(double), cudaMemcpyDeviceToHost, stream));
-        CK(cudaStreamSynchronize(stream));
+        CK(sync());
         d_in.release(); d_o.release(); d_ix.release();
         return BF_OK;
     }
@@ -1547,7 +1549,7 @@ template <typename T> struct Engine : EngineBase {
             CK(dst[k]->ensure((size_t)npad));
             k_convert_labels<T><<<(unsigned)((npad + 255) / 256), 256, 0, stream>>>(tmp.p, dst[k]->p, nmodel, npad, 1);
             CK(cudaGetLastError());
-            CK(cudaStreamSynchronize(stream));
+            CK(sync());
             stats.h2d_bytes += (size_t)nmodel * sizeof(double);
         }
         tmp.release();
@@ -1693,7 +1695,7 @@ template <typename T> struct Engine : EngineBase {
                 CK(cudaGetLastError());
             }
             publish(h_nsel2.data() + g.g0, d_nsel2.p + g.g0, (size_t)ng * sizeof(int));
-            CK(cudaStreamSynchronize(stream));
+            CK(sync());
             h_off2[g.g0] = 0;
             for (int s = g.g0; s < g.g1; s++) {
                 h_off2[s + 1] = h_off2[s] + h_nsel2[s];
@@ -1734,7 +1736,7 @@ template <typename T> struct Engine : EngineBase {
                     stats.kernel_launches += 7;
                     CK(cudaGetLastError());
                     publish(h_nsel2.data() + g.g0, d_nsel2.p + g.g0, (size_t)ng * sizeof(int));
-                    CK(cudaStreamSynchronize(stream));
+                    CK(sync());
                     for (int s = g.g0; s < g.g1; s++) {
                         h_off2[s + 1] = h_off2[s] + h_nsel2[s];
                         if (nsel) nsel[g.s0 + s] = h_nsel2[s];
@@ -1770,7 +1772,7 @@ template <typename T> struct Engine : EngineBase {
             CK(cudaMemcpyAsync(hd + 8 * ntot + dst * 9, pp.o_cov + off * 9, cnt * 9 * sizeof(double), cudaMemcpyDeviceToHost, stream));
             CK(cudaMemcpyAsync(levid + g.s0 + g.g0, pp.o_levid + g.g0, (size_t)ng * sizeof(double), cudaMemcpyDeviceToHost, stream));
             CK(cudaMemcpyAsync(chi2min + g.s0 + g.g0, pp.o_chi2min + g.g0, (size_t)ng * sizeof(double), cudaMemcpyDeviceToHost, stream));
-            CK(cudaStreamSynchronize(stream));
+            CK(sync());
             float ms = 0.f;
             CK(cudaEventElapsedTime(&ms, evP0, evP1));
             stats.ms_post += ms;
@@ -2151,7 +2153,7 @@ static void merge_stats(bf_handle* h) {
         t.fallbacks += s.fallbacks; t.survivors += s.survivors; t.selected += s.selected;
         t.h2d_bytes += s.h2d_bytes; t.d2h_bytes += s.d2h_bytes; t.selected2 += s.selected2; t.clipped += s.clipped;
         t.fixups += s.fixups; t.flux_more_launches += s.flux_more_launches; t.regroups += s.regroups;
-        t.unconverged += s.unconverged;
+        t.unconverged += s.unconverged; t.host_syncs = std::max(t.host_syncs, s.host_syncs);
     }
     h->stats = t;
 }

@@ -88,6 +88,7 @@ typedef struct bf_stats {
     int64_t flux_more_launches; /* flux iterations beyond the ones the sweep runs itself (whole-pool passes) */
     int64_t regroups;       /* star groups split because their candidate records overflowed the pool      */
     int64_t unconverged;    /* stars whose mag or flux loop was stopped by the iteration cap (max_iter)     */
+    int64_t host_syncs;     /* times the host waited for the device inside the call (control read-backs)    */
 } bf_stats;
 
 void bf_default_options(bf_options* opt);

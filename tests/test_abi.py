@@ -34,7 +34,7 @@ def test_struct_layout_matches_header(lib):
     assert (o.ltol, o.ltol_subthresh, o.init_thresh, o.wt_thresh, o.select_slack) == (3e-2, 1e-2, 5e-3, 1e-3, 0.5)
     assert (o.dim_prior, o.max_iter, o.apply_parallax_clip) == (1, 0, 1)
     assert C.sizeof(_lib.Options) == 8 * 8 + 5 * 8 + 4 * 4
-    assert C.sizeof(_lib.Stats) == 4 * 8 + 10 * 8 + 3 * 8 + 4 * 8
+    assert C.sizeof(_lib.Stats) == 4 * 8 + 10 * 8 + 3 * 8 + 5 * 8
     assert C.sizeof(_lib.Records) == 8 + 8 + 4 + 4 + 8 + 8
     po = _lib.PostOptions()
     lib.bf_default_post_options(C.byref(po))
