@@ -21,7 +21,7 @@ SYMBOLS = ("bf_default_options", "bf_create", "bf_destroy", "bf_last_error", "bf
            "bf_set_grid_device", "bf_set_labels", "bf_loglike_full", "bf_sweep_batch",
            "bf_get_stats", "bf_flush_l2", "bf_device_count", "bf_version",
            "bf_default_gal_params", "bf_default_post_options", "bf_set_model_priors", "bf_fit_batch",
-           "bf_get_seds", "bf_get_trace", "bf_create_multi", "bf_num_devices", "bf_nccl_unique_id",
+           "bf_get_seds", "bf_offsets_weights", "bf_get_trace", "bf_create_multi", "bf_num_devices", "bf_nccl_unique_id",
            "bf_nccl_init", "bf_set_grid_bcast", "bf_bcast_host", "bf_allreduce_max")
 
 
@@ -129,6 +129,7 @@ def load():
     lib.bf_fit_batch.argtypes = [vp, C.c_int64, dp, dp, u8p, dp, dp, dp, dp, dp, op,
                                  C.POINTER(PostOptions), i32p, i32p, i64p, dp, dp, C.POINTER(Draws)]
     lib.bf_get_seds.argtypes = [vp, C.c_int64, i32p, dp, dp, C.c_int32, dp, dp, dp]
+    lib.bf_offsets_weights.argtypes = [vp, C.c_int64, C.c_int32, dp, dp, u8p, i32p, dp, dp, dp, dp, u8p, C.c_int32, dp, dp]
     lib.bf_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.bf_get_trace.argtypes = [vp]
     lib.bf_get_trace.restype = C.c_char_p
@@ -385,6 +386,37 @@ class Handle:
                                           int(bool(return_flux)), _ptr(seds, C.c_double),
                                           _ptr(rvecs, C.c_double), _ptr(drvecs, C.c_double)))
         return seds, rvecs, drvecs
+
+    def offsets_weights(self, phot, err, mask, idxs, reds, dreds, dists, old_offsets=None, mask_fit=None,
+                        dim_prior=True):
+        """The device part of ``photometric_offsets`` (brutus/utils.py:1268-1271, :1299-1309): returns
+        ``(seds, wt)``, the flux SEDs of the posterior samples ``(Nobj, Nsamps, Nfilt)`` and, for every band with
+        ``mask_fit``, the likelihood weights of the samples with that band left out, ``(Nfilt, Nobj, Nsamps)``."""
+        phot = np.ascontiguousarray(phot, dtype=np.float64)
+        err = np.ascontiguousarray(err, dtype=np.float64)
+        mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        ix = np.ascontiguousarray(idxs, dtype=np.int32)
+        nobj, nfilt = phot.shape
+        if nfilt != self.nfilt or err.shape != phot.shape or mask.shape != phot.shape or ix.ndim != 2 or ix.shape[0] != nobj:
+            raise ValueError("phot, err, mask must be (Nobj, Nfilt) and idxs (Nobj, Nsamps)")
+        nsamps = ix.shape[1]
+        a = np.ascontiguousarray(reds, dtype=np.float64)
+        r = np.ascontiguousarray(dreds, dtype=np.float64)
+        d = np.ascontiguousarray(dists, dtype=np.float64)
+        if a.shape != ix.shape or r.shape != ix.shape or d.shape != ix.shape:
+            raise ValueError("reds, dreds, dists must have the shape of idxs")
+        oo = None if old_offsets is None else np.ascontiguousarray(old_offsets, dtype=np.float64)
+        mf = np.ones(nfilt, dtype=np.uint8) if mask_fit is None else np.ascontiguousarray(mask_fit, dtype=np.uint8)
+        if (oo is not None and oo.shape != (nfilt,)) or mf.shape != (nfilt,):
+            raise ValueError("old_offsets and mask_fit must have Nfilt entries")
+        seds = np.empty((nobj, nsamps, nfilt))
+        wt = np.empty((nfilt, nobj, nsamps))
+        self._check(self._lib.bf_offsets_weights(
+            self._h, nobj, nsamps, _ptr(phot, C.c_double), _ptr(err, C.c_double), _ptr(mask, C.c_uint8),
+            _ptr(ix, C.c_int32), _ptr(a, C.c_double), _ptr(r, C.c_double), _ptr(d, C.c_double),
+            _ptr(oo, C.c_double), _ptr(mf, C.c_uint8), int(bool(dim_prior)), _ptr(seds, C.c_double),
+            _ptr(wt, C.c_double)))
+        return seds, wt
 
     def set_model_priors(self, lnprior=None, feh=None, loga=None):
         """Stage the static inputs of lnpost: the `lnprior` grid (brutus/fitting.py:1004) and the label

@@ -99,6 +99,80 @@ __global__ void k_get_seds(const float* __restrict__ rows, int rs, int nfilt, in
     if (drvecs) drvecs[t] = (double)dv;
 }
 
+// photometric_offsets, the per-sample part (brutus/utils.py:1268-1271 and :1293-1309): one thread per posterior
+// sample (object o, sample k).  The sample's SED in flux on the staged grid (_get_seds :286-347, then / dist^2),
+// and for every band b that is being fitted the log-likelihood of the sample with band b left out --
+// phot_loglike(phot * old_offsets, err * old_offsets, mask without b, seds) (:1162-1222) -- summed over the
+// bands in their order, float64.
+template <typename T>
+__global__ void __launch_bounds__(256) k_offsets_lnl(const float* __restrict__ rows, int rs, int nfilt, int64_t nobj, int nsamps,
+                                                     const int* __restrict__ idx, const double* __restrict__ av,
+                                                     const double* __restrict__ rv, const double* __restrict__ dist,
+                                                     const double* __restrict__ phot, const double* __restrict__ var,
+                                                     const uint8_t* __restrict__ mask, const uint8_t* __restrict__ mask_fit,
+                                                     int dim_prior, double* __restrict__ seds, double* __restrict__ lnl) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = nobj * nsamps;
+    if (t >= n) return;
+    const int64_t o = t / nsamps;
+    const float* __restrict__ row = rows + (int64_t)idx[t] * rs;
+    const double d = dist[t], id2 = 1.0 / (d * d);
+    double sed[BF_MAX_FILT];
+#pragma unroll 1
+    for (int j = 0; j < nfilt; j++) {
+        const T mag0 = (T)row[j], r0 = (T)row[nfilt + j], dr = (T)row[2 * nfilt + j];
+        const T rvec = r0 + (T)rv[t] * dr;                       // :337
+        const T m = mag0 + (T)av[t] * rvec;                      // :338
+        sed[j] = (double)Num<T>::exp2(T(-kC2) * m) * id2;        // :343, :1271
+        seds[t * nfilt + j] = sed[j];
+    }
+    const double* __restrict__ ph = phot + o * nfilt;            // phot * old_offsets
+    const double* __restrict__ vr = var + o * nfilt;             // (err * old_offsets)^2
+    const uint8_t* __restrict__ mk = mask + o * nfilt;
+    for (int b = 0; b < nfilt; b++) {
+        if (!mask_fit[b]) continue;
+        double chi2 = 0., lnvar = 0.;
+        int ndim = 0;
+        for (int j = 0; j < nfilt; j++) {
+            if (!mk[j] || j == b) continue;
+            const double r = ph[j] - sed[j];
+            chi2 += r * r / vr[j];
+            lnvar += log(vr[j]);
+            ndim++;
+        }
+        double l;
+        if (dim_prior) {                                         // chi2 distribution with Ndim - 3 dof (:1215-1219)
+            const double a = 0.5 * (ndim - 3);
+            const double xl = (a - 1.) == 0. ? 0. : (a - 1.) * log(chi2);   // scipy.special.xlogy
+            l = xl - 0.5 * chi2 - lgamma(a) - 0.6931471805599453 * a;
+        } else {
+            l = -0.5 * chi2 - 0.5 * (ndim * 1.8378770664093453 + lnvar);
+        }
+        lnl[(int64_t)b * n + t] = l;
+    }
+}
+
+// weights of the samples of one object for one fitted band: exp(lnl - logsumexp(lnl)) over the object's samples
+// (brutus/utils.py:1308-1309; scipy's logsumexp: a non-finite maximum is replaced by 0).  One warp per (band, object).
+__global__ void __launch_bounds__(256) k_offsets_wt(const double* __restrict__ lnl, const uint8_t* __restrict__ mask_fit,
+                                                    int nfilt, int64_t nobj, int nsamps, double* __restrict__ wt) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= nfilt * nobj) return;
+    const int b = (int)(w / nobj);
+    if (!mask_fit[b]) return;
+    const double* __restrict__ x = lnl + w * nsamps;
+    double m = -CUDART_INF;
+    for (int k = lane; k < nsamps; k += 32) m = fmax(m, x[k]);
+    for (int off = 16; off; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if (!isfinite(m)) m = 0.;   // scipy; a NaN entry (fmax skips it) still turns the sum, hence every weight, into NaN
+    double s = 0.;
+    for (int k = lane; k < nsamps; k += 32) s += exp(x[k] - m);
+    for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    const double lse = log(s) + m;
+    for (int k = lane; k < nsamps; k += 32) wt[w * nsamps + k] = exp(x[k] - lse);
+}
+
 template <typename T>
 __global__ void k_reset_red(typename Enc<T>::U* red, const int* list, int nlist, unsigned mask) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -504,6 +578,10 @@ struct EngineBase {
     virtual int set_model_priors(const double* lnprior, const double* feh, const double* loga) = 0;
     virtual int get_seds(int64_t n, const int32_t* idx, const double* av, const double* rv, int flux, double* seds,
                          double* rvecs, double* drvecs) = 0;
+    virtual int offsets_weights(int64_t nobj, int nsamps, const double* phot, const double* errv, const uint8_t* mask,
+                                const int32_t* idxs, const double* reds, const double* dreds, const double* dists,
+                                const double* old_offsets, const uint8_t* mask_fit, int dim_prior, double* seds,
+                                double* wt) = 0;
     virtual int fit_batch(int64_t nstar, const double* flux, const double* errv, const uint8_t* mask,
                           const double* par, const double* perr, const double* coords, const double* ext_mean,
                           const double* ext_std, const bf_options* opt, const bf_post_options* po, int32_t* ndim,
@@ -1534,6 +1612,66 @@ template <typename T> struct Engine : EngineBase {
         return BF_OK;
     }
 
+    // ---- photometric_offsets: SEDs of the posterior samples and the leave-one-band-out weights (bf_offsets_weights) ----
+    int offsets_weights(int64_t nobj, int nsamps, const double* phot, const double* errv, const uint8_t* mask,
+                        const int32_t* idxs, const double* reds, const double* dreds, const double* dists,
+                        const double* old_offsets, const uint8_t* mask_fit, int dim_prior, double* seds,
+                        double* wt) override {
+        CK(cudaSetDevice(device));
+        if (!kt) { err = "bf_offsets_weights: no grid (call bf_set_grid)"; return BF_E_NOGRID; }
+        if (nobj < 0 || nsamps < 1) { err = "bf_offsets_weights: nobj must be >= 0 and nsamps >= 1"; return BF_E_INVALID; }
+        if (nobj == 0) return BF_OK;
+        if (!phot || !errv || !mask || !idxs || !reds || !dreds || !dists || !mask_fit || !seds || !wt) {
+            err = "bf_offsets_weights: null argument"; return BF_E_INVALID;
+        }
+        const int64_t n = nobj * nsamps;
+        for (int64_t i = 0; i < n; i++)
+            if (idxs[i] < 0 || idxs[i] >= nmodel) { err = "bf_offsets_weights: model index out of range"; return BF_E_INVALID; }
+        // per-object inputs with the previous offsets applied (brutus/utils.py:1303-1304)
+        std::vector<double> hp((size_t)nobj * nfilt), hv((size_t)nobj * nfilt);
+        for (int64_t o = 0; o < nobj; o++)
+            for (int j = 0; j < nfilt; j++) {
+                const double f = old_offsets ? old_offsets[j] : 1.0;
+                const double e = errv[o * nfilt + j] * f;
+                hp[(size_t)o * nfilt + j] = phot[o * nfilt + j] * f;
+                hv[(size_t)o * nfilt + j] = e * e;
+            }
+        DevBuf<double> d_in, d_obj, d_o;
+        DevBuf<int> d_ix;
+        DevBuf<uint8_t> d_mk;
+        CK(d_in.ensure((size_t)3 * n));
+        CK(d_obj.ensure((size_t)2 * nobj * nfilt));
+        CK(d_ix.ensure((size_t)n));
+        CK(d_mk.ensure((size_t)nobj * nfilt + nfilt));
+        CK(d_o.ensure((size_t)n * nfilt * 3));   // seds [n][nfilt], lnl [nfilt][n], wt [nfilt][n]
+        CK(cudaMemcpyAsync(d_in.p, reds, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_in.p + n, dreds, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_in.p + 2 * n, dists, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_obj.p, hp.data(), hp.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_obj.p + hp.size(), hv.data(), hv.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_ix.p, idxs, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_mk.p, mask, (size_t)nobj * nfilt, cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_mk.p + (size_t)nobj * nfilt, mask_fit, (size_t)nfilt, cudaMemcpyHostToDevice, stream));
+        double* o_s = d_o.p;
+        double* o_l = d_o.p + (size_t)n * nfilt;
+        double* o_w = d_o.p + (size_t)2 * n * nfilt;
+        const uint8_t* d_mfit = d_mk.p + (size_t)nobj * nfilt;
+        CK(cudaMemsetAsync(o_w, 0, (size_t)n * nfilt * sizeof(double), stream));   // bands that are not fitted: zeros
+        k_offsets_lnl<T><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_rows.p, rs, nfilt, nobj, nsamps, d_ix.p, d_in.p,
+                                                                        d_in.p + n, d_in.p + 2 * n, d_obj.p,
+                                                                        d_obj.p + hp.size(), d_mk.p, d_mfit, dim_prior, o_s, o_l);
+        const int64_t nwarp = (int64_t)nfilt * nobj;
+        k_offsets_wt<<<(unsigned)((nwarp * 32 + 255) / 256), 256, 0, stream>>>(o_l, d_mfit, nfilt, nobj, nsamps, o_w);
+        CK(cudaGetLastError());
+        stats.kernel_launches += 2;
+        CK(cudaMemcpyAsync(seds, o_s, (size_t)n * nfilt * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(wt, o_w, (size_t)n * nfilt * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(sync());
+        stats.h2d_bytes += (size_t)n * (3 * sizeof(double) + sizeof(int)) + (size_t)nobj * nfilt * 17;
+        stats.d2h_bytes += (size_t)2 * n * nfilt * sizeof(double);
+        return BF_OK;
+    }
+
     // ---- static per-model priors / labels of lnpost (bf_set_model_priors) ----
     int set_model_priors(const double* lnprior, const double* feh, const double* loga) override {
         CK(cudaSetDevice(device));
@@ -2320,6 +2458,15 @@ int bf_get_seds(bf_handle* h, int64_t n, const int32_t* idx, const double* av, c
     if (!h) return BF_E_INVALID;
     h->err.clear();
     return h->e0()->get_seds(n, idx, av, rv, return_flux, seds, rvecs, drvecs);
+}
+
+int bf_offsets_weights(bf_handle* h, int64_t nobj, int32_t nsamps, const double* phot, const double* err, const uint8_t* mask,
+                       const int32_t* idxs, const double* reds, const double* dreds, const double* dists,
+                       const double* old_offsets, const uint8_t* mask_fit, int32_t dim_prior, double* seds, double* wt) {
+    if (!h) return BF_E_INVALID;
+    h->err.clear();
+    return h->e0()->offsets_weights(nobj, nsamps, phot, err, mask, idxs, reds, dreds, dists, old_offsets, mask_fit, dim_prior,
+                                    seds, wt);
 }
 
 int bf_flush_l2(bf_handle* h) {

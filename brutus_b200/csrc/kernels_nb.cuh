@@ -464,7 +464,8 @@ template <typename T, int NB> struct SweepSmem {
     static constexpr size_t off_red = off_qkey + sizeof(uint32_t) * kQueue;   // [warp][star][kSweepRed] of T
     static constexpr size_t off_snap = off_red + sizeof(T) * (kTile / 32) * kStarChunk * kSweepRed;
     static constexpr size_t off_int = off_snap + sizeof(T) * kStarChunk * 2;
-    static constexpr size_t bytes = off_int + sizeof(int) * (kStarChunk * 3 + 4 + 2 * (kTile / 32));   // + queue tail, head, warp counts
+    static constexpr size_t off_bal = off_int + sizeof(int) * (kStarChunk * 3 + 4 + 2 * (kTile / 32));   // + queue tail, head, warp counts
+    static constexpr size_t bytes = off_bal + sizeof(uint32_t) * kStarChunk * (kTile / 32);             // candidate words [star][warp]
 };
 
 // The dense phase for entries [head, head + n) of the CTA's ring buffer (n <= kTile): one entry per thread, the
@@ -551,7 +552,7 @@ __global__ void __launch_bounds__(kTile, (sweep_min_ctas<T, NB>())) k_sweep(cons
     T* s_qrv = reinterpret_cast<T*>(smem + SM::off_qrv);
     T* s_qlp = reinterpret_cast<T*>(smem + SM::off_qlp);
     uint32_t* s_qkey = reinterpret_cast<uint32_t*>(smem + SM::off_qkey);
-    T* s_red = reinterpret_cast<T*>(smem + SM::off_red);                   // [8][32][kSweepRed]: per-warp maxima
+    T* s_red = reinterpret_cast<T*>(smem + SM::off_red);                   // [32][8][kSweepRed]: per-star, per-warp maxima
     T* s_snap = reinterpret_cast<T*>(smem + SM::off_snap);                 // [32][2]
     int* s_slot = reinterpret_cast<int*>(smem + SM::off_int);              // [32]
     int* s_kspec = s_slot + kStarChunk;
@@ -560,6 +561,7 @@ __global__ void __launch_bounds__(kTile, (sweep_min_ctas<T, NB>())) k_sweep(cons
     int* s_head = s_qtot + 1;                                              // ring position of the oldest queued entry
     unsigned long long* s_base = reinterpret_cast<unsigned long long*>(s_qtot + 2);   // pool position of the flush
     int* s_wc = s_qtot + 4;                                                // [2][8]: candidates per warp since the last meeting
+    uint32_t* s_bal = reinterpret_cast<uint32_t*>(smem + SM::off_bal);     // [32][8]: the candidate map words of this CTA
 
     const int first = blockIdx.y * kStarChunk;
     const int nst = min(kStarChunk, p.nlist - first);
@@ -581,7 +583,9 @@ __global__ void __launch_bounds__(kTile, (sweep_min_ctas<T, NB>())) k_sweep(cons
     }
 
     const int64_t i = (int64_t)blockIdx.x * kTile + threadIdx.x;  // npad is a multiple of kTile
-    const bool valid = i < p.nmodel;
+    // padding models exist in the last tile only; a CTA-uniform count keeps the per-star test to one compare
+    const int nvalid = (int)(p.nmodel - (int64_t)blockIdx.x * kTile < (int64_t)kTile ? p.nmodel - (int64_t)blockIdx.x * kTile : (int64_t)kTile);
+    const bool valid = (int)threadIdx.x < nvalid;
     const DevOpts<T> o = p.o;
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     float* tile_w = s_tile + wrp * 32 * RS;                         // this warp's 32 models
@@ -595,10 +599,9 @@ __global__ void __launch_bounds__(kTile, (sweep_min_ctas<T, NB>())) k_sweep(cons
     __syncthreads();
     ModelRegs<T, NB> m;
     load_model_row<T, NB>(tile_w + lane * RS, o, m);
-    const int64_t word = i >> 5;
     const T ninf = Num<T>::neg_inf();
     const T ln_init_c = o.ln_init - T(kCandMargin);
-    T* w_red = s_red + wrp * kStarChunk * kSweepRed;               // lane s stores the warp's maxima for star s
+    T* w_red = s_red + wrp * kSweepRed;                            // the warp's maxima for star s: [s][wrp][kSweepRed]
     int pend = 0;                                                   // queued entries not yet processed (CTA-uniform)
 
     for (int s = 0; s < nst; s++) {
@@ -622,8 +625,8 @@ __global__ void __launch_bounds__(kTile, (sweep_min_ctas<T, NB>())) k_sweep(cons
         l1 = warp_max_fast(l1); b1 = warp_max_fast(b1);
         const T lpm = warp_max_fast(lp);
         const T lqm = warp_max_fast(lq);
-        if (lane == s) {
-            T* w = w_red + s * kSweepRed;
+        {   // warp-uniform values to a warp-uniform address: every lane stores (no branch, no lane test)
+            T* w = w_red + s * (kTile / 32) * kSweepRed;
             w[0] = l0; w[1] = b0; w[2] = l1; w[3] = b1; w[4] = lpm; w[5] = lqm;
         }
         // --- candidate bit, queue ---
@@ -632,13 +635,18 @@ __global__ void __launch_bounds__(kTile, (sweep_min_ctas<T, NB>())) k_sweep(cons
         const bool likely = lp > thr1;                              // may survive the cull
         const bool cand = valid && (likely || lq > thr2);
         const unsigned bal = __ballot_sync(0xffffffffu, cand);
-        if (lane == 0) p.cand[(int64_t)slot * p.nwords + word] = bal;
+        s_bal[s * (kTile / 32) + wrp] = bal;                        // written to the map after the star loop, a sector per star
         const int par = (s / kFlushStars) & 1;                      // parity of the warp-count buffer in use
         if (bal) {   // push the warp's candidates of this star into the CTA's queue: one shared-memory atomic per warp
             int base = 0;
             if (lane == 0) {   // inline PTX: the compiler would wrap a one-lane atomicAdd in its own warp aggregation
                 const int n = __popc(bal);
-                const uint32_t a_tot = (uint32_t)__cvta_generic_to_shared(s_qtot);
+                // the address is made to depend on a lane id ptxas cannot tie to the branch (it is 0 here): with a
+                // provably uniform address ptxas wraps each atomic in a warp aggregation (vote, find-leader, popc,
+                // shuffle: ~12 instructions) that a single active lane does not need
+                uint32_t lid;
+                asm volatile("mov.u32 %0, %%laneid;" : "=r"(lid));
+                const uint32_t a_tot = (uint32_t)__cvta_generic_to_shared(s_qtot) + (lid << 2);
                 asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(base) : "r"(a_tot), "r"(n) : "memory");
                 if (base < kQueue && base + n >= kQueue)                      // the push that wraps the ring
                     asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(a_tot), "r"(-kQueue) : "memory");
@@ -678,6 +686,9 @@ __global__ void __launch_bounds__(kTile, (sweep_min_ctas<T, NB>())) k_sweep(cons
     }
     if (pend > 0) dense_flush<T, NB>(p, o, s_star, s_tile, s_tag, s_qav, s_qrv, s_qlp, s_qkey, s_head, pend, s_base);
     __syncthreads();
+    // the candidate map: the CTA's 8 words of a star are one 32-byte sector
+    for (int t = threadIdx.x; t < nst * (kTile / 32); t += kTile)
+        p.cand[(int64_t)s_slot[t / (kTile / 32)] * p.nwords + (int64_t)blockIdx.x * (kTile / 32) + t % (kTile / 32)] = s_bal[t];
     // combine the warps' maxima and publish them; NaN maxima (every lane NaN) must not poison the
     // unsigned-encoded atomics
     for (int t = threadIdx.x; t < nst * kSweepRed; t += kTile) {
@@ -685,7 +696,7 @@ __global__ void __launch_bounds__(kTile, (sweep_min_ctas<T, NB>())) k_sweep(cons
         bool any = false;
 #pragma unroll
         for (int w = 0; w < kTile / 32; w++) {
-            const T x = s_red[w * kStarChunk * kSweepRed + t];
+            const T x = s_red[((t / kSweepRed) * (kTile / 32) + w) * kSweepRed + t % kSweepRed];
             if (x == x) { v = any ? Num<T>::max(v, x) : x; any = true; }
         }
         const int s = t / kSweepRed, k = t % kSweepRed;

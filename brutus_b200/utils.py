@@ -2,19 +2,17 @@
 (SURVEY.md section 8f row 4): ``get_seds`` (brutus/utils.py:1089-1159), ``phot_loglike`` (:1162-1222) and
 ``photometric_offsets`` (:1225-1400).
 
-The grid-touching arithmetic -- ``_get_seds`` for (model, Av, Rv) samples (:286-347) -- runs on the device
-through ``bf_get_seds``; the rest works on ``(Nobj, Nsamps, Nfilt)`` arrays and consumes the caller's ``rstate``
-exactly as the reference does, so results are reproducible draw for draw.  No CPU fallback for the SEDs.
+Everything that scales with the number of posterior samples runs on the device: ``_get_seds`` for the (model, Av,
+Rv) samples (:286-347, ``bf_get_seds``) and, for ``photometric_offsets``, the leave-one-band-out chi2 likelihoods of
+the samples and their normalised weights (``bf_offsets_weights``).  The bootstrap over objects stays on the host: it
+consumes the caller's ``rstate`` exactly as the reference does, so results are reproducible draw for draw.
+``phot_loglike`` itself is kept as the reference's public helper for arbitrary ``models`` arrays.  No CPU fallback
+for the device parts.
 """
 import sys
 
 import numpy as np
 from scipy.special import gammaln, xlogy
-
-try:
-    from scipy.special import logsumexp
-except ImportError:  # pragma: no cover
-    from scipy.misc import logsumexp
 
 from . import fitting
 
@@ -83,12 +81,11 @@ def photometric_offsets(phot, err, mask, models, idxs, reds, dreds, dists, sel=N
         old_offsets = np.ones(nfilt)
     if rstate is None:
         rstate = np.random
-    # SEDs of every posterior sample, on the device (:1268-1271)
-    seds = get_seds(models, av=np.asarray(reds, dtype=np.float64).ravel(),
-                    rv=np.asarray(dreds, dtype=np.float64).ravel(), return_flux=True,
-                    idx=np.asarray(idxs).ravel(), precision=precision, device=device)
-    seds = seds / np.asarray(dists, dtype=np.float64).ravel()[:, None] ** 2
-    seds = seds.reshape(nobj, nsamps, nfilt)
+    # On the device, over the (Nobj, Nsamps, Nfilt) samples (bf_offsets_weights): their SEDs (:1268-1271) and,
+    # per fitted band, the likelihood weights of the samples with that band left out (:1299-1309)
+    h = fitting.get_handle(models, precision=precision, device=device)
+    seds, wt_dev = h.offsets_weights(phot, err, mask, idxs, reds, dreds, dists, old_offsets=old_offsets,
+                                     mask_fit=mask_fit, dim_prior=dim_prior)
     ratios, nratio = np.ones(nfilt), np.zeros(nfilt, dtype=int)
     ratios_err = np.zeros(nfilt)
     for i in range(nfilt):
@@ -102,12 +99,8 @@ def photometric_offsets(phot, err, mask, models, idxs, reds, dreds, dists, sel=N
         if n == 0:
             continue
         ratio = seds[s, :, i] / phot[s, None, i]
-        if mask_fit[i]:   # weights from the likelihood ignoring the current band (:1299-1309)
-            mtemp = np.array(mask)
-            mtemp[:, i] = False
-            lnl = np.array([phot_loglike(p * old_offsets, e * old_offsets, mt, sed, dim_prior=dim_prior)
-                            for p, e, mt, sed in zip(phot[s], err[s], mtemp[s], seds[s])])
-            wt = np.exp(lnl - logsumexp(lnl, axis=1)[:, None])
+        if mask_fit[i]:   # weights from the likelihood ignoring the current band (:1299-1309), from the device
+            wt = wt_dev[i][s]
         else:
             wt = np.ones((n, nsamps))
         wt = wt * weights[s]

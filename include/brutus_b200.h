@@ -258,6 +258,21 @@ int bf_fit_batch(bf_handle* h, int64_t nstar, const double* flux, const double* 
 int bf_get_seds(bf_handle* h, int64_t n, const int32_t* idx, const double* av, const double* rv,
                 int32_t return_flux, double* seds, double* rvecs, double* drvecs);
 
+/* The device part of photometric_offsets (brutus/utils.py:1225-1400) for nobj objects with nsamps posterior samples
+ * each, on the first device of the handle:
+ *   seds [nobj*nsamps*nfilt]   flux-density SEDs of the samples, get_seds(models[idxs], av=reds, rv=dreds,
+ *                              return_flux=True) / dists^2 (:1268-1271)
+ *   wt   [nfilt][nobj*nsamps]  for every band b with mask_fit[b] != 0: exp(lnl - logsumexp(lnl)) over the samples of
+ *                              an object, lnl = phot_loglike(phot * old_offsets, err * old_offsets, mask without
+ *                              band b, seds, dim_prior) (:1162-1222, :1299-1309); zeros for the other bands
+ * phot, err [nobj*nfilt] float64; mask [nobj*nfilt], mask_fit [nfilt] uint8; idxs int32, reds, dreds, dists float64
+ * [nobj*nsamps]; old_offsets [nfilt] or NULL (ones).  What is left to the caller is the bootstrap (:1311-1333), which
+ * consumes the caller's random state. */
+int bf_offsets_weights(bf_handle* h, int64_t nobj, int32_t nsamps, const double* phot, const double* err,
+                       const uint8_t* mask, const int32_t* idxs, const double* reds, const double* dreds,
+                       const double* dists, const double* old_offsets, const uint8_t* mask_fit, int32_t dim_prior,
+                       double* seds, double* wt);
+
 /* Statistics of the most recent bf_loglike_full / bf_sweep_batch / bf_fit_batch call on this handle. */
 int bf_get_stats(const bf_handle* h, bf_stats* out);
 
