@@ -21,7 +21,7 @@ SYMBOLS = ("bf_default_options", "bf_create", "bf_destroy", "bf_last_error", "bf
            "bf_set_grid_device", "bf_set_labels", "bf_loglike_full", "bf_sweep_batch",
            "bf_get_stats", "bf_flush_l2", "bf_device_count", "bf_version",
            "bf_default_gal_params", "bf_default_post_options", "bf_set_model_priors", "bf_fit_batch",
-           "bf_get_seds", "bf_offsets_weights", "bf_get_trace", "bf_create_multi", "bf_num_devices", "bf_nccl_unique_id",
+           "bf_get_seds", "bf_offsets_weights", "bf_set_init", "bf_get_trace", "bf_create_multi", "bf_num_devices", "bf_nccl_unique_id",
            "bf_nccl_init", "bf_set_grid_bcast", "bf_bcast_host", "bf_allreduce_max")
 
 
@@ -130,6 +130,7 @@ def load():
                                  C.POINTER(PostOptions), i32p, i32p, i64p, dp, dp, C.POINTER(Draws)]
     lib.bf_get_seds.argtypes = [vp, C.c_int64, i32p, dp, dp, C.c_int32, dp, dp, dp]
     lib.bf_offsets_weights.argtypes = [vp, C.c_int64, C.c_int32, dp, dp, u8p, i32p, dp, dp, dp, dp, u8p, C.c_int32, dp, dp]
+    lib.bf_set_init.argtypes = [vp, dp, dp]
     lib.bf_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.bf_get_trace.argtypes = [vp]
     lib.bf_get_trace.restype = C.c_char_p
@@ -417,6 +418,18 @@ class Handle:
             _ptr(oo, C.c_double), _ptr(mf, C.c_uint8), int(bool(dim_prior)), _ptr(seds, C.c_double),
             _ptr(wt, C.c_double)))
         return seds, wt
+
+    def set_init(self, av_init=None, rv_init=None):
+        """Per-model start of the magnitude fit for ``loglike_full`` (``av_init`` / ``rv_init`` of the reference's
+        ``loglike``, brutus/fitting.py:700-703); ``set_init()`` restores the default (the prior means)."""
+        if av_init is None and rv_init is None:
+            self._check(self._lib.bf_set_init(self._h, None, None))
+            return
+        a = np.ascontiguousarray(av_init, dtype=np.float64)
+        r = np.ascontiguousarray(rv_init, dtype=np.float64)
+        if a.shape != (self.nmodel,) or r.shape != (self.nmodel,):
+            raise ValueError("av_init and rv_init must have one entry per model")
+        self._check(self._lib.bf_set_init(self._h, _ptr(a, C.c_double), _ptr(r, C.c_double)))
 
     def set_model_priors(self, lnprior=None, feh=None, loga=None):
         """Stage the static inputs of lnpost: the `lnprior` grid (brutus/fitting.py:1004) and the label

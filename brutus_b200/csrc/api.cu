@@ -576,6 +576,7 @@ struct EngineBase {
                             int32_t* n_iter, int64_t* n_surv, double* max_lnprob, int64_t* offsets,
                             bf_records* out) = 0;
     virtual int set_model_priors(const double* lnprior, const double* feh, const double* loga) = 0;
+    virtual int set_init(const double* av_init, const double* rv_init) = 0;
     virtual int get_seds(int64_t n, const int32_t* idx, const double* av, const double* rv, int flux, double* seds,
                          double* rvecs, double* drvecs) = 0;
     virtual int offsets_weights(int64_t nobj, int nsamps, const double* phot, const double* errv, const uint8_t* mask,
@@ -769,6 +770,8 @@ template <typename T> struct Engine : EngineBase {
     // device posterior (bf_fit_batch)
     cudaEvent_t evP0 = nullptr, evP1 = nullptr;
     bool have_prior[3] = {false, false, false};   // lnprior, feh, loga staged?
+    DevBuf<T> d_av_init, d_rv_init;               // per-model start of the magnitude fit (bf_set_init), [npad]
+    bool have_init = false, use_init = false;     // staged? / in effect for the launches of the current call (B1 only)
     DevBuf<T> d_lnprior, d_feh, d_loga, d_lnp1, d_lnp2, d_lnb1, d_keys, d_keys_sorted, d_clip;
     DevBuf<int> d_seg;
     DevBuf<char> d_cubtmp;
@@ -855,6 +858,7 @@ template <typename T> struct Engine : EngineBase {
         d_ctr.release(); d_blk.release(); d_cand.release();
         d_probe.release(); d_ncand.release(); d_base.release(); d_tot.release(); d_red.release(); d_out.release(); d_flush.release();
         d_lnprior.release(); d_feh.release(); d_loga.release(); d_lnp1.release(); d_lnp2.release(); d_gstar.release();
+        d_av_init.release(); d_rv_init.release();
         d_lnb1.release(); d_keys.release(); d_keys_sorted.release(); d_clip.release(); d_seg.release(); d_cubtmp.release();
         d_ord.release(); d_rstar.release(); d_nsel2.release(); d_sel2.release(); d_oidx.release(); d_off2.release(); d_cdf.release();
         d_ptot.release(); d_odbl.release(); h_nsel2.release();
@@ -921,6 +925,7 @@ template <typename T> struct Engine : EngineBase {
         rs = row_stride(nf);
         nlabel = 0;
         have_prior[0] = have_prior[1] = have_prior[2] = false;
+        have_init = false;
         const size_t nval = (size_t)nm * nf * 3;
         CK(d_grid.ensure((size_t)3 * nf * npad));
         CK(d_rows.ensure((size_t)rs * npad));
@@ -1055,6 +1060,7 @@ template <typename T> struct Engine : EngineBase {
         if (ntile < 128 || max_iter < 2) return BF_OK;   // small grids: a re-sweep is cheaper than a probe
         ProbeParams<T> pp;
         pp.grid = d_grid.p; pp.npad = npad; pp.nmodel = nmodel; pp.stars = d_stars.p; pp.nstar = ns;
+        pp.av_init = use_init ? d_av_init.p : nullptr; pp.rv_init = use_init ? d_rv_init.p : nullptr;
         pp.tile_stride = 32; pp.o = o; pp.out = d_probe.p;   // 1/32 of the grid: measured best (16: +0.65 ms of probe; 64: more re-sweeps)
         if (const char* e = getenv("BRUTUS_B200_PROBE_STRIDE")) pp.tile_stride = std::max(1, atoi(e));
         for (size_t k = 0; k < (size_t)ns * 2 * kProbeIter; k++) h_probe[k] = Enc<T>::enc(-std::numeric_limits<T>::infinity());
@@ -1123,6 +1129,7 @@ template <typename T> struct Engine : EngineBase {
                 sp.cand = d_cand.p; sp.nwords = nwords; sp.labels = d_labels.p; sp.ext = d_ext.p; sp.nlabel = nlabel;
                 sp.pool = pl; sp.pool_cap = pool_cap; sp.pool_count = (unsigned long long*)(d_ctr.p + CTR_POOL);
                 sp.nit_first = nit_first;
+                sp.av_init = use_init ? d_av_init.p : nullptr; sp.rv_init = use_init ? d_rv_init.p : nullptr;
                 phase_begin();
                 { TRACE("k_sweep"); CK((cudaError_t)kt->sweep(sp, stream)); }
                 CK(cudaGetLastError());
@@ -1200,6 +1207,7 @@ template <typename T> struct Engine : EngineBase {
             phase_begin();
             RecParams<T> rp{};
             rp.rows = d_rows.p; rp.stars = d_stars.p; rp.star_int = d_star_int.p; rp.o = o; rp.pool = pl; rp.red = d_red.p;
+            rp.av_init = use_init ? d_av_init.p : nullptr; rp.rv_init = use_init ? d_rv_init.p : nullptr;
             if (nfix > 0) {
                 rp.n = nfix; rp.list = fixlist();
                 { TRACE("k_fixup"); kt->fixup(rp, stream); }
@@ -1335,10 +1343,12 @@ template <typename T> struct Engine : EngineBase {
         int nm = 0;
         std::vector<char> exact(1, 0);
         CK(cudaEventRecord(ev0, stream));
+        use_init = have_init;   // av_init / rv_init of loglike (brutus/fitting.py:700-703): this entry point only
         if (!rc) rc = probe_k(1, o, max_iter);
         int64_t tot = 0;
         bool fits = true;
         if (!rc) rc = process_group(1, 0, 1, o, max_iter, exact, &nm, &fits, &tot);
+        use_init = false;
         nlabel = saved_labels;
         if (rc) return rc;
         if (!fits) { err = "bf_loglike_full: candidate pool too small for one star"; return BF_E_NOMEM; }
@@ -1669,6 +1679,30 @@ template <typename T> struct Engine : EngineBase {
         CK(sync());
         stats.h2d_bytes += (size_t)n * (3 * sizeof(double) + sizeof(int)) + (size_t)nobj * nfilt * 17;
         stats.d2h_bytes += (size_t)2 * n * nfilt * sizeof(double);
+        return BF_OK;
+    }
+
+    // ---- per-model start of the magnitude fit: av_init / rv_init of loglike (bf_set_init) ----
+    int set_init(const double* av_init, const double* rv_init) override {
+        CK(cudaSetDevice(device));
+        if (!av_init && !rv_init) { have_init = false; return BF_OK; }
+        if (!kt) { err = "bf_set_init: call bf_set_grid first"; return BF_E_NOGRID; }
+        if (!av_init || !rv_init) { err = "bf_set_init: give both av_init and rv_init, or neither"; return BF_E_INVALID; }
+        for (int64_t i = 0; i < nmodel; i++)
+            if (!std::isfinite(av_init[i]) || !std::isfinite(rv_init[i])) { err = "bf_set_init: non-finite initial value"; return BF_E_INVALID; }
+        const double* src[2] = {av_init, rv_init};
+        DevBuf<T>* dst[2] = {&d_av_init, &d_rv_init};
+        DevBuf<double> tmp;
+        CK(tmp.ensure((size_t)nmodel));
+        for (int k = 0; k < 2; k++) {
+            CK(cudaMemcpyAsync(tmp.p, src[k], (size_t)nmodel * sizeof(double), cudaMemcpyHostToDevice, stream));
+            CK(dst[k]->ensure((size_t)npad));
+            k_convert_labels<T><<<(unsigned)((npad + 255) / 256), 256, 0, stream>>>(tmp.p, dst[k]->p, nmodel, npad, 1);
+            CK(cudaGetLastError());
+            CK(sync());
+        }
+        tmp.release();
+        have_init = true;
         return BF_OK;
     }
 
@@ -2396,6 +2430,12 @@ int bf_set_model_priors(bf_handle* h, const double* lnprior, const double* feh, 
     h->err.clear();
     for (auto* e : h->eng) { int rc = e->set_model_priors(lnprior, feh, loga); if (rc) return rc; }
     return BF_OK;
+}
+
+int bf_set_init(bf_handle* h, const double* av_init, const double* rv_init) {
+    if (!h) return BF_E_INVALID;
+    h->err.clear();
+    return h->e0()->set_init(av_init, rv_init);   // bf_loglike_full runs on the first device
 }
 
 int bf_fit_batch(bf_handle* h, int64_t nstar, const double* flux, const double* err, const uint8_t* mask,

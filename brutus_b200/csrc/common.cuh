@@ -437,6 +437,8 @@ template <typename T> struct SweepParams {
     int64_t pool_cap;
     unsigned long long* pool_count;   // [1] records appended so far (keeps counting past pool_cap)
     int nit_first;            // flux iterations the sweep runs on likely survivors: min(2, max_iter)
+    const T* av_init;         // [npad] per-model start of the magnitude fit (brutus/fitting.py:700-703), or both null:
+    const T* rv_init;         // the prior means (every caller but bf_loglike_full after bf_set_init)
 };
 
 // passes over the n records of the pool that need the model's coefficients again (both rare)
@@ -450,6 +452,8 @@ template <typename T> struct RecParams {
     const int* list;          // k_fixup: pool indices to redo; k_flux_more: the survivors of the active stars
     const int* nlist;         // k_flux_more: length of the list (device)
     typename Enc<T>::U* red;
+    const T* av_init;         // as in SweepParams
+    const T* rv_init;
 };
 
 // Kernel launchers instantiated once per band count (inst.cu, -DBF_NB=n).
@@ -463,6 +467,8 @@ template <typename T> struct ProbeParams {
     int tile_stride;
     DevOpts<T> o;
     typename Enc<T>::U* out;      // [nstar][2 * kProbeIter]: (L_k, B_k)
+    const T* av_init;             // as in SweepParams
+    const T* rv_init;
 };
 
 template <typename T> struct KTable {

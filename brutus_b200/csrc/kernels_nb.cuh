@@ -28,11 +28,13 @@ template <typename T, int NB> struct ModelRegs {
     P2<T> r0[NP];   // R_j + Rbar D_j                         (brutus/utils.py:337-338 at rv = rv_gauss[0])
     P2<T> D[NP];    // dR/dRv
     T bbar;
+    T A0, R0;       // expansion point of the model terms = where the magnitude fit starts: the prior means (Abar, Rbar)
+                    // unless the caller of loglike supplied av_init / rv_init (brutus/fitting.py:700-703)
 };
 
 template <typename T, int NB>
 __device__ __forceinline__ void finish_model(const T (&mu)[NB + 1], const T (&R)[NB + 1], const T (&D)[NB + 1],
-                                             const DevOpts<T>& o, ModelRegs<T, NB>& m) {
+                                             T A0, T R0, ModelRegs<T, NB>& m) {
     constexpr int NP = ModelRegs<T, NB>::NP;
     T r0[2 * NP], cb[2 * NP], Dd[2 * NP];
     T sum = T(0);
@@ -40,14 +42,15 @@ __device__ __forceinline__ void finish_model(const T (&mu)[NB + 1], const T (&R)
     for (int j = 0; j < 2 * NP; j++) {
         if (j < NB) {
             Dd[j] = D[j];
-            r0[j] = fma(o.Rbar, D[j], R[j]);
-            cb[j] = fma(o.Abar, r0[j], mu[j]);
+            r0[j] = fma(R0, D[j], R[j]);
+            cb[j] = fma(A0, r0[j], mu[j]);
             sum += cb[j];
         } else {
             Dd[j] = r0[j] = cb[j] = T(0);   // padding band: zero model terms, zero star weights
         }
     }
     m.bbar = sum * (T(1) / T(NB));
+    m.A0 = A0; m.R0 = R0;
 #pragma unroll
     for (int p = 0; p < NP; p++) {
         const T c0 = m.bbar - cb[2 * p];
@@ -64,11 +67,11 @@ __host__ __device__ constexpr int tile_stride(int nb) { return (row_stride(nb) /
 
 // ModelRegs from a model's 3 NB raw coefficients v = [mu | R | D]
 template <typename T, int NB>
-__device__ __forceinline__ void model_from_coeffs(const float (&v)[row_stride(NB)], const DevOpts<T>& o, ModelRegs<T, NB>& m) {
+__device__ __forceinline__ void model_from_coeffs(const float (&v)[row_stride(NB)], T A0, T R0, ModelRegs<T, NB>& m) {
     T mu[NB + 1], R[NB + 1], D[NB + 1];
 #pragma unroll
     for (int j = 0; j < NB; j++) { mu[j] = (T)v[j]; R[j] = (T)v[NB + j]; D[j] = (T)v[2 * NB + j]; }
-    finish_model<T, NB>(mu, R, D, o, m);
+    finish_model<T, NB>(mu, R, D, A0, R0, m);
 }
 
 // a model's coefficients from the coefficient-major grid (fully coalesced: thread = model)
@@ -80,16 +83,16 @@ __device__ __forceinline__ void load_coeffs(const float* __restrict__ grid, int6
 
 template <typename T, int NB>
 __device__ __forceinline__ void load_model(const float* __restrict__ grid, int64_t npad, int64_t i,
-                                           const DevOpts<T>& o, ModelRegs<T, NB>& m) {
+                                           T A0, T R0, ModelRegs<T, NB>& m) {
     float v[row_stride(NB)];
     load_coeffs<NB>(grid, npad, i, v);
-    model_from_coeffs<T, NB>(v, o, m);
+    model_from_coeffs<T, NB>(v, A0, R0, m);
 }
 
 // from a contiguous, 16-byte aligned row of row_stride(NB) floats: the model-major copy of the grid in HBM
 // (3-4 sectors per model: the per-record gathers) or the CTA's tile in shared memory
 template <typename T, int NB>
-__device__ __forceinline__ void load_model_row(const float* __restrict__ row, const DevOpts<T>& o, ModelRegs<T, NB>& m) {
+__device__ __forceinline__ void load_model_row(const float* __restrict__ row, T A0, T R0, ModelRegs<T, NB>& m) {
     constexpr int RS = row_stride(NB);
     float v[RS];
     const float4* __restrict__ p4 = reinterpret_cast<const float4*>(row);
@@ -98,7 +101,17 @@ __device__ __forceinline__ void load_model_row(const float* __restrict__ row, co
         float4 t = p4[k];
         v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
     }
-    model_from_coeffs<T, NB>(v, o, m);
+    model_from_coeffs<T, NB>(v, A0, R0, m);
+}
+
+// The expansion point of model i: the caller's per-model (av_init, rv_init) when the kernel is instantiated for them
+// (INIT: bf_loglike_full after bf_set_init), else the prior means, which then stay compile-time aliases of o.Abar /
+// o.Rbar (no extra registers on the throughput path).
+template <typename T, bool INIT>
+__device__ __forceinline__ void init_point(const DevOpts<T>& o, const T* __restrict__ av_init, const T* __restrict__ rv_init,
+                                           int64_t i, T& A0, T& R0) {
+    if (INIT) { A0 = av_init[i]; R0 = rv_init[i]; }
+    else { A0 = o.Abar; R0 = o.Rbar; }
 }
 
 // Result of the flux-space MLE at fixed (A, rho): brutus/fitting.py:430-576 (_get_sed_mle), normalised.
@@ -251,7 +264,7 @@ __device__ __forceinline__ void magfit_one(const ModelRegs<T, NB>& m, const DevO
     constexpr int NP = (NB + 1) / 2;
     const T ninf = Num<T>::neg_inf();
     const T S = srow[SR_SC + SC_S];
-    A = o.Abar; rho = o.Rbar;
+    A = m.A0; rho = m.R0;
     P2<T> u[NP], r[NP];
     T Q, Tm, gs;
     mag_init<T, NB>(m, srow, u, e, r, Q, Tm, gs);
@@ -281,7 +294,7 @@ __device__ __forceinline__ void magfit_one(const ModelRegs<T, NB>& m, const DevO
 // (:246-263).  The host turns them into the speculated iteration count of the full sweep, which
 // verifies it on the whole grid (so a wrong guess costs a re-sweep, never a wrong answer).
 // =================================================================================================
-template <typename T, int NB>
+template <typename T, int NB, bool INIT>
 __global__ void __launch_bounds__(kTile) k_kprobe(const ProbeParams<T> p) {
     using U = typename Enc<T>::U;
     constexpr int NP = (NB + 1) / 2;
@@ -297,7 +310,11 @@ __global__ void __launch_bounds__(kTile) k_kprobe(const ProbeParams<T> p) {
     const int64_t i = (int64_t)blockIdx.x * p.tile_stride * kTile + threadIdx.x;   // < npad; padding replicates a real model
     const DevOpts<T> o = p.o;
     ModelRegs<T, NB> m;
-    load_model<T, NB>(p.grid, p.npad, i, o, m);
+    {
+        T A0, R0;
+        init_point<T, INIT>(o, p.av_init, p.rv_init, i, A0, R0);
+        load_model<T, NB>(p.grid, p.npad, i, A0, R0, m);
+    }
     const int lane = threadIdx.x & 31;
     const T ninf = Num<T>::neg_inf();
     T acc[2 * kProbeIter];
@@ -307,7 +324,7 @@ __global__ void __launch_bounds__(kTile) k_kprobe(const ProbeParams<T> p) {
         const T* __restrict__ srow = s_star[s];
         const T S = srow[SR_SC + SC_S];
         const T c = srow[SR_SC + SC_MBAR] - m.bbar;
-        T A = o.Abar, rho = o.Rbar;
+        T A = m.A0, rho = m.R0;
         P2<T> u[NP], e[NP], r[NP];
         T Q, Tm, gs;
         mag_init<T, NB>(m, srow, u, e, r, Q, Tm, gs);
@@ -332,13 +349,13 @@ __global__ void __launch_bounds__(kTile) k_kprobe(const ProbeParams<T> p) {
         atomicMax(&p.out[(int64_t)first * 2 * kProbeIter + t], s_red[t / (2 * kProbeIter)][t % (2 * kProbeIter)]);
 }
 
-// residuals at an arbitrary (A, rho): e'_j = cm_j - cb_j - (A r_j - Abar r0_j), r_j = r0_j + (rho - Rbar) D_j
+// residuals at an arbitrary (A, rho): e'_j = cm_j - cb_j - (A r_j - A0 r0_j), r_j = r0_j + (rho - R0) D_j
 template <typename T, int NB>
 __device__ __forceinline__ void resid_at(const ModelRegs<T, NB>& m, const DevOpts<T>& o,
                                          const T* __restrict__ srow, T A, T rho, P2<T> (&e)[(NB + 1) / 2],
                                          P2<T> (&r)[(NB + 1) / 2]) {
     constexpr int NP = (NB + 1) / 2;
-    const P2<T> drho = bc2(rho - o.Rbar), A2 = bc2(A), nAbar = bc2(-o.Abar);
+    const P2<T> drho = bc2(rho - m.R0), A2 = bc2(A), nAbar = bc2(-m.A0);
 #pragma unroll
     for (int p = 0; p < NP; p++) {
         r[p] = fma2(drho, m.D[p], m.r0[p]);
@@ -471,7 +488,7 @@ template <typename T, int NB> struct SweepSmem {
 // The dense phase for entries [head, head + n) of the CTA's ring buffer (n <= kTile): one entry per thread, the
 // records appended to the pool as one contiguous block.  All threads of the CTA must call it (it contains
 // barriers); warps whose 32 threads are all beyond n only keep the barriers company.
-template <typename T, int NB>
+template <typename T, int NB, bool INIT>
 __device__ __forceinline__ void dense_flush(const SweepParams<T>& p, const DevOpts<T>& o, const T* __restrict__ s_star,
                                             const float* __restrict__ s_tile, const int* __restrict__ s_tag,
                                             const T* __restrict__ q_av, const T* __restrict__ q_rv,
@@ -508,7 +525,11 @@ __device__ __forceinline__ void dense_flush(const SweepParams<T>& p, const DevOp
     }
     const T* __restrict__ srow = s_star + s * kStarSmem;
     ModelRegs<T, NB> m;
-    load_model_row<T, NB>(s_tile + ml * RS, o, m);
+    {
+        T A0, R0;
+        init_point<T, INIT>(o, p.av_init, p.rv_init, (int64_t)blockIdx.x * kTile + ml, A0, R0);
+        load_model_row<T, NB>(s_tile + ml * RS, A0, R0, m);
+    }
     const T c = srow[SR_SC + SC_MBAR] - m.bbar;
     P2<T> e[NP], r[NP];
     Mle<T, NB> r4;
@@ -538,7 +559,7 @@ __device__ __forceinline__ void dense_flush(const SweepParams<T>& p, const DevOp
 // instantiation (verification) takes what it needs.
 template <typename T, int NB> constexpr int sweep_min_ctas() { return sizeof(T) == 8 ? 1 : (NB <= 8 ? 3 : 2); }
 
-template <typename T, int NB>
+template <typename T, int NB, bool INIT>
 __global__ void __launch_bounds__(kTile, (sweep_min_ctas<T, NB>())) k_sweep(const SweepParams<T> p) {
     using U = typename Enc<T>::U;
     using SM = SweepSmem<T, NB>;
@@ -597,8 +618,10 @@ __global__ void __launch_bounds__(kTile, (sweep_min_ctas<T, NB>())) k_sweep(cons
         for (int k = 0; k < row_stride(NB) / 4; k++) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
     }
     __syncthreads();
+    T A0, R0;
+    init_point<T, INIT>(o, p.av_init, p.rv_init, i, A0, R0);   // i < npad: the init arrays are padded like the grid
     ModelRegs<T, NB> m;
-    load_model_row<T, NB>(tile_w + lane * RS, o, m);
+    load_model_row<T, NB>(tile_w + lane * RS, A0, R0, m);
     const T ninf = Num<T>::neg_inf();
     const T ln_init_c = o.ln_init - T(kCandMargin);
     T* w_red = s_red + wrp * kSweepRed;                            // the warp's maxima for star s: [s][wrp][kSweepRed]
@@ -677,14 +700,14 @@ __global__ void __launch_bounds__(kTile, (sweep_min_ctas<T, NB>())) k_sweep(cons
             if (kFlushStars > 1 && lane == 0) s_wc[(par ^ 1) * (kTile / 32) + wrp] = 0;
             if (pend >= kTile) {
                 do {
-                    dense_flush<T, NB>(p, o, s_star, s_tile, s_tag, s_qav, s_qrv, s_qlp, s_qkey, s_head, kTile, s_base);
+                    dense_flush<T, NB, INIT>(p, o, s_star, s_tile, s_tag, s_qav, s_qrv, s_qlp, s_qkey, s_head, kTile, s_base);
                     pend -= kTile;
                 } while (pend >= kTile);
-                load_model_row<T, NB>(tile_w + lane * RS, o, m);   // this thread's own model again
+                load_model_row<T, NB>(tile_w + lane * RS, A0, R0, m);   // this thread's own model again
             }
         }
     }
-    if (pend > 0) dense_flush<T, NB>(p, o, s_star, s_tile, s_tag, s_qav, s_qrv, s_qlp, s_qkey, s_head, pend, s_base);
+    if (pend > 0) dense_flush<T, NB, INIT>(p, o, s_star, s_tile, s_tag, s_qav, s_qrv, s_qlp, s_qkey, s_head, pend, s_base);
     __syncthreads();
     // the candidate map: the CTA's 8 words of a star are one 32-byte sector
     for (int t = threadIdx.x; t < nst * (kTile / 32); t += kTile)
@@ -711,7 +734,7 @@ __global__ void __launch_bounds__(kTile, (sweep_min_ctas<T, NB>())) k_sweep(cons
 // non-survivor keeps its magnitude-fit values (brutus/fitting.py:805-810 scatters survivors only): redo the
 // MLE and icov at the magnitude fit kept in the record.
 // =================================================================================================
-template <typename T, int NB>
+template <typename T, int NB, bool INIT>
 __global__ void __launch_bounds__(kTile) k_fixup(const RecParams<T> p) {
     constexpr int NP = (NB + 1) / 2;
     const int64_t t = (int64_t)blockIdx.x * kTile + threadIdx.x;
@@ -723,7 +746,12 @@ __global__ void __launch_bounds__(kTile) k_fixup(const RecParams<T> p) {
     const DevOpts<T> o = p.o;
     const T* __restrict__ srow = p.stars + (int64_t)slot * kStarStride;
     ModelRegs<T, NB> m;
-    load_model_row<T, NB>(p.rows + (int64_t)pl.model[q] * row_stride(NB), o, m);
+    {
+        const int64_t i = pl.model[q];
+        T A0, R0;
+        init_point<T, INIT>(o, p.av_init, p.rv_init, i, A0, R0);
+        load_model_row<T, NB>(p.rows + i * row_stride(NB), A0, R0, m);
+    }
     const T c = srow[SR_SC + SC_MBAR] - m.bbar;
     const T A = pl.lnl[q], rho = pl.lnprob[q];
     P2<T> e[NP], r[NP];
@@ -743,7 +771,7 @@ __global__ void __launch_bounds__(kTile) k_fixup(const RecParams<T> p) {
 //   "lerr <= ltol"  <=>  max{lnl_new_i : |lnl_new_i - lnl_old_i| > ltol} <= max lnl_new + ln(ltol_subthresh)
 // It visits the list of those survivors that k_flux_list (api.cu) extracted from the pool.
 // =================================================================================================
-template <typename T, int NB>
+template <typename T, int NB, bool INIT>
 __global__ void __launch_bounds__(kTile) k_flux_more(const RecParams<T> p) {
     constexpr int NP = (NB + 1) / 2;
     __shared__ StarAgg<T, 2> agg;
@@ -768,7 +796,12 @@ __global__ void __launch_bounds__(kTile) k_flux_more(const RecParams<T> p) {
             const DevOpts<T> o = p.o;
             const T* __restrict__ srow = p.stars + (int64_t)slot * kStarStride;
             ModelRegs<T, NB> m;
-            load_model_row<T, NB>(p.rows + (int64_t)pl.model[q] * row_stride(NB), o, m);
+            {
+                const int64_t i = pl.model[q];
+                T A0, R0;
+                init_point<T, INIT>(o, p.av_init, p.rv_init, i, A0, R0);
+                load_model_row<T, NB>(p.rows + i * row_stride(NB), A0, R0, m);
+            }
             const T c = srow[SR_SC + SC_MBAR] - m.bbar;
             T A = pl.av[q], rho = pl.rv[q], eta = pl.eta[q], lold = pl.lold[q];
             P2<T> e[NP], r[NP];
@@ -795,30 +828,36 @@ __global__ void __launch_bounds__(kTile) k_flux_more(const RecParams<T> p) {
 template <typename T, int NB> void launch_kprobe(const ProbeParams<T>& p, cudaStream_t st) {
     const int64_t ntile = p.npad / kTile;
     dim3 grid((unsigned)((ntile + p.tile_stride - 1) / p.tile_stride), (unsigned)((p.nstar + kStarChunk - 1) / kStarChunk));
-    k_kprobe<T, NB><<<grid, kTile, 0, st>>>(p);
+    if (p.av_init) k_kprobe<T, NB, true><<<grid, kTile, 0, st>>>(p);
+    else k_kprobe<T, NB, false><<<grid, kTile, 0, st>>>(p);
 }
-template <typename T, int NB> int launch_sweep(const SweepParams<T>& p, cudaStream_t st) {
+template <typename T, int NB, bool INIT> int launch_sweep_(const SweepParams<T>& p, cudaStream_t st) {
     static bool configured[64] = {};   // per device: dynamic shared memory above 48 KB needs an opt-in
     int dev = 0;
     cudaGetDevice(&dev);
     constexpr size_t bytes = SweepSmem<T, NB>::bytes;
     if (dev < 64 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_sweep<T, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        cudaError_t e = cudaFuncSetAttribute(k_sweep<T, NB, INIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return (int)e;
         configured[dev] = true;
     }
     dim3 grid((unsigned)(p.npad / kTile), (unsigned)((p.nlist + kStarChunk - 1) / kStarChunk));
-    k_sweep<T, NB><<<grid, kTile, bytes, st>>>(p);
+    k_sweep<T, NB, INIT><<<grid, kTile, bytes, st>>>(p);
     return (int)cudaSuccess;
+}
+template <typename T, int NB> int launch_sweep(const SweepParams<T>& p, cudaStream_t st) {
+    return p.av_init ? launch_sweep_<T, NB, true>(p, st) : launch_sweep_<T, NB, false>(p, st);
 }
 template <typename T, int NB> void launch_fixup(const RecParams<T>& p, cudaStream_t st) {
     if (p.n <= 0) return;
-    k_fixup<T, NB><<<(unsigned)((p.n + kTile - 1) / kTile), kTile, 0, st>>>(p);
+    if (p.av_init) k_fixup<T, NB, true><<<(unsigned)((p.n + kTile - 1) / kTile), kTile, 0, st>>>(p);
+    else k_fixup<T, NB, false><<<(unsigned)((p.n + kTile - 1) / kTile), kTile, 0, st>>>(p);
 }
 template <typename T, int NB> void launch_flux_more(const RecParams<T>& p, cudaStream_t st) {
     if (p.n <= 0) return;
     const int64_t ctas = (p.n + kTile - 1) / kTile;   // p.n: upper bound of the list length, the kernel reads *nlist
-    k_flux_more<T, NB><<<(unsigned)(ctas < kPassCtas ? ctas : kPassCtas), kTile, 0, st>>>(p);
+    if (p.av_init) k_flux_more<T, NB, true><<<(unsigned)(ctas < kPassCtas ? ctas : kPassCtas), kTile, 0, st>>>(p);
+    else k_flux_more<T, NB, false><<<(unsigned)(ctas < kPassCtas ? ctas : kPassCtas), kTile, 0, st>>>(p);
 }
 
 }  // namespace bf

@@ -61,24 +61,42 @@ def loglike(data, data_err, data_mask, mag_coeffs,
     return tuple ``(lnl, Ndim, chi2[, scale, av, rv, icov_sar])`` (float64 arrays of length
     Nmodel), same in-place clean-up of ``data_mask`` (:709) and the same ``ValueError`` (:691-693).
 
-    ``init_thresh=None`` keeps every model in the flux-space refinement (:769-775).  ``av_init``/``rv_init`` other
-    than the defaults (the prior means, :700-703) are not supported by the kernels.  ``precision`` selects float32
-    (throughput) or float64 (verification) math.
+    ``init_thresh=None`` keeps every model in the flux-space refinement (:769-775).  ``av_init``/``rv_init`` (per-model
+    start of the magnitude fit, default the prior means, :700-703) are staged on the device for this call
+    (``bf_set_init``).  ``precision`` selects float32 (throughput) or float64 (verification) math.
     """
     if init_thresh is not None and init_thresh > ltol_subthresh:
         raise ValueError("The initial threshold must be smaller than or equal "
                          "to the final threshold applied to be useful!")
-    if av_init is not None or rv_init is not None:
-        raise NotImplementedError("av_init/rv_init must be None (prior means are used)")
+    if av_gauss is None:   # :695-696
+        av_gauss = (0., 1e6)
+    custom_init = av_init is not None or rv_init is not None
+    if custom_init:   # :700-703: a missing one defaults to its prior mean
+        nmodel = mag_coeffs.shape[0]
+        a0 = np.zeros(nmodel) + av_gauss[0] if av_init is None else np.asarray(av_init, dtype=np.float64)
+        r0 = np.zeros(nmodel) + rv_gauss[0] if rv_init is None else np.asarray(rv_init, dtype=np.float64)
+        if a0.shape != (nmodel,) or r0.shape != (nmodel,):
+            raise ValueError("av_init and rv_init must have shape (Nmodel,)")
     h = get_handle(mag_coeffs, precision=precision, device=device)
+    if custom_init:
+        h.set_init(a0, r0)
     opts = _lib.make_options(avlim=avlim, av_gauss=av_gauss, rvlim=rvlim, rv_gauss=rv_gauss,
                              dim_prior=dim_prior, ltol=ltol, ltol_subthresh=ltol_subthresh,
                              init_thresh=0. if init_thresh is None else init_thresh)
     par = np.nan if parallax is None or parallax_err is None else float(parallax)
     perr = np.nan if parallax is None or parallax_err is None else float(parallax_err)
-    lnl, chi2, sc, av, rv, icov, mclean, diag = h.loglike_full(
-        data, data_err, data_mask, par, perr, opts, want_icov=return_vals)
+    try:
+        lnl, chi2, sc, av, rv, icov, mclean, diag = h.loglike_full(
+            data, data_err, data_mask, par, perr, opts, want_icov=return_vals)
+    finally:
+        if custom_init:
+            h.set_init()
     data_mask[...] = mclean  # brutus/fitting.py:709 mutates the caller's mask
+    # The reference fits IN the caller's av_init / rv_init arrays (:202, :232) and returns them as av / rv (:809):
+    # after the call they hold the fitted values.  Mirrored for float64 arrays (anything else the reference copies).
+    for given, fitted in ((av_init, av), (rv_init, rv)):
+        if isinstance(given, np.ndarray) and given.dtype == np.float64 and given.flags.writeable:
+            given[...] = fitted
     out = (lnl, int(diag[0]), chi2)
     if return_vals:
         out = out + (sc, av, rv, icov)

@@ -136,6 +136,12 @@ int bf_set_grid_device(bf_handle* h, const void* d_coeffs, int64_t nmodel, int32
  * labels[l*nmodel + i], float64. */
 int bf_set_labels(bf_handle* h, const double* labels, int32_t nlabel);
 
+/* av_init / rv_init of loglike (brutus/fitting.py:583, :700-703): where the magnitude fit of each model starts
+ * (float64 [nmodel] each).  Staged once; in effect for every later bf_loglike_full on the handle until cleared with
+ * (NULL, NULL) or until the grid is replaced.  The default -- the prior means av_gauss[0], rv_gauss[0] -- is what
+ * BruteForce.fit always uses (:1983-1992), so the batch calls ignore these arrays. */
+int bf_set_init(bf_handle* h, const double* av_init, const double* rv_init);
+
 /* B1: one star, full-length outputs -- the contract of
  *   loglike(data, data_err, data_mask, mag_coeffs, ..., return_vals=True)  (brutus/fitting.py:579-820)
  * flux/err: nfilt float64; mask: nfilt uint8 (NOT modified; mask_clean_out receives the cleaned mask

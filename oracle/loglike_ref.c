@@ -114,10 +114,11 @@ static double chisquare_logpdf(double x, double df) {
  *             (tests: float32 kernels may flip models within rounding of that threshold)
  * returns 0, or -1 on the ValueError of :691-693, -2 on allocation failure.
  */
-int brutus_ref_loglike(const double *data, const double *err, uint8_t *mask_io, int nfilt,
-                       const float *coeffs, int64_t nmodel, const ref_options *o, double parallax,
-                       double parallax_err, double *lnl, double *chi2, double *scale, double *av,
-                       double *rv, double *icov, int64_t *diag, uint8_t *surv_out, double *lnlp_out) {
+static int loglike_impl(const double *data, const double *err, uint8_t *mask_io, int nfilt,
+                        const float *coeffs, int64_t nmodel, const ref_options *o, double parallax,
+                        double parallax_err, const double *av_init, const double *rv_init, double *lnl,
+                        double *chi2, double *scale, double *av, double *rv, double *icov, int64_t *diag,
+                        uint8_t *surv_out, double *lnlp_out) {
     if (o->init_thresh > o->ltol_subthresh) return -1; /* :691-693 */
     const int max_iter = o->max_iter > 0 ? o->max_iter : 1000;
 
@@ -168,10 +169,10 @@ int brutus_ref_loglike(const double *data, const double *err, uint8_t *mask_io, 
             for (int c = 0; c < 3; c++)
                 mco[((size_t)i * nb + k) * 3 + c] = coeffs[((size_t)i * nfilt + band[k]) * 3 + c];
 
-    /* initial magnitudes at (av_init, rv_init) = prior means (:700-703, :728-733) */
+    /* initial magnitudes at (av_init, rv_init), by default the prior means (:700-703, :728-733) */
     for (int64_t i = 0; i < nmodel; i++) {
-        av[i] = 0. + o->av_gauss[0];
-        rv[i] = 0. + o->rv_gauss[0];
+        av[i] = av_init ? av_init[i] : 0. + o->av_gauss[0];
+        rv[i] = rv_init ? rv_init[i] : 0. + o->rv_gauss[0];
         double sed[64];
         get_seds_one(mco + (size_t)i * nb * 3, nb, av[i], rv[i], 0, sed, rvecs + (size_t)i * nb,
                      drvecs + (size_t)i * nb);
@@ -385,6 +386,24 @@ int brutus_ref_loglike(const double *data, const double *err, uint8_t *mask_io, 
     if (diag) { diag[0] = Ndim; diag[1] = n_mag; diag[2] = n_flux; diag[3] = nsel; }
     free(icov_new); free(sel); free(mco); free(resid); free(rvecs); free(drvecs); free(wk);
     return 0;
+}
+
+int brutus_ref_loglike(const double *data, const double *err, uint8_t *mask_io, int nfilt,
+                       const float *coeffs, int64_t nmodel, const ref_options *o, double parallax,
+                       double parallax_err, double *lnl, double *chi2, double *scale, double *av,
+                       double *rv, double *icov, int64_t *diag, uint8_t *surv_out, double *lnlp_out) {
+    return loglike_impl(data, err, mask_io, nfilt, coeffs, nmodel, o, parallax, parallax_err, NULL, NULL, lnl,
+                        chi2, scale, av, rv, icov, diag, surv_out, lnlp_out);
+}
+
+/* the same with the caller's per-model av_init / rv_init (nmodel each; NULL = the prior mean, :700-703) */
+int brutus_ref_loglike_init(const double *data, const double *err, uint8_t *mask_io, int nfilt,
+                            const float *coeffs, int64_t nmodel, const ref_options *o, double parallax,
+                            double parallax_err, const double *av_init, const double *rv_init, double *lnl,
+                            double *chi2, double *scale, double *av, double *rv, double *icov,
+                            int64_t *diag, uint8_t *surv_out, double *lnlp_out) {
+    return loglike_impl(data, err, mask_io, nfilt, coeffs, nmodel, o, parallax, parallax_err, av_init, rv_init,
+                        lnl, chi2, scale, av, rv, icov, diag, surv_out, lnlp_out);
 }
 
 /*

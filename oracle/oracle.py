@@ -38,6 +38,10 @@ def _load():
         lib.brutus_ref_loglike.argtypes = [dp, dp, u8p, C.c_int, fp, C.c_int64,
                                            C.POINTER(RefOptions), C.c_double, C.c_double,
                                            dp, dp, dp, dp, dp, dp, i64p, u8p, dp]
+        lib.brutus_ref_loglike_init.restype = C.c_int
+        lib.brutus_ref_loglike_init.argtypes = [dp, dp, u8p, C.c_int, fp, C.c_int64,
+                                                C.POINTER(RefOptions), C.c_double, C.c_double, dp, dp,
+                                                dp, dp, dp, dp, dp, dp, i64p, u8p, dp]
         lib.brutus_ref_select.restype = C.c_int64
         lib.brutus_ref_select.argtypes = [C.c_int64, dp, dp, dp, C.c_int, C.c_double, C.c_double,
                                           C.c_int, dp, dp, dp, C.c_double, dp, u8p]
@@ -68,7 +72,7 @@ def make_options(avlim=(0., 20.), av_gauss=(0., 1e6), rvlim=(1., 8.), rv_gauss=(
 
 
 def loglike(data, data_err, data_mask, mag_coeffs, parallax=None, parallax_err=None,
-            return_vals=False, return_diag=False, **kwargs):
+            return_vals=False, return_diag=False, av_init=None, rv_init=None, **kwargs):
     """Same contract as the reference ``loglike`` (brutus/fitting.py:579): returns
     ``(lnl, Ndim, chi2[, scale, av, rv, icov_sar])`` and cleans ``data_mask`` in place."""
     lib = _load()
@@ -88,9 +92,13 @@ def loglike(data, data_err, data_mask, mag_coeffs, parallax=None, parallax_err=N
     diag = np.zeros(4, dtype=np.int64)
     surv = np.zeros(n, dtype=np.uint8)
     lnlp = np.zeros(n)
-    rc = lib.brutus_ref_loglike(_p(d, C.c_double), _p(e, C.c_double), _p(m, C.c_uint8), nf,
-                                _p(co, C.c_float), n, C.byref(o), par, perr,
-                                _p(lnl, C.c_double), _p(chi2, C.c_double), _p(sc, C.c_double),
+    a0 = None if av_init is None else np.ascontiguousarray(av_init, dtype=np.float64)
+    r0 = None if rv_init is None else np.ascontiguousarray(rv_init, dtype=np.float64)
+    rc = lib.brutus_ref_loglike_init(_p(d, C.c_double), _p(e, C.c_double), _p(m, C.c_uint8), nf,
+                                     _p(co, C.c_float), n, C.byref(o), par, perr,
+                                     None if a0 is None else _p(a0, C.c_double),
+                                     None if r0 is None else _p(r0, C.c_double),
+                                     _p(lnl, C.c_double), _p(chi2, C.c_double), _p(sc, C.c_double),
                                 _p(av, C.c_double), _p(rv, C.c_double), _p(icov, C.c_double),
                                 _p(diag, C.c_int64), _p(surv, C.c_uint8), _p(lnlp, C.c_double))
     if rc:

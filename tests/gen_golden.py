@@ -41,6 +41,9 @@ LOGLIKE_CASES = {
     "loose_tol": dict(grid=dict(nmodel=2_000, nfilt=6, seed=1013),
                       stars=dict(nstar=3, seed=2013, snr_range=(5., 20.)),
                       kw=dict(ltol=1e-3, ltol_subthresh=5e-2, init_thresh=1e-4)),
+    # caller-supplied per-model start of the magnitude fit (brutus/fitting.py:583, :700-703)
+    "av_rv_init": dict(grid=dict(nmodel=2_000, nfilt=7, seed=1015, kind="locus"),
+                       stars=dict(nstar=4, seed=2015, dropout=0.1), kw={}, init=dict(seed=3015)),
 }
 
 
@@ -50,7 +53,12 @@ def build_case(name):
     st = mock.make_stars(grid, **spec["stars"])
     for (i, j) in spec.get("negflux", []):
         st["flux"][i, j] = -0.1 * abs(st["flux"][i, j])
-    return grid, labels, st, spec["kw"]
+    kw = dict(spec["kw"])
+    if "init" in spec:
+        rs = np.random.RandomState(spec["init"]["seed"])
+        kw["av_init"] = rs.uniform(0., 3., grid.shape[0])
+        kw["rv_init"] = rs.uniform(2.6, 4.2, grid.shape[0])
+    return grid, labels, st, kw
 
 
 def gen_loglike(fit, only=None):
@@ -62,10 +70,16 @@ def gen_loglike(fit, only=None):
         out = {}
         for i in range(len(st["flux"])):
             m = st["mask"][i].copy()
+            # array-valued keywords (av_init, rv_init) are the reference's working arrays: it updates them in place and
+            # returns them as av / rv (brutus/fitting.py:202, :232, :809), so every star gets fresh copies
+            kwi = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in kw.items()}
             r = fit.loglike(st["flux"][i], st["err"][i], m, gF, return_vals=True,
-                            parallax=st["parallax"][i], parallax_err=st["parallax_err"][i], **kw)
+                            parallax=st["parallax"][i], parallax_err=st["parallax_err"][i], **kwi)
             for key, val in zip(("lnl", "ndim", "chi2", "scale", "av", "rv", "icov"), r):
-                out["%s_%d" % (key, i)] = np.asarray(val)
+                out["%s_%d" % (key, i)] = np.array(val)
+            for k, v in kwi.items():
+                if isinstance(v, np.ndarray):
+                    out["%s_after_%d" % (k, i)] = v
             out["mask_%d" % i] = m
         np.savez_compressed(os.path.join(GOLD, "loglike_%s.npz" % name), **out)
         print("wrote", name)

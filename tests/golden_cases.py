@@ -13,6 +13,12 @@ build_case = gen_golden.build_case
 KEYS = ("lnl", "ndim", "chi2", "scale", "av", "rv", "icov")
 
 
+def fresh(kw):
+    """Copies of the array-valued keywords (av_init, rv_init): loglike fits IN those arrays (brutus/fitting.py:202,
+    :232, :809), so every call gets its own."""
+    return {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in kw.items()}
+
+
 def load_loglike(name):
     return np.load(os.path.join(GOLD, "loglike_%s.npz" % name))
 

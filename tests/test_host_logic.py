@@ -66,8 +66,8 @@ def test_loglike_argument_errors():
     st = mock.make_stars(grid, 1, seed=6)
     with pytest.raises(ValueError, match="initial threshold"):    # brutus/fitting.py:691-693
         fitting.loglike(st["flux"][0], st["err"][0], st["mask"][0].copy(), grid, init_thresh=0.5)
-    with pytest.raises(NotImplementedError):
-        fitting.loglike(st["flux"][0], st["err"][0], st["mask"][0].copy(), grid, av_init=np.zeros(200))
+    with pytest.raises(ValueError, match="av_init"):              # one start value per model (:700-703)
+        fitting.loglike(st["flux"][0], st["err"][0], st["mask"][0].copy(), grid, av_init=np.zeros(199))
 
 
 def test_imf_prior_is_normalised_and_broken_at_half_a_solar_mass():

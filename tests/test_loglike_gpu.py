@@ -76,8 +76,13 @@ def _run_case(fitting, oracle_mod, name, precision):
         args = (st["flux"][i], st["err"][i])
         pk = dict(parallax=st["parallax"][i], parallax_err=st["parallax_err"][i])
         m = st["mask"][i].copy()
+        kwi = gc.fresh(kw)
         out = fitting.loglike(*args, m, grid, return_vals=True, precision=precision,
-                              return_diag=True, **pk, **kw)
+                              return_diag=True, **pk, **kwi)
+        for k in ("av_init", "rv_init"):   # the reference leaves the fitted values in the caller's arrays
+            if k in kwi:
+                assert np.array_equal(kwi[k], out[4 if k == "av_init" else 5]), (name, i, k)
+                assert np.allclose(kwi[k], gold["%s_after_%d" % (k, i)], rtol=0, atol=1e-8 if precision == "f64" else 1e-2)
         orc = oracle_mod.loglike(*args, st["mask"][i].copy(), grid, return_vals=True,
                                  return_diag=True, **pk, **kw)
         assert np.array_equal(m, gold["mask_%d" % i])
@@ -131,3 +136,27 @@ def test_threshold_valueerror(fitting):
     with pytest.raises(ValueError):
         fitting.loglike(st["flux"][0], st["err"][0], st["mask"][0].copy(), grid,
                         init_thresh=0.5, ltol_subthresh=1e-2)
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_rv_init_only_and_default_restored(fitting, oracle_mod, precision):
+    """rv_init alone (av_init then defaults to the prior mean, brutus/fitting.py:700-703) against the oracle, and the
+    cached handle goes back to the default start afterwards."""
+    grid, labels = mock.make_grid(6_000, 8, seed=1210, kind="locus")
+    st = mock.make_stars(grid, 2, seed=2210)
+    rv0 = np.random.RandomState(7).uniform(2.5, 4.5, grid.shape[0])
+    for i in range(2):
+        pk = dict(parallax=st["parallax"][i], parallax_err=st["parallax_err"][i])
+        args = (st["flux"][i], st["err"][i])
+        base = fitting.loglike(*args, st["mask"][i].copy(), grid, return_vals=True, precision=precision, **pk)
+        out = fitting.loglike(*args, st["mask"][i].copy(), grid, return_vals=True, precision=precision,
+                              return_diag=True, rv_init=rv0.copy(), av_gauss=(0.3, 2.0), **pk)
+        orc = oracle_mod.loglike(*args, st["mask"][i].copy(), grid, return_vals=True, return_diag=True,
+                                 rv_init=rv0.copy(), av_gauss=(0.3, 2.0), **pk)
+        tag = ("rv_init", i, precision)
+        assert out[7]["n_iter_mag"] == orc[7]["n_iter_mag"], tag
+        assert out[7]["n_iter_flux"] == orc[7]["n_iter_flux"], tag
+        (_compare_f64 if precision == "f64" else _compare_f32)(out[:7], orc[:7], tag)
+        again = fitting.loglike(*args, st["mask"][i].copy(), grid, return_vals=True, precision=precision, **pk)
+        for a, b in zip(base, again):
+            assert np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True), tag
