@@ -142,7 +142,7 @@ def test_threshold_valueerror(fitting):
 def test_rv_init_only_and_default_restored(fitting, oracle_mod, precision):
     """rv_init alone (av_init then defaults to the prior mean, brutus/fitting.py:700-703) against the oracle, and the
     cached handle goes back to the default start afterwards."""
-    grid, labels = mock.make_grid(6_000, 8, seed=1210, kind="locus")
+    grid, labels = mock.make_grid(40_000, 8, seed=1210, kind="locus")   # >= 32 768 models: the iteration-count probe runs too
     st = mock.make_stars(grid, 2, seed=2210)
     rv0 = np.random.RandomState(7).uniform(2.5, 4.5, grid.shape[0])
     for i in range(2):
