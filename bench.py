@@ -361,6 +361,7 @@ def run_b200(args):
         for k, v in st.items():
             agg[k] = agg.get(k, 0) + v
     barrier()
+    n_iter_val, n_surv_val = np.array(res["n_iter"]), np.array(res["n_surv"])   # of the last device-timed step
     if tracing:   # per-kernel CUDA-event times of the device-timed steps (stderr; the JSON line stays alone on stdout)
         for name, (cnt, ms) in sorted(h.trace().items(), key=lambda kv: -kv[1][1]):
             sys.stderr.write("trace value-steps  %-22s %6d launches %10.3f ms/step\n" % (name, cnt, ms / args.steps))
@@ -419,6 +420,15 @@ def run_b200(args):
                  "warp_inst_per_32_pairs": wi, "achieved_ginst_s": g / 1e9,
                  "peak_ginst_s": 148 * 4 * clocks["sm_mhz"] * 1e6 / 1e9,
                  "frac": g / (148 * 4 * clocks["sm_mhz"] * 1e6)}
+    # algorithmic flop-instructions per star = Nmodel x Nb x (5 + 15 K_mag + 35 + Nsurv/Nmodel x 43 K_flux),
+    # with the iteration counts and survivor fractions the stars of this rank actually had (Nb taken as Nfilt)
+    k_mag, k_flux = n_iter_val[:, 0].astype(float), n_iter_val[:, 1].astype(float)
+    flop_star = cfg["nmodel"] * cfg["nfilt"] * (5. + 15. * k_mag + 35. + n_surv_val / cfg["nmodel"] * 43. * k_flux)
+    algo_flop = {"per_star_mean": float(flop_star.mean()), "k_mag_mean": float(k_mag.mean()), "k_flux_mean": float(k_flux.mean()),
+                 "survivor_frac_mean": float(n_surv_val.mean() / cfg["nmodel"]),
+                 "achieved_tflop_instr_s": float(flop_star.mean()) * (loc_stars / ndev) / (agg["ms_device"] * 1e-3) / 1e12,
+                 "note": "flop-instructions of the reference's arithmetic (an FMA counts once) over the whole device step, per GPU; "
+                         "a B200 issues 148 SM x 128 FP32 lanes x ~1.9 GHz = 36 T lane-instructions/s"}
     line = {
         "metric": METRIC, "value": value, "unit": "stars/s", "n_gpus": ngpu, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -458,6 +468,7 @@ def run_b200(args):
                              "traffic (`traffic`, ncu, per launch) is far below the algorithmic bytes: the kernel is "
                              "bound by FP32 issue / the FMA pipe (`issue`), DESIGN.md section 5",
                      "issue": issue,
+                     "algorithmic_flop_instr": algo_flop,
                      "kernel_share_of_step": agg["ms_magfit"] / agg["ms_device"],
                      "launches": int(agg["magfit_launches"]),
                      "ms_per_launch": agg["ms_magfit"] / launches},

@@ -44,6 +44,8 @@ def test_b200_arm_line():
     r = d["roofline"]
     assert r["bound"] in ("hbm", "tensor") and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert r["limiter"] == "fp32-issue" and 0 < r["step_frac"] <= r["frac"] <= r["frac_per_pass"]
+    af = r["algorithmic_flop_instr"]
+    assert af["per_star_mean"] > 0 and af["k_mag_mean"] >= 1 and af["k_flux_mean"] >= 2 and 0 < af["survivor_frac_mean"] <= 1
     assert d["config"] == _run(["--impl", "reference", "--config", "1", "--steps", "1", "--warmup", "0"])["config"]
     assert d["e2e_fit_api"]["value"] > 0 and d["cpu_baseline"]["one_core"]["cores"] == 1
     c = d["cpu_baseline"]
