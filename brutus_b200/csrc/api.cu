@@ -772,6 +772,8 @@ template <typename T> struct Engine : EngineBase {
     bool have_prior[3] = {false, false, false};   // lnprior, feh, loga staged?
     DevBuf<T> d_av_init, d_rv_init;               // per-model start of the magnitude fit (bf_set_init), [npad]
     bool have_init = false, use_init = false;     // staged? / in effect for the launches of the current call (B1 only)
+    bool presweep_cfg = true, presweep = true;    // sweeps in two launches (see process_group; BRUTUS_B200_PRESWEEP=0 turns it
+                                                  // off for A/B measurements); off for B1, where every model is a candidate
     DevBuf<T> d_lnprior, d_feh, d_loga, d_lnp1, d_lnp2, d_lnb1, d_keys, d_keys_sorted, d_clip;
     DevBuf<int> d_seg;
     DevBuf<char> d_cubtmp;
@@ -894,6 +896,7 @@ template <typename T> struct Engine : EngineBase {
             CK(cudaEventCreateWithFlags(&ev_cp[k], cudaEventDisableTiming));
         }
         if (const char* e = getenv("BRUTUS_B200_TRACE")) trace_on = atoi(e) != 0;
+        if (const char* e = getenv("BRUTUS_B200_PRESWEEP")) presweep_cfg = presweep = atoi(e) != 0;
         CK(h_ctr.resize(CTR_COUNT));
         CK(d_ctr.ensure(CTR_COUNT));
         CK(d_tot.ensure(2));
@@ -1130,11 +1133,36 @@ template <typename T> struct Engine : EngineBase {
                 sp.pool = pl; sp.pool_cap = pool_cap; sp.pool_count = (unsigned long long*)(d_ctr.p + CTR_POOL);
                 sp.nit_first = nit_first;
                 sp.av_init = use_init ? d_av_init.p : nullptr; sp.rv_init = use_init ? d_rv_init.p : nullptr;
+                // A candidate is flagged against the maxima known when its CTA starts, so the sweep is issued in two
+                // launches: a strided subsample of the model tiles first, then the rest -- every CTA of the second
+                // launch starts from the maxima of the first, whatever the order of the grid (an ordered lattice keeps
+                // its best models in a few tiles).  On a small grid a wave of CTAs covers every tile of a star chunk
+                // and nothing is published in time: there the grid is swept twice, first for the maxima alone
+                // (cheap: the grid is L2-resident and the work is in the candidates' dense phase).  With every model a
+                // candidate anyway (B1, a star redone after a fallback) one plain launch does.
+                const int64_t ntile = npad / kTile;
+                int nlaunch = 1;
                 phase_begin();
-                { TRACE("k_sweep"); CK((cudaError_t)kt->sweep(sp, stream)); }
+                if (!presweep || ntile < 2) {
+                    sp.tile_mode = 0; sp.tile_S = 1; sp.maxima_only = 0;
+                    { TRACE("k_sweep"); CK((cudaError_t)kt->sweep(sp, stream)); }
+                } else if (ntile < 1024) {
+                    nlaunch = 2;
+                    sp.tile_mode = 0; sp.tile_S = 1; sp.maxima_only = 1;
+                    { TRACE("k_sweep_maxima"); CK((cudaError_t)kt->sweep(sp, stream)); }
+                    sp.maxima_only = 0;
+                    { TRACE("k_sweep"); CK((cudaError_t)kt->sweep(sp, stream)); }
+                } else {
+                    nlaunch = 2;
+                    sp.tile_S = (int)std::min<int64_t>(32, std::max<int64_t>(2, ntile / 128)); sp.maxima_only = 0;
+                    sp.tile_mode = 1;
+                    { TRACE("k_sweep"); CK((cudaError_t)kt->sweep(sp, stream)); }
+                    sp.tile_mode = 2;
+                    { TRACE("k_sweep"); CK((cudaError_t)kt->sweep(sp, stream)); }
+                }
                 CK(cudaGetLastError());
                 CK(cudaEventRecord(evB, stream));
-                stats.kernel_launches++; stats.magfit_launches++; stats.magfit_star_passes += nl;
+                stats.kernel_launches += nlaunch; stats.magfit_launches += nlaunch; stats.magfit_star_passes += nl;
                 publish(h_red.data(), d_red.p, (size_t)ns * kNumRed * sizeof(U));
                 publish(h_ctr.data(), d_ctr.p, CTR_COUNT * sizeof(int));
                 CK(sync());
@@ -1344,11 +1372,13 @@ template <typename T> struct Engine : EngineBase {
         std::vector<char> exact(1, 0);
         CK(cudaEventRecord(ev0, stream));
         use_init = have_init;   // av_init / rv_init of loglike (brutus/fitting.py:700-703): this entry point only
+        presweep = false;
         if (!rc) rc = probe_k(1, o, max_iter);
         int64_t tot = 0;
         bool fits = true;
         if (!rc) rc = process_group(1, 0, 1, o, max_iter, exact, &nm, &fits, &tot);
         use_init = false;
+        presweep = presweep_cfg;
         nlabel = saved_labels;
         if (rc) return rc;
         if (!fits) { err = "bf_loglike_full: candidate pool too small for one star"; return BF_E_NOMEM; }

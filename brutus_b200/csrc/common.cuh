@@ -439,6 +439,9 @@ template <typename T> struct SweepParams {
     int nit_first;            // flux iterations the sweep runs on likely survivors: min(2, max_iter)
     const T* av_init;         // [npad] per-model start of the magnitude fit (brutus/fitting.py:700-703), or both null:
     const T* rv_init;         // the prior means (every caller but bf_loglike_full after bf_set_init)
+    int tile_mode;            // which model tiles the launch covers: 0 all, 1 the multiples of tile_S, 2 the others
+    int tile_S;               // >= 2 when tile_mode != 0
+    int maxima_only;          // 1: only the per-star maxima are produced (no candidates, no records)
 };
 
 // passes over the n records of the pool that need the model's coefficients again (both rare)

@@ -481,7 +481,7 @@ template <typename T, int NB> struct SweepSmem {
     static constexpr size_t off_red = off_qkey + sizeof(uint32_t) * kQueue;   // [warp][star][kSweepRed] of T
     static constexpr size_t off_snap = off_red + sizeof(T) * (kTile / 32) * kStarChunk * kSweepRed;
     static constexpr size_t off_int = off_snap + sizeof(T) * kStarChunk * 2;
-    static constexpr size_t off_bal = off_int + sizeof(int) * (kStarChunk * 3 + 4 + 2 * (kTile / 32));   // + queue tail, head, warp counts
+    static constexpr size_t off_bal = off_int + sizeof(int) * (kStarChunk * 3 + 4 + 2 * (kTile / 32) + 4);   // + queue tail, head, warp counts, tile
     static constexpr size_t bytes = off_bal + sizeof(uint32_t) * kStarChunk * (kTile / 32);             // candidate words [star][warp]
 };
 
@@ -493,7 +493,7 @@ __device__ __forceinline__ void dense_flush(const SweepParams<T>& p, const DevOp
                                             const float* __restrict__ s_tile, const int* __restrict__ s_tag,
                                             const T* __restrict__ q_av, const T* __restrict__ q_rv,
                                             const T* __restrict__ q_lp, const uint32_t* __restrict__ q_key, int* s_head,
-                                            int n, unsigned long long* s_base) {
+                                            int n, unsigned long long* s_base, const int* s_tileid) {
     constexpr int NP = (NB + 1) / 2;
     constexpr int RS = tile_stride(NB);
     const bool act = (int)threadIdx.x < n;
@@ -518,7 +518,7 @@ __device__ __forceinline__ void dense_flush(const SweepParams<T>& p, const DevOp
     const PoolArrays<T>& pl = p.pool;
     const bool wr = act && q < p.pool_cap;
     if (wr) {   // what is known already goes out first (coalesced stores of the warp's records): fewer live registers below
-        pl.model[q] = (int)(blockIdx.x * kTile + ml);
+        pl.model[q] = *s_tileid * kTile + ml;
         pl.sflag[q] = s_tag[s] | (fluxed ? kFlagFluxed << 24 : 0);
         pl.lp[q] = lp;
         pl.lnl[q] = A; pl.lnprob[q] = rho;   // the magnitude fit, kept for k_fixup until k_final overwrites it
@@ -527,7 +527,7 @@ __device__ __forceinline__ void dense_flush(const SweepParams<T>& p, const DevOp
     ModelRegs<T, NB> m;
     {
         T A0, R0;
-        init_point<T, INIT>(o, p.av_init, p.rv_init, (int64_t)blockIdx.x * kTile + ml, A0, R0);
+        init_point<T, INIT>(o, p.av_init, p.rv_init, (int64_t)*s_tileid * kTile + ml, A0, R0);
         load_model_row<T, NB>(s_tile + ml * RS, A0, R0, m);
     }
     const T c = srow[SR_SC + SC_MBAR] - m.bbar;
@@ -582,6 +582,7 @@ __global__ void __launch_bounds__(kTile, (sweep_min_ctas<T, NB>())) k_sweep(cons
     int* s_head = s_qtot + 1;                                              // ring position of the oldest queued entry
     unsigned long long* s_base = reinterpret_cast<unsigned long long*>(s_qtot + 2);   // pool position of the flush
     int* s_wc = s_qtot + 4;                                                // [2][8]: candidates per warp since the last meeting
+    int* s_tileid = s_wc + 2 * (kTile / 32);                               // the CTA's model tile (kept out of the registers)
     uint32_t* s_bal = reinterpret_cast<uint32_t*>(smem + SM::off_bal);     // [32][8]: the candidate map words of this CTA
 
     const int first = blockIdx.y * kStarChunk;
@@ -601,12 +602,25 @@ __global__ void __launch_bounds__(kTile, (sweep_min_ctas<T, NB>())) k_sweep(cons
         const volatile U* rr = p.red + (int64_t)slot * kNumRed;
         s_snap[2 * t] = Enc<T>::dec(rr[RED_LP]);
         s_snap[2 * t + 1] = Enc<T>::dec(rr[RED_M0]);
+        // a maxima-only launch flags nothing: thresholds of +inf (no test in the star loop)
+        if (p.maxima_only) s_snap[2 * t] = s_snap[2 * t + 1] = -Num<T>::neg_inf();
     }
 
-    const int64_t i = (int64_t)blockIdx.x * kTile + threadIdx.x;  // npad is a multiple of kTile
+    // The model tile of this CTA.  A sweep is two launches: first the tiles that are multiples of tile_S -- a strided
+    // subsample of the grid -- then the rest, whose CTAs all start from the per-star maxima the first launch published
+    // (s_snap above): the running thresholds are tight from the first CTA on, whatever the order of the grid.  Small
+    // grids (a CTA wave covers every tile of a star chunk, so nothing is published in time) are instead swept twice,
+    // first in maxima-only mode (tile_mode 0 both times).
+    const int tile = p.tile_mode == 0 ? (int)blockIdx.x
+                   : p.tile_mode == 1 ? (int)blockIdx.x * p.tile_S
+                                      : (int)blockIdx.x + (int)blockIdx.x / (p.tile_S - 1) + 1;
+    if (threadIdx.x == 0) *s_tileid = tile;                 // read back where it is needed again (dense phase, map)
+    const int64_t i = (int64_t)tile * kTile + threadIdx.x;  // npad is a multiple of kTile
     // padding models exist in the last tile only; a CTA-uniform count keeps the per-star test to one compare
-    const int nvalid = (int)(p.nmodel - (int64_t)blockIdx.x * kTile < (int64_t)kTile ? p.nmodel - (int64_t)blockIdx.x * kTile : (int64_t)kTile);
-    const bool valid = (int)threadIdx.x < nvalid;
+    const int nvalid = (int)(p.nmodel - (int64_t)tile * kTile < (int64_t)kTile ? p.nmodel - (int64_t)tile * kTile : (int64_t)kTile);
+    // the bound is re-read from shared memory in the star loop (one LDS + compare): held as a predicate across the
+    // loop it is spilled through a register to local memory
+    if (threadIdx.x == 0) s_tileid[1] = nvalid;
     const DevOpts<T> o = p.o;
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     float* tile_w = s_tile + wrp * 32 * RS;                         // this warp's 32 models
@@ -656,7 +670,7 @@ __global__ void __launch_bounds__(kTile, (sweep_min_ctas<T, NB>())) k_sweep(cons
         const T thr1 = Num<T>::max(s_snap[2 * s], lpm) + ln_init_c;
         const T thr2 = Num<T>::max(s_snap[2 * s + 1], lqm) + o.ln_wt - srow[SR_SC + SC_SLACK];
         const bool likely = lp > thr1;                              // may survive the cull
-        const bool cand = valid && (likely || lq > thr2);
+        const bool cand = (int)threadIdx.x < reinterpret_cast<const volatile int*>(s_tileid)[1] && (likely || lq > thr2);
         const unsigned bal = __ballot_sync(0xffffffffu, cand);
         s_bal[s * (kTile / 32) + wrp] = bal;                        // written to the map after the star loop, a sector per star
         const int par = (s / kFlushStars) & 1;                      // parity of the warp-count buffer in use
@@ -700,18 +714,19 @@ __global__ void __launch_bounds__(kTile, (sweep_min_ctas<T, NB>())) k_sweep(cons
             if (kFlushStars > 1 && lane == 0) s_wc[(par ^ 1) * (kTile / 32) + wrp] = 0;
             if (pend >= kTile) {
                 do {
-                    dense_flush<T, NB, INIT>(p, o, s_star, s_tile, s_tag, s_qav, s_qrv, s_qlp, s_qkey, s_head, kTile, s_base);
+                    dense_flush<T, NB, INIT>(p, o, s_star, s_tile, s_tag, s_qav, s_qrv, s_qlp, s_qkey, s_head, kTile, s_base, s_tileid);
                     pend -= kTile;
                 } while (pend >= kTile);
                 load_model_row<T, NB>(tile_w + lane * RS, A0, R0, m);   // this thread's own model again
             }
         }
     }
-    if (pend > 0) dense_flush<T, NB, INIT>(p, o, s_star, s_tile, s_tag, s_qav, s_qrv, s_qlp, s_qkey, s_head, pend, s_base);
+    if (pend > 0) dense_flush<T, NB, INIT>(p, o, s_star, s_tile, s_tag, s_qav, s_qrv, s_qlp, s_qkey, s_head, pend, s_base, s_tileid);
     __syncthreads();
     // the candidate map: the CTA's 8 words of a star are one 32-byte sector
-    for (int t = threadIdx.x; t < nst * (kTile / 32); t += kTile)
-        p.cand[(int64_t)s_slot[t / (kTile / 32)] * p.nwords + (int64_t)blockIdx.x * (kTile / 32) + t % (kTile / 32)] = s_bal[t];
+    if (!p.maxima_only)
+        for (int t = threadIdx.x; t < nst * (kTile / 32); t += kTile)
+            p.cand[(int64_t)s_slot[t / (kTile / 32)] * p.nwords + (int64_t)*s_tileid * (kTile / 32) + t % (kTile / 32)] = s_bal[t];
     // combine the warps' maxima and publish them; NaN maxima (every lane NaN) must not poison the
     // unsigned-encoded atomics
     for (int t = threadIdx.x; t < nst * kSweepRed; t += kTile) {
@@ -841,7 +856,10 @@ template <typename T, int NB, bool INIT> int launch_sweep_(const SweepParams<T>&
         if (e != cudaSuccess) return (int)e;
         configured[dev] = true;
     }
-    dim3 grid((unsigned)(p.npad / kTile), (unsigned)((p.nlist + kStarChunk - 1) / kStarChunk));
+    const int64_t ntile = p.npad / kTile, nsub = p.tile_mode == 0 ? ntile : (ntile + p.tile_S - 1) / p.tile_S;
+    const int64_t nx = p.tile_mode == 2 ? ntile - nsub : nsub;
+    if (nx <= 0) return (int)cudaSuccess;
+    dim3 grid((unsigned)nx, (unsigned)((p.nlist + kStarChunk - 1) / kStarChunk));
     k_sweep<T, NB, INIT><<<grid, kTile, bytes, st>>>(p);
     return (int)cudaSuccess;
 }
