@@ -539,14 +539,35 @@ template <typename T> __global__ void __launch_bounds__(kTile) k_out_full(const 
 
 // in-place exclusive scan of n ints by one CTA; total -> *tot
 __global__ void __launch_bounds__(1024) k_scan_blocks(int* v, int64_t n, int64_t* tot) {
+    // exclusive scan of n block counts in place, one CTA, 8 consecutive entries per thread and round (the scan of the
+    // 578 k block counts of a 1 000-star batch took 0.5 ms at one entry per thread: 565 rounds of two barriers each)
+    constexpr int kPer = 8;
     __shared__ int s_w[32];
     int64_t carry = 0;
-    for (int64_t b = 0; b < n; b += 1024) {
-        int64_t t = b + threadIdx.x;
-        int x = t < n ? v[t] : 0;
+    for (int64_t b = 0; b < n; b += 1024 * kPer) {
+        const int64_t t0 = b + (int64_t)threadIdx.x * kPer;
+        int x[kPer];
+        if (t0 + kPer <= n) {
+            const int4 a = *reinterpret_cast<const int4*>(v + t0), c = *reinterpret_cast<const int4*>(v + t0 + 4);
+            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = c.x; x[5] = c.y; x[6] = c.z; x[7] = c.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < kPer; k++) x[k] = t0 + k < n ? v[t0 + k] : 0;
+        }
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < kPer; k++) { const int y = x[k]; x[k] = sum; sum += y; }   // exclusive within the thread
         int total;
-        int ex = block_exscan_1024(x, s_w, total);
-        if (t < n) v[t] = (int)(carry + ex);
+        const int ex = block_exscan_1024(sum, s_w, total);
+        const int base = (int)carry + ex;
+        if (t0 + kPer <= n) {
+            *reinterpret_cast<int4*>(v + t0) = make_int4(base + x[0], base + x[1], base + x[2], base + x[3]);
+            *reinterpret_cast<int4*>(v + t0 + 4) = make_int4(base + x[4], base + x[5], base + x[6], base + x[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kPer; k++)
+                if (t0 + k < n) v[t0 + k] = base + x[k];
+        }
         carry += total;
     }
     if (threadIdx.x == 0) *tot = carry;
