@@ -1813,6 +1813,12 @@ template <typename T> struct Engine : EngineBase {
             G.age_lnden[x] = (T)(std::log(as / 2.) + std::log(std::erf(b / std::sqrt(2.)) - std::erf(a / std::sqrt(2.))));
         }
         G.min_age = (T)g.min_age; G.max_age = (T)g.max_age;
+        const double l2e = 1.4426950408889634;
+        G.l2_iR_thin = (T)(-l2e / g.R_thin); G.l2_iZ_thin = (T)(-l2e / g.Z_thin);
+        G.l2_iR_thick = (T)(-l2e / g.R_thick); G.l2_iZ_thick = (T)(-l2e / g.Z_thick);
+        G.l2_ln_f_thick = (T)(l2e * std::log(g.f_thick)); G.l2_irq = (T)(-l2e / g.r_q_halo);
+        G.l2_halo = (T)(l2e * ((double)G.eta * (double)G.ln_Reff_solar + (double)G.ln_f_halo));
+        G.nh_eta = (T)(-0.5 * g.eta_halo);
         return G;
     }
 
@@ -1974,8 +1980,9 @@ template <typename T> struct Engine : EngineBase {
             if (n2 > 0) {
                 const unsigned nb1 = (unsigned)((n1 + kTile - 1) / kTile);
                 { TRACE("k_post_write"); k_post_write<T><<<nb1, kTile, 0, stream>>>(pp); }
-                if (pp.zov) { TRACE("k_post_mc"); k_post_mc<T, true><<<(unsigned)((n2 + kTile - 1) / kTile), kTile, 0, stream>>>(pp); }
-                else { TRACE("k_post_mc"); k_post_mc<T, false><<<(unsigned)((n2 + kTile - 1) / kTile), kTile, 0, stream>>>(pp); }
+                if (pp.zov) { TRACE("k_post_mc"); k_post_mc<T, true, false><<<(unsigned)((n2 + kTile - 1) / kTile), kTile, 0, stream>>>(pp); }
+                else if (G.same_rs) { TRACE("k_post_mc"); k_post_mc<T, false, true><<<(unsigned)((n2 + kTile - 1) / kTile), kTile, 0, stream>>>(pp); }
+                else { TRACE("k_post_mc"); k_post_mc<T, false, false><<<(unsigned)((n2 + kTile - 1) / kTile), kTile, 0, stream>>>(pp); }
                 stats.kernel_launches += 2;
             }
             { TRACE("k_post_cdf"); k_post_cdf<T><<<ng, 1024, 0, stream>>>(pp); }

@@ -144,6 +144,10 @@ template <typename T> struct GalDev {
     T feh_mu[3], feh_isig2[3], feh_lnorm[3];  // thin, thick, halo                (:380-408)
     T age_mu[3], age_isig[3], age_lnden[3];   // truncated normals                (:455-470, brutus/utils.py:232-284)
     T min_age, max_age;
+    // the same constants in the base-2 form the Monte Carlo loop uses (gal_prior2): multiplied out on the host, in
+    // float64, instead of once per pair of draws
+    T l2_iR_thin, l2_iZ_thin, l2_iR_thick, l2_iZ_thick;   // -log2(e) x inverse scale lengths
+    T l2_ln_f_thick, l2_irq, l2_halo, nh_eta;             // log2(e) ln f_thick; -log2(e) / r_q; log2(e) (eta ln Reff_sun + ln f_halo); -eta / 2
 };
 // heliocentric -> galactocentric, linear in the distance d: x = d ax + x0, y = d ay, z = d az + z0
 template <typename T> struct GalStar { T ax, ay, az, x0, z0; };
@@ -392,24 +396,24 @@ template <typename T> struct McCtx {
 // parts, prior = arg * 2^lg2h: the accumulation over draws needs 2^(lg2 prior - reference) = arg * 2^(lg2h - reference),
 // one exponential and no logarithm.
 // T = double runs the same code on plain pairs.
-template <typename T>
+// SAME: Rs_thin == Rs_thick known at compile time (the defaults): as a run-time select the second pair of square roots
+// is predicated off but still issued.
+template <typename T, bool SAME = false>
 __device__ __forceinline__ void gal_prior2(const GalDev<T>& G, const GalStar<T>& gs, const ModelW<T>& w, P2<T> s, P2<T> d,
                                            P2<T>& lg2h, P2<T>& arg) {
     const P2<T> x = fma2(d, bc2(gs.ax), bc2(gs.x0)), y = mul2(d, bc2(gs.ay)), z = fma2(d, bc2(gs.az), bc2(gs.z0));
     const P2<T> R2 = fma2(x, x, mul2(y, y));
     const P2<T> dz = sub2(abs2(z), bc2(G.aZ_solar));
     const P2<T> Rthin = sqrt2(add2(R2, bc2(G.Rs_thin2)));
-    const P2<T> Rthick = G.same_rs ? Rthin : sqrt2(add2(R2, bc2(G.Rs_thick2)));
+    const P2<T> Rthick = (SAME || G.same_rs) ? Rthin : sqrt2(add2(R2, bc2(G.Rs_thick2)));
     // log2 of the disk densities relative to the solar neighbourhood
-    const P2<T> lt = fma2(sub2(Rthin, bc2(G.R_solar)), bc2(T(-kLog2e) * G.iR_thin), mul2(dz, bc2(T(-kLog2e) * G.iZ_thin)));
-    const P2<T> lk = fma2(sub2(Rthick, bc2(G.R_solar)), bc2(T(-kLog2e) * G.iR_thick),
-                          fma2(dz, bc2(T(-kLog2e) * G.iZ_thick), bc2(T(kLog2e) * G.ln_f_thick)));
+    const P2<T> lt = fma2(sub2(Rthin, bc2(G.R_solar)), bc2(G.l2_iR_thin), mul2(dz, bc2(G.l2_iZ_thin)));
+    const P2<T> lk = fma2(sub2(Rthick, bc2(G.R_solar)), bc2(G.l2_iR_thick), fma2(dz, bc2(G.l2_iZ_thick), bc2(G.l2_ln_f_thick)));
     const P2<T> rp = sqrt2(add2(fma2(z, z, R2), bc2(G.rq2)));
-    const P2<T> q = fma2(ex22(fma2(rp, bc2(T(-kLog2e) * G.irq), bc2(T(kLog2e)))), bc2(-G.dq), bc2(G.q_inf));
+    const P2<T> q = fma2(ex22(fma2(rp, bc2(G.l2_irq), bc2(T(kLog2e)))), bc2(-G.dq), bc2(G.q_inf));
     const P2<T> zq = mul2(z, rcp2(q));
     // log2 of the halo density: -eta/2 log2(Reff^2) + eta log2(Reff_solar) + log2 f_halo
-    const P2<T> lh = fma2(lg22(add2(fma2(zq, zq, R2), bc2(G.Rs_halo2))), bc2(T(-0.5) * G.eta),
-                          bc2(T(kLog2e) * (G.eta * G.ln_Reff_solar + G.ln_f_halo)));
+    const P2<T> lh = fma2(lg22(add2(fma2(zq, zq, R2), bc2(G.Rs_halo2))), bc2(G.nh_eta), bc2(G.l2_halo));
     const P2<T> nt = ex22(sub2(lt, lh)), nk = ex22(sub2(lk, lh));
     const P2<T> s0 = add2(add2(nt, nk), bc2(T(1)));
     const P2<T> s1 = fma2(nt, bc2(w.f[0]), fma2(nk, bc2(w.f[1]), bc2(w.f[2])));
@@ -432,7 +436,7 @@ template <typename T> struct McPair {
     }
 };
 
-template <typename T, bool ZOV>
+template <typename T, bool ZOV, bool SAME = false>
 __device__ __forceinline__ void mc_pair(const PostParams<T>& p, const McCtx<T>& c, int j, McPair<T>& o) {
     T za[3], zb[3];
     if (ZOV) {
@@ -456,7 +460,7 @@ __device__ __forceinline__ void mc_pair(const PostParams<T>& p, const McCtx<T>& 
     const P2<T> dist = rsqrt2(sc), par = mul2(sc, dist);
     P2<T> lp = bc2(T(0));
     o.arg = bc2(T(1));
-    if (p.G.use) gal_prior2<T>(p.G, c.gs, c.w, sc, dist, lp, o.arg);
+    if (p.G.use) gal_prior2<T, SAME>(p.G, c.gs, c.w, sc, dist, lp, o.arg);
     if (c.pivar > T(0)) {
         const P2<T> d = sub2(par, bc2(c.par));
         lp = fma2(mul2(d, d), bc2(c.par_c2), add2(lp, bc2(c.par_k2)));
@@ -500,7 +504,7 @@ template <typename T> struct Lse {
 };
 
 // (:1038-1106) one thread per model of the second selection.  ZOV: normals supplied by the host (test mode)
-template <typename T, bool ZOV> __global__ void __launch_bounds__(kTile, 4) k_post_mc(const PostParams<T> p) {
+template <typename T, bool ZOV, bool SAME> __global__ void __launch_bounds__(kTile, 4) k_post_mc(const PostParams<T> p) {
     const int64_t u = (int64_t)blockIdx.x * kTile + threadIdx.x;
     const bool in = u < p.n2;
     int slot = -1;
@@ -518,7 +522,7 @@ template <typename T, bool ZOV> __global__ void __launch_bounds__(kTile, 4) k_po
         {
             const P2<T> s0 = bc2(c.scale), d0 = rsqrt2(s0);
             P2<T> l0 = bc2(T(0)), a0 = bc2(T(1));
-            if (p.G.use) gal_prior2<T>(p.G, c.gs, c.w, s0, d0, l0, a0);
+            if (p.G.use) gal_prior2<T, SAME>(p.G, c.gs, c.w, s0, d0, l0, a0);
             if (c.pivar > T(0)) {
                 const P2<T> d = sub2(mul2(s0, d0), bc2(c.par));
                 l0 = fma2(mul2(d, d), bc2(c.par_c2), add2(l0, bc2(c.par_k2)));
@@ -530,7 +534,7 @@ template <typename T, bool ZOV> __global__ void __launch_bounds__(kTile, 4) k_po
         int neff = 0;
         for (int j = 0; j < p.nmc; j += 2) {
             McPair<T> m;
-            mc_pair<T, ZOV>(p, c, j, m);
+            mc_pair<T, ZOV, SAME>(p, c, j, m);
             const P2<T> e = mul2(m.arg, ex22(sub2(m.lg2h, bc2(ref2))));
             const bool in1 = m.inb[1] && j + 1 < p.nmc;
             // max(NaN, 0) = 0: a NaN prior counts as exp(-inf) like in the reference (:1095)
@@ -546,7 +550,7 @@ template <typename T, bool ZOV> __global__ void __launch_bounds__(kTile, 4) k_po
             Lse<T> acc;
             for (int j = 0; j < p.nmc; j += 2) {
                 McPair<T> m;
-                mc_pair<T, ZOV>(p, c, j, m);
+                mc_pair<T, ZOV, SAME>(p, c, j, m);
                 acc.add(m.lnp(0));
                 if (j + 1 < p.nmc) acc.add(m.lnp(1));
             }
