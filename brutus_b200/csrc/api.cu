@@ -1981,7 +1981,7 @@ template <typename T> struct Engine : EngineBase {
                 const unsigned nb1 = (unsigned)((n1 + kTile - 1) / kTile);
                 { TRACE("k_post_write"); k_post_write<T><<<nb1, kTile, 0, stream>>>(pp); }
                 if (pp.zov) { TRACE("k_post_mc"); k_post_mc<T, true, false><<<(unsigned)((n2 + kTile - 1) / kTile), kTile, 0, stream>>>(pp); }
-                else if (G.same_rs) { TRACE("k_post_mc"); k_post_mc<T, false, true><<<(unsigned)((n2 + kTile - 1) / kTile), kTile, 0, stream>>>(pp); }
+                else if (G.same_rs && G.use) { TRACE("k_post_mc"); k_post_mc<T, false, true><<<(unsigned)((n2 + kTile - 1) / kTile), kTile, 0, stream>>>(pp); }
                 else { TRACE("k_post_mc"); k_post_mc<T, false, false><<<(unsigned)((n2 + kTile - 1) / kTile), kTile, 0, stream>>>(pp); }
                 stats.kernel_launches += 2;
             }

@@ -396,8 +396,9 @@ template <typename T> struct McCtx {
 // parts, prior = arg * 2^lg2h: the accumulation over draws needs 2^(lg2 prior - reference) = arg * 2^(lg2h - reference),
 // one exponential and no logarithm.
 // T = double runs the same code on plain pairs.
-// SAME: Rs_thin == Rs_thick known at compile time (the defaults): as a run-time select the second pair of square roots
-// is predicated off but still issued.
+// SAME: the production configuration known at compile time -- the Galactic prior in use with Rs_thin == Rs_thick (the
+// defaults).  As run-time tests the second pair of square roots is predicated off but still issued, and the branch
+// around the prior costs its not-taken initialisations and splits the schedule of the loop.
 template <typename T, bool SAME = false>
 __device__ __forceinline__ void gal_prior2(const GalDev<T>& G, const GalStar<T>& gs, const ModelW<T>& w, P2<T> s, P2<T> d,
                                            P2<T>& lg2h, P2<T>& arg) {
@@ -460,7 +461,7 @@ __device__ __forceinline__ void mc_pair(const PostParams<T>& p, const McCtx<T>& 
     const P2<T> dist = rsqrt2(sc), par = mul2(sc, dist);
     P2<T> lp = bc2(T(0));
     o.arg = bc2(T(1));
-    if (p.G.use) gal_prior2<T, SAME>(p.G, c.gs, c.w, sc, dist, lp, o.arg);
+    if (SAME || p.G.use) gal_prior2<T, SAME>(p.G, c.gs, c.w, sc, dist, lp, o.arg);
     if (c.pivar > T(0)) {
         const P2<T> d = sub2(par, bc2(c.par));
         lp = fma2(mul2(d, d), bc2(c.par_c2), add2(lp, bc2(c.par_k2)));
@@ -522,7 +523,7 @@ template <typename T, bool ZOV, bool SAME> __global__ void __launch_bounds__(kTi
         {
             const P2<T> s0 = bc2(c.scale), d0 = rsqrt2(s0);
             P2<T> l0 = bc2(T(0)), a0 = bc2(T(1));
-            if (p.G.use) gal_prior2<T, SAME>(p.G, c.gs, c.w, s0, d0, l0, a0);
+            if (SAME || p.G.use) gal_prior2<T, SAME>(p.G, c.gs, c.w, s0, d0, l0, a0);
             if (c.pivar > T(0)) {
                 const P2<T> d = sub2(mul2(s0, d0), bc2(c.par));
                 l0 = fma2(mul2(d, d), bc2(c.par_c2), add2(l0, bc2(c.par_k2)));
