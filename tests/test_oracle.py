@@ -77,3 +77,31 @@ def test_live_reference(oracle_mod):
                                              st["parallax_err"][i])
         assert np.array_equal(sel, sel_o)
         assert gc.rel_err(lnprob, lp) < TOL
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
+def test_live_reference_av_rv_init(oracle_mod):
+    """Caller-supplied per-model start of the magnitude fit (brutus/fitting.py:583, :700-703), including the
+    reference's in-place update of the caller's arrays (:202, :232, :809)."""
+    from brutus_b200 import mock
+    fit = ref_import.import_reference()
+    grid, labels = mock.make_grid(3000, 6, seed=41, kind="locus")
+    st = mock.make_stars(grid, 3, seed=42, dropout=0.1)
+    gF = np.array(grid, order="F")
+    rs = np.random.RandomState(43)
+    a0, r0 = rs.uniform(0., 2.5, grid.shape[0]), rs.uniform(2.7, 4.1, grid.shape[0])
+    for i in range(3):
+        pk = dict(parallax=st["parallax"][i], parallax_err=st["parallax_err"][i])
+        for kw in (dict(av_init=a0, rv_init=r0), dict(rv_init=r0), dict(av_init=a0, av_gauss=(0.5, 1.5))):
+            kr = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in kw.items()}
+            ko = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in kw.items()}
+            ref = fit.loglike(st["flux"][i], st["err"][i], st["mask"][i].copy(), gF, return_vals=True, **pk, **kr)
+            ref = tuple(np.array(x) for x in ref)
+            out = oracle_mod.loglike(st["flux"][i], st["err"][i], st["mask"][i].copy(), grid, return_vals=True, **pk, **ko)
+            for key, a, b in zip(gc.KEYS, out, ref):
+                if key != "ndim":
+                    assert gc.rel_err(a, b) < TOL, (i, sorted(kw), key)
+            for k, pos in (("av_init", 4), ("rv_init", 5)):   # the reference returns the caller's arrays as av / rv
+                if k in kr:
+                    assert np.array_equal(kr[k], ref[pos])
