@@ -148,3 +148,16 @@ def test_default_prior_is_ps1_lf_without_mini(bf_case):            # brutus/fitt
                     lngalprior=gc.toy_galprior, data_coords=np.zeros((4, 2)), apply_agewt=False, apply_grad=False)
     from brutus_b200 import pdf
     assert np.allclose(out[5], pdf.ps1_MrLF_lnprior(bf.models_labels["Mr"]))
+
+
+def test_two_launch_sweep_tile_partition():
+    """The sweep is issued in two launches: the model tiles that are multiples of S, then the
+    others, enumerated as j -> j + j // (S - 1) + 1 (csrc/kernels_nb.cuh, k_sweep; csrc/api.cu, process_group).
+    Restated here: together they visit every tile exactly once, for the S the host derives from the tile count."""
+    for ntile in (1024, 1025, 1031, 3907, 4096, 11719, 40000):
+        S = min(32, max(2, ntile // 128))
+        nsub = (ntile + S - 1) // S
+        first = [j * S for j in range(nsub)]
+        rest = [j + j // (S - 1) + 1 for j in range(ntile - nsub)]
+        assert sorted(first + rest) == list(range(ntile)), (ntile, S)
+        assert len(first) >= 128 and all(t % S for t in rest)
