@@ -466,7 +466,9 @@ def run_b200(args):
                              "bytes / the whole device step (sweep + cull + flux continuation + selection + ordered "
                              "records).  32 stars reuse a grid tile held in registers and shared memory, so the DRAM "
                              "traffic (`traffic`, ncu, per launch) is far below the algorithmic bytes: the kernel is "
-                             "bound by FP32 issue / the FMA pipe (`issue`), DESIGN.md section 5",
+                             "bound by FP32 issue / the FMA pipe (`issue`; ncu: issue active 70 %, FMA pipe 58 %, 24 warps "
+                             "per SM), DESIGN.md section 5.  A sweep round is two launches (a strided subsample of the "
+                             "model tiles, then the rest): `launches` counts both",
                      "issue": issue,
                      "algorithmic_flop_instr": algo_flop,
                      "kernel_share_of_step": agg["ms_magfit"] / agg["ms_device"],
